@@ -1,0 +1,400 @@
+// bnb.cu -- the inner R^3 translation branch-and-bound as a GPU-resident best-first search, and
+// the per-level driver of the outer SO(3) search.
+//
+// Replaces FastGoICP::branch_and_bound_R3 of the reference (fgoicp/fgoicp.cpp:102-174), where a
+// host std::priority_queue pops <= 32 translation cubes, crosses to the device for their bounds
+// (2 cudaMalloc + <= 32 launches + <= 64 blocking reductions + 2 cudaFree per batch) and comes back
+// to prune and spawn children.  Here one thread block owns one rotation cube's whole search:
+//   - the open list ("pool") lives in shared memory as 64-bit keys
+//         [ lb bits : 32 | level : 3 | insertion seq : 13 | iz : 4 | iy : 4 | ix : 4 ]
+//     so a plain unsigned sort yields the reference's heap order (smaller lb first, ties -> larger
+//     span first; common.hpp:120-127) made total by the insertion sequence number;
+//   - every iteration: bitonic sort + compaction of the pool, the reference's stop test, pop of
+//     <= 32 cubes, bound evaluation with the same fused evaluator as bounds.cu, update of
+//     best_ub / best_error / best_t, pruning, and spawning of 8 children per surviving cube;
+//   - nothing returns to the host until the search is over; many rotation cubes run concurrently
+//     (one block each), which is where the parallelism of a whole outer level comes from.
+// Cube centres are dyadic ( -1 + (2i+1) 2^-level ), so integer coordinates reproduce the reference's
+// float arithmetic (t - span/2 + bit*span, fgoicp.cpp:159-163) exactly.
+#include "common.cuh"
+#include "bounds_eval.cuh"
+
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#define BNB_POOL       8192            // >= 1 + 8 + 64 + 512 + 4096 = 4681 nodes ever pushed
+#define BNB_BATCH_MAX  32              // fgoicp.cpp:122
+#define BNB_MIN_TSPAN  0.1f            // fgoicp.cpp:155
+#define BNB_KEY_MAX    0xffffffffffffffffull
+
+struct BnbOut
+{
+    float best_ub;
+    float best_t[3];
+    unsigned long long evals;
+    unsigned int batches;
+    unsigned int pushed;
+};
+
+__device__ __forceinline__ unsigned long long bnb_key(float lb, unsigned level, unsigned seq, unsigned ix, unsigned iy, unsigned iz)
+{
+    unsigned lo = (level << 25) | (seq << 12) | (iz << 8) | (iy << 4) | ix;
+    return ((unsigned long long)__float_as_uint(lb) << 32) | lo;
+}
+
+template <int SAMPLER, int NWARPS>
+__global__ void __launch_bounds__(NWARPS * 32)
+k_bnb_r3(LutDev L, const float4* __restrict__ data, int ns, const float4* __restrict__ rot, int fix_rot,
+         float best_sse, float sse_threshold, int batch_max, BnbOut* __restrict__ out)
+{
+    extern __shared__ unsigned long long pool[];          // BNB_POOL keys
+    __shared__ float sR[9];
+    __shared__ float s_sin;
+    __shared__ float4 s_tc[BNB_BATCH_MAX];
+    __shared__ unsigned long long s_bkey[BNB_BATCH_MAX];
+    __shared__ double s_part[NWARPS][BD_CPW][2];
+    __shared__ float s_lb[BNB_BATCH_MAX], s_ub[BNB_BATCH_MAX];
+    __shared__ int s_n, s_m, s_nb, s_stop;
+    __shared__ float s_best_error, s_best_ub, s_best_t[3];
+    __shared__ unsigned int s_seq, s_batches;
+    __shared__ unsigned long long s_evals;
+
+    const int NT = NWARPS * 32;
+    const int tid = threadIdx.x;
+    const int r = blockIdx.x;
+
+    if (tid == 0)
+    {
+        float4 rc = rot[r];
+        float Rm[9];
+        fg_rotation_matrix(rc.x, rc.y, rc.z, Rm);
+        for (int k = 0; k < 9; ++k) sR[k] = Rm[k];
+        s_sin = fix_rot ? 0.0f : fg_rot_sin(rc.w);
+        pool[0] = bnb_key(0.0f, 0, 0, 0, 0, 0);          // root: t = 0, span = 1, lb = 0 (fgoicp.cpp:113)
+        s_n = 1; s_seq = 1;
+        s_best_error = best_sse;                          // fgoicp.cpp:104
+        s_best_ub = FG_INF;                               // fgoicp.cpp:106
+        s_best_t[0] = s_best_t[1] = s_best_t[2] = 0.0f;   // fgoicp.cpp:105
+        s_evals = 0; s_batches = 0; s_stop = 0;
+    }
+    __syncthreads();
+
+    while (true)
+    {
+        // ---- (a) sort the pool ascending; dead entries (KEY_MAX) sink to the end
+        const int n = s_n;
+        int P = 32; while (P < n) P <<= 1;
+        for (int i = n + tid; i < P; i += NT) pool[i] = BNB_KEY_MAX;
+        __syncthreads();
+        for (int k = 2; k <= P; k <<= 1)
+            for (int j = k >> 1; j > 0; j >>= 1)
+            {
+                for (int i = tid; i < P; i += NT)
+                {
+                    int ixj = i ^ j;
+                    if (ixj > i)
+                    {
+                        unsigned long long a = pool[i], b = pool[ixj];
+                        bool up = ((i & k) == 0);
+                        if ((a > b) == up) { pool[i] = b; pool[ixj] = a; }
+                    }
+                }
+                __syncthreads();
+            }
+        // ---- (b) live count m = index of the first dead entry
+        if (tid == 0) s_m = (pool[P - 1] != BNB_KEY_MAX) ? P : -1;
+        __syncthreads();
+        for (int i = tid; i < P; i += NT)
+        {
+            bool live = pool[i] != BNB_KEY_MAX;
+            bool prev_live = (i == 0) ? true : (pool[i - 1] != BNB_KEY_MAX);
+            if (!live && prev_live) s_m = i;              // exactly one thread at most
+        }
+        __syncthreads();
+        // ---- (c) stop test and (d) batch pop
+        if (tid == 0)
+        {
+            int m = s_m;
+            int stop = 0, nb = 0;
+            if (m <= 0) stop = 1;
+            else
+            {
+                float top_lb = __uint_as_float((unsigned)(pool[0] >> 32));
+                if (__fsub_rn(s_best_error, top_lb) < sse_threshold) stop = 1;      // fgoicp.cpp:120
+                else nb = min(m, batch_max);
+            }
+            s_stop = stop; s_nb = nb;
+        }
+        __syncthreads();
+        if (s_stop) break;
+        const int m = s_m, nb = s_nb;
+        if (tid < nb)
+        {
+            unsigned long long key = pool[tid];
+            s_bkey[tid] = key;
+            unsigned lo = (unsigned)key;
+            unsigned level = (lo >> 25) & 7u, ix = lo & 15u, iy = (lo >> 4) & 15u, iz = (lo >> 8) & 15u;
+            float span = __uint_as_float((127u - level) << 23);                  // 2^-level
+            float4 t;
+            t.x = __fmaf_rn((float)(2 * ix + 1), span, -1.0f);                   // exact: dyadic
+            t.y = __fmaf_rn((float)(2 * iy + 1), span, -1.0f);
+            t.z = __fmaf_rn((float)(2 * iz + 1), span, -1.0f);
+            t.w = span;
+            s_tc[tid] = t;
+            pool[tid] = BNB_KEY_MAX;                                             // popped
+        }
+        __syncthreads();
+
+        // ---- (e) bounds of the batch (registration.cu:88-152 fused)
+        fg_eval_chunk<SAMPLER, NWARPS>(L, data, 0, ns, sR, s_sin, fix_rot != 0, s_tc, nb, s_part);
+        __syncthreads();
+        if (tid < nb)
+        {
+            double su, sl;
+            fg_eval_gather<NWARPS>(s_part, nb, tid, su, sl);
+            s_ub[tid] = (float)su; s_lb[tid] = (float)sl;
+        }
+        __syncthreads();
+
+        // ---- (f) best of the batch (fgoicp.cpp:139-145): first minimum in pop order
+        if (tid == 0)
+        {
+            int idx_min = 0;
+            for (int i = 1; i < nb; ++i) if (s_ub[i] < s_ub[idx_min]) idx_min = i;
+            float u = s_ub[idx_min];
+            s_best_ub = s_best_ub < u ? s_best_ub : u;
+            if (u < s_best_error)
+            {
+                s_best_error = u;
+                s_best_t[0] = s_tc[idx_min].x; s_best_t[1] = s_tc[idx_min].y; s_best_t[2] = s_tc[idx_min].z;
+            }
+            s_evals += (unsigned long long)nb * (unsigned long long)ns;           // fgoicp.cpp:132 (x ns)
+            s_batches += 1;
+        }
+        __syncthreads();
+
+        // ---- (g) spawn children of surviving cubes (fgoicp.cpp:148-169), in pop order
+        const float best_error = s_best_error;
+        if (tid < 32)
+        {
+            bool spawn = false;
+            if (tid < nb)
+            {
+                float lbv = s_lb[tid];
+                float span = s_tc[tid].w;
+                spawn = !(lbv >= best_error) && !(span < BNB_MIN_TSPAN);
+            }
+            unsigned mask = __ballot_sync(0xffffffffu, spawn);
+            int before = __popc(mask & ((1u << tid) - 1u));
+            int total = __popc(mask);
+            if (spawn)
+            {
+                unsigned lo = (unsigned)s_bkey[tid];
+                unsigned level = (lo >> 25) & 7u, ix = lo & 15u, iy = (lo >> 4) & 15u, iz = (lo >> 8) & 15u;
+                unsigned seq0 = s_seq + 8u * before;
+                int base = m + 8 * before;
+                float lbv = s_lb[tid];
+#pragma unroll
+                for (unsigned k = 0; k < 8; ++k)
+                    pool[base + k] = bnb_key(lbv, level + 1, seq0 + k, 2 * ix + (k & 1u), 2 * iy + ((k >> 1) & 1u), 2 * iz + ((k >> 2) & 1u));
+            }
+            __syncwarp();
+            if (tid == 0) { s_n = m + 8 * total; s_seq += 8u * total; }
+        }
+        __syncthreads();
+
+        // ---- (h) prune everything that can no longer be popped (lb >= best_error, fgoicp.cpp:126)
+        const unsigned be_bits = __float_as_uint(best_error);
+        const int n_new = s_n;
+        for (int i = tid; i < n_new; i += NT)
+        {
+            unsigned long long key = pool[i];
+            if (key != BNB_KEY_MAX && (unsigned)(key >> 32) >= be_bits) pool[i] = BNB_KEY_MAX;
+        }
+        __syncthreads();
+    }
+
+    if (tid == 0)
+    {
+        BnbOut o;
+        o.best_ub = s_best_ub;
+        o.best_t[0] = s_best_t[0]; o.best_t[1] = s_best_t[1]; o.best_t[2] = s_best_t[2];
+        o.evals = s_evals; o.batches = s_batches; o.pushed = s_seq;
+        out[r] = o;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+
+template <int SAMPLER, int NWARPS>
+static int launch_bnb_t(fgoicp_ctx* c, const float4* d_rot, int Rn, int fix_rot, float best_sse, float thr, BnbOut* d_out)
+{
+    size_t smem = sizeof(unsigned long long) * BNB_POOL;
+    FG_CUDA(cudaFuncSetAttribute(k_bnb_r3<SAMPLER, NWARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_bnb_r3<SAMPLER, NWARPS><<<Rn, NWARPS * 32, smem, c->stream>>>(c->lut, c->d_data, (int)c->ns, d_rot, fix_rot,
+                                                                 best_sse, thr, BNB_BATCH_MAX, d_out);
+    FG_CUDA(cudaGetLastError());
+    return FGOICP_OK;
+}
+
+template <int NWARPS>
+static int launch_bnb_w(fgoicp_ctx* c, const float4* d_rot, int Rn, int fix_rot, float best_sse, float thr, BnbOut* d_out)
+{
+    switch (c->sampler)
+    {
+    case FGOICP_SAMPLER_PACKED: return launch_bnb_t<FGOICP_SAMPLER_PACKED, NWARPS>(c, d_rot, Rn, fix_rot, best_sse, thr, d_out);
+    case FGOICP_SAMPLER_TEX:    return launch_bnb_t<FGOICP_SAMPLER_TEX, NWARPS>(c, d_rot, Rn, fix_rot, best_sse, thr, d_out);
+    default:                    return launch_bnb_t<FGOICP_SAMPLER_GRID, NWARPS>(c, d_rot, Rn, fix_rot, best_sse, thr, d_out);
+    }
+}
+
+// Few rotation cubes: big blocks (latency).  Many: smaller blocks, several per SM (throughput).
+static int launch_bnb(fgoicp_ctx* c, const float4* d_rot, int Rn, int fix_rot, float best_sse, float thr, BnbOut* d_out)
+{
+    if (Rn >= 3 * c->sm_count) return launch_bnb_w<8>(c, d_rot, Rn, fix_rot, best_sse, thr, d_out);
+    return launch_bnb_w<16>(c, d_rot, Rn, fix_rot, best_sse, thr, d_out);
+}
+
+static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+// host cubes -> device, run Rn searches, results to host vector
+static int bnb_batch_host(fgoicp_ctx* c, const float* rot_xyz_span, int Rn, int fix_rot, float best_sse,
+                          float sse_threshold, std::vector<BnbOut>& res, float* ms)
+{
+    size_t b_rot = align256(sizeof(float4) * Rn), b_out = align256(sizeof(BnbOut) * Rn);
+    int rc = fg::ensure_scratch(c, b_rot + b_out);
+    if (rc) return rc;
+    rc = fg::ensure_pinned(c, b_rot + b_out);
+    if (rc) return rc;
+    char* hp = (char*)c->h_pinned;
+    char* dp = (char*)c->d_scratch;
+    memcpy(hp, rot_xyz_span, sizeof(float4) * Rn);
+    FG_CUDA(cudaMemcpyAsync(dp, hp, sizeof(float4) * Rn, cudaMemcpyHostToDevice, c->stream));
+    FG_CUDA(cudaEventRecord(c->ev0, c->stream));
+    rc = launch_bnb(c, (const float4*)dp, Rn, fix_rot, best_sse, sse_threshold, (BnbOut*)(dp + b_rot));
+    if (rc) return rc;
+    FG_CUDA(cudaEventRecord(c->ev1, c->stream));
+    FG_CUDA(cudaMemcpyAsync(hp + b_rot, dp + b_rot, sizeof(BnbOut) * Rn, cudaMemcpyDeviceToHost, c->stream));
+    FG_CUDA(cudaStreamSynchronize(c->stream));
+    res.resize(Rn);
+    memcpy(res.data(), hp + b_rot, sizeof(BnbOut) * Rn);
+    if (ms) FG_CUDA(cudaEventElapsedTime(ms, c->ev0, c->ev1));
+    return FGOICP_OK;
+}
+
+extern "C" int fgoicp_bnb_r3_batch(fgoicp_ctx* c, const float* rot_xyz_span, int Rn, int fix_rot,
+                                   float best_sse, float sse_threshold,
+                                   float* best_ub, float* best_t, uint64_t* evals)
+{
+    FG_ARG(c && rot_xyz_span && best_ub, "NULL pointer");
+    FG_ARG(Rn > 0, "Rn must be positive");
+    FG_CUDA(cudaSetDevice(c->device));
+    std::vector<BnbOut> res;
+    int rc = bnb_batch_host(c, rot_xyz_span, Rn, fix_rot, best_sse, sse_threshold, res, nullptr);
+    if (rc) return rc;
+    for (int i = 0; i < Rn; ++i)
+    {
+        best_ub[i] = res[i].best_ub;
+        if (best_t) { best_t[3 * i] = res[i].best_t[0]; best_t[3 * i + 1] = res[i].best_t[1]; best_t[3 * i + 2] = res[i].best_t[2]; }
+        if (evals) evals[i] = res[i].evals;
+    }
+    return FGOICP_OK;
+}
+
+extern "C" int fgoicp_bnb_r3(fgoicp_ctx* c, const float rot_xyz_span[4], int fix_rot,
+                             float best_sse, float sse_threshold,
+                             float* best_ub, float best_t[3], uint64_t* evals)
+{
+    return fgoicp_bnb_r3_batch(c, rot_xyz_span, 1, fix_rot, best_sse, sse_threshold, best_ub, best_t, evals);
+}
+
+int fg_icp_run(fgoicp_ctx* c, const float R0[9], const float t0[3], int max_iter, float thr,
+               float* sse, float R[9], float t[3], int* iters);
+
+// Rotation(x, y, z) on the host: same unfused fp32 arithmetic as the reference (common.hpp:37-57)
+static void host_rotation(float x, float y, float z, float* R)
+{
+    float r = x * x + y * y + z * z;
+    for (int i = 0; i < 9; ++i) R[i] = (i % 4 == 0) ? 1.0f : 0.0f;
+    if (r > 1.0f) return;
+    float ww = 1.0f - r, w = sqrtf(ww);
+    float wx = w * x, xx = x * x, wy = w * y, xy = x * y, yy = y * y, wz = w * z, xz = x * z, yz = y * z, zz = z * z;
+    R[0] = ww + xx - yy - zz; R[1] = 2 * (xy - wz);     R[2] = 2 * (xz + wy);
+    R[3] = 2 * (xy + wz);     R[4] = ww - xx + yy - zz; R[5] = 2 * (yz - wx);
+    R[6] = 2 * (xz - wy);     R[7] = 2 * (yz + wx);     R[8] = ww - xx - yy + zz;
+}
+
+extern "C" int fgoicp_so3_level_ub(fgoicp_ctx* c, const float* cubes, int n,
+                                   float best_sse, float sse_threshold,
+                                   float* ub, float* bt,
+                                   float* io_best_sse, float io_best_R[9], float io_best_t[3],
+                                   fgoicp_level_stats* stats)
+{
+    FG_ARG(c && io_best_sse && io_best_R && io_best_t, "NULL pointer");
+    FG_ARG(n >= 0, "n must be non-negative");
+    if (stats) { memset(stats, 0, sizeof(*stats)); stats->best_icp_index = -1; }
+    if (n == 0) return FGOICP_OK;
+    FG_ARG(cubes && ub && bt, "NULL pointer");
+    FG_CUDA(cudaSetDevice(c->device));
+    std::vector<BnbOut> res;
+    float ms = 0.f;
+    int rc = bnb_batch_host(c, cubes, n, 1, best_sse, sse_threshold, res, &ms);       // fgoicp.cpp:69
+    if (rc) return rc;
+    uint64_t evals = 0;
+    for (int i = 0; i < n; ++i)
+    {
+        ub[i] = res[i].best_ub;
+        bt[3 * i] = res[i].best_t[0]; bt[3 * i + 1] = res[i].best_t[1]; bt[3 * i + 2] = res[i].best_t[2];
+        evals += res[i].evals;
+    }
+    // ICP on promising cubes (fgoicp.cpp:74-88).  The trigger compares against the LEVEL-START
+    // best_sse so that the set of refined cubes does not depend on how the level was sharded.
+    uint32_t n_icp = 0, icp_iters = 0;
+    int best_idx = -1;
+    cudaEvent_t e0 = c->ev0, e1 = c->ev1;
+    FG_CUDA(cudaEventRecord(e0, c->stream));
+    for (int i = 0; i < n; ++i)
+    {
+        if (!((double)ub[i] < (double)best_sse * 1.8)) continue;
+        float R0[9], e, R[9], t[3];
+        int it = 0;
+        host_rotation(cubes[4 * i], cubes[4 * i + 1], cubes[4 * i + 2], R0);
+        rc = fg_icp_run(c, R0, bt + 3 * i, 100, (float)0.005, &e, R, t, &it);         // fgoicp.cpp:76
+        if (rc) return rc;
+        ++n_icp; icp_iters += (uint32_t)it;
+        if (e < *io_best_sse)                                                          // fgoicp.cpp:79-84
+        {
+            *io_best_sse = e;
+            best_idx = i;
+            memcpy(io_best_R, R, sizeof(float) * 9);
+            memcpy(io_best_t, t, sizeof(float) * 3);
+        }
+    }
+    FG_CUDA(cudaEventRecord(e1, c->stream));
+    FG_CUDA(cudaStreamSynchronize(c->stream));
+    float ms_icp = 0.f;
+    FG_CUDA(cudaEventElapsedTime(&ms_icp, e0, e1));
+    if (stats) { stats->evals = evals; stats->n_icp = n_icp; stats->icp_iters = icp_iters; stats->ms_bnb_ub = ms; stats->ms_icp = ms_icp; stats->best_icp_index = best_idx; }
+    return FGOICP_OK;
+}
+
+extern "C" int fgoicp_so3_level_lb(fgoicp_ctx* c, const float* cubes, int n,
+                                   float best_sse, float sse_threshold,
+                                   float* lb, fgoicp_level_stats* stats)
+{
+    FG_ARG(c, "NULL context");
+    FG_ARG(n >= 0, "n must be non-negative");
+    if (stats) memset(stats, 0, sizeof(*stats));
+    if (n == 0) return FGOICP_OK;
+    FG_ARG(cubes && lb, "NULL pointer");
+    FG_CUDA(cudaSetDevice(c->device));
+    std::vector<BnbOut> res;
+    float ms = 0.f;
+    int rc = bnb_batch_host(c, cubes, n, 0, best_sse, sse_threshold, res, &ms);       // fgoicp.cpp:90
+    if (rc) return rc;
+    uint64_t evals = 0;
+    for (int i = 0; i < n; ++i) { lb[i] = res[i].best_ub; evals += res[i].evals; }
+    if (stats) { stats->evals = evals; stats->ms_bnb_lb = ms; }
+    return FGOICP_OK;
+}

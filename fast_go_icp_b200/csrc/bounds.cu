@@ -1,0 +1,287 @@
+// bounds.cu -- fused batched upper/lower bound evaluation over
+// (rotation cube x translation cube x data point).
+//
+// Replaces Registration::compute_sse_error(rnode, tnodes, fix_rot, pool) of the reference
+// (fgoicp/registration.cu:88-152): there, every translation cube costs one 32-thread-block
+// launch of kernComputeBounds (registration.cu:27-60) writing 2 floats per point to scratch,
+// two blocking thrust::reduce calls, plus cudaMalloc/cudaFree per batch.  Here one launch
+// covers a whole list of (rotation cube, translation cube) pairs, the per-point terms are
+// reduced in registers -> warp shuffles -> shared memory and never touch HBM.
+//
+// Work decomposition (one thread block = one rotation cube x one slice of the data points):
+//   - the block stages up to 32 translation cubes at a time in shared memory;
+//   - warps are arranged as Wc cube-groups x Wp point-slices; a warp owns CPW=4 cubes and
+//     strides over its points with coalesced float4 loads (x, y, z, |p|^2), rotates each point
+//     once and evaluates its 4 cubes -> 4 independent 32-byte gathers in flight per lane;
+//   - per-cube sums are accumulated in fp64 (B200 has full-rate-enough FP64: 2 DADD per
+//     evaluation), reduced by butterfly shuffles, then across point-slices in a fixed order,
+//     so results are deterministic and independent of the launch geometry up to 1 ulp of fp64.
+#include "common.cuh"
+
+#include <algorithm>
+#include <vector>
+
+#include "bounds_eval.cuh"
+
+#define BD_THREADS 256
+#define BD_WARPS   (BD_THREADS / 32)
+
+template <int SAMPLER>
+__global__ void __launch_bounds__(BD_THREADS)
+k_bounds_multi(LutDev L, const float4* __restrict__ data, int ns,
+               const float4* __restrict__ rot, const float* __restrict__ Rmats, int fix_rot,
+               const float4* __restrict__ tcubes, int T, int S,
+               double* __restrict__ partial, float* __restrict__ lb, float* __restrict__ ub,
+               unsigned int* __restrict__ best_ub_bits)
+{
+    __shared__ float sR[9];
+    __shared__ float s_sin;
+    __shared__ float4 s_tc[BD_CHUNK];
+    __shared__ double s_part[BD_WARPS][BD_CPW][2];
+
+    const int r = blockIdx.x / S;
+    const int slice = blockIdx.x - r * S;
+    if (threadIdx.x == 0)
+    {
+        float4 rc = rot[r];
+        if (Rmats)
+        {
+            for (int k = 0; k < 9; ++k) sR[k] = Rmats[9 * r + k];
+        }
+        else
+        {
+            float Rm[9];
+            fg_rotation_matrix(rc.x, rc.y, rc.z, Rm);      // R = I outside the ball (common.hpp:41)
+            for (int k = 0; k < 9; ++k) sR[k] = Rm[k];
+        }
+        s_sin = fix_rot ? 0.0f : fg_rot_sin(rc.w);
+    }
+
+    // this block's slice of the data points
+    const int per = (ns + S - 1) / S;
+    const int p0 = slice * per;
+    const int p1 = min(ns, p0 + per);
+
+    for (int c0 = 0; c0 < T; c0 += BD_CHUNK)
+    {
+        const int nch = min(BD_CHUNK, T - c0);
+        __syncthreads();
+        if (threadIdx.x < nch) s_tc[threadIdx.x] = tcubes[(size_t)r * T + c0 + threadIdx.x];
+        __syncthreads();
+
+        fg_eval_chunk<SAMPLER, BD_WARPS>(L, data, p0, p1, sR, s_sin, fix_rot != 0, s_tc, nch, s_part);
+        __syncthreads();
+        if (threadIdx.x < nch)
+        {
+            int c = threadIdx.x;
+            double su, sl;
+            fg_eval_gather<BD_WARPS>(s_part, nch, c, su, sl);
+            size_t o = (size_t)r * T + c0 + c;
+            if (S == 1)
+            {
+                float fu = (float)su, fl = (float)sl;
+                ub[o] = fu; lb[o] = fl;
+                if (best_ub_bits) atomicMin(best_ub_bits, __float_as_uint(fu));   // fu >= 0: bit order = value order
+            }
+            else
+            {
+                partial[(o * S + slice) * 2 + 0] = su;
+                partial[(o * S + slice) * 2 + 1] = sl;
+            }
+        }
+    }
+}
+
+__global__ void k_bounds_finish(const double* __restrict__ partial, int n, int S,
+                                float* __restrict__ lb, float* __restrict__ ub,
+                                unsigned int* __restrict__ best_ub_bits)
+{
+    int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= n) return;
+    double su = 0.0, sl = 0.0;
+    for (int s = 0; s < S; ++s) { su += partial[((size_t)o * S + s) * 2]; sl += partial[((size_t)o * S + s) * 2 + 1]; }
+    float fu = (float)su, fl = (float)sl;
+    ub[o] = fu; lb[o] = fl;
+    if (best_ub_bits) atomicMin(best_ub_bits, __float_as_uint(fu));
+}
+
+template <int SAMPLER>
+__global__ void k_lut_sample(LutDev L, const float* __restrict__ q, size_t n, float* __restrict__ out)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = fg_sample<SAMPLER>(L, q[3 * i], q[3 * i + 1], q[3 * i + 2]);
+}
+
+__global__ void k_rot_sin(const float* __restrict__ spans, int n, float* __restrict__ out)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = fg_rot_sin(spans[i]);
+}
+
+__global__ void k_set_u32(unsigned int* p, unsigned int v) { *p = v; }
+
+// ---------------------------------------------------------------------------------------------
+
+static int pick_slices(const fgoicp_ctx* c, int Rn)
+{
+    // enough blocks for ~4 per SM; at least 256 points per block
+    long long want = 4LL * c->sm_count;
+    int S = (int)std::max(1LL, (want + Rn - 1) / Rn);
+    int maxS = (int)std::max((size_t)1, c->ns / 256);
+    return std::min(S, maxS);
+}
+
+struct BoundsLaunch
+{
+    const float4* d_rot; const float* d_Rmats; int Rn; int fix_rot;
+    const float4* d_tc; int T; float* d_lb; float* d_ub; float* d_best_ub; double* d_partial; int S;
+};
+
+static int run_bounds(fgoicp_ctx* c, const BoundsLaunch& b)
+{
+    unsigned int* d_bits = (unsigned int*)b.d_best_ub;
+    if (d_bits) k_set_u32<<<1, 1, 0, c->stream>>>(d_bits, 0x7f800000u);
+    dim3 grid((unsigned)(b.Rn * b.S));
+#define FG_LAUNCH_BOUNDS(SMP)                                                                        \
+    k_bounds_multi<SMP><<<grid, BD_THREADS, 0, c->stream>>>(c->lut, c->d_data, (int)c->ns, b.d_rot,  \
+        b.d_Rmats, b.fix_rot, b.d_tc, b.T, b.S, b.d_partial, b.d_lb, b.d_ub, b.S == 1 ? d_bits : nullptr)
+    switch (c->sampler)
+    {
+    case FGOICP_SAMPLER_PACKED: FG_LAUNCH_BOUNDS(FGOICP_SAMPLER_PACKED); break;
+    case FGOICP_SAMPLER_TEX:    FG_LAUNCH_BOUNDS(FGOICP_SAMPLER_TEX); break;
+    default:                    FG_LAUNCH_BOUNDS(FGOICP_SAMPLER_GRID); break;
+    }
+#undef FG_LAUNCH_BOUNDS
+    FG_CUDA(cudaGetLastError());
+    if (b.S > 1)
+    {
+        int n = b.Rn * b.T;
+        k_bounds_finish<<<(n + 255) / 256, 256, 0, c->stream>>>(b.d_partial, n, b.S, b.d_lb, b.d_ub, d_bits);
+        FG_CUDA(cudaGetLastError());
+    }
+    return FGOICP_OK;
+}
+
+static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+// host-buffer path: stage through pinned memory, one H2D, one launch, one D2H
+static int bounds_host(fgoicp_ctx* c, const float* rot_xyz_span, const float* Rmats, int Rn, int fix_rot,
+                       const float* t_xyz_span, int T, float* lb, float* ub)
+{
+    FG_ARG(c && rot_xyz_span && t_xyz_span && lb && ub, "NULL pointer");
+    FG_ARG(Rn > 0 && T > 0, "Rn and T must be positive");
+    FG_CUDA(cudaSetDevice(c->device));
+    int S = pick_slices(c, Rn);
+    size_t n = (size_t)Rn * T;
+    size_t b_rot = align256(sizeof(float4) * Rn);
+    size_t b_R = align256(Rmats ? sizeof(float) * 9 * Rn : 0);
+    size_t b_tc = align256(sizeof(float4) * n);
+    size_t b_out = align256(sizeof(float) * n);
+    size_t b_part = S > 1 ? align256(sizeof(double) * 2 * n * S) : 0;
+    size_t in_bytes = b_rot + b_R + b_tc;
+    int rc = fg::ensure_scratch(c, in_bytes + 2 * b_out + b_part);
+    if (rc) return rc;
+    rc = fg::ensure_pinned(c, in_bytes + 2 * b_out);
+    if (rc) return rc;
+    char* hp = (char*)c->h_pinned;
+    char* dp = (char*)c->d_scratch;
+    memcpy(hp, rot_xyz_span, sizeof(float4) * Rn);
+    if (Rmats) memcpy(hp + b_rot, Rmats, sizeof(float) * 9 * Rn);
+    memcpy(hp + b_rot + b_R, t_xyz_span, sizeof(float4) * n);
+    FG_CUDA(cudaMemcpyAsync(dp, hp, in_bytes, cudaMemcpyHostToDevice, c->stream));
+    BoundsLaunch b;
+    b.d_rot = (const float4*)dp;
+    b.d_Rmats = Rmats ? (const float*)(dp + b_rot) : nullptr;
+    b.Rn = Rn; b.fix_rot = fix_rot;
+    b.d_tc = (const float4*)(dp + b_rot + b_R);
+    b.T = T;
+    b.d_lb = (float*)(dp + in_bytes);
+    b.d_ub = (float*)(dp + in_bytes + b_out);
+    b.d_best_ub = nullptr;
+    b.d_partial = S > 1 ? (double*)(dp + in_bytes + 2 * b_out) : nullptr;
+    b.S = S;
+    rc = run_bounds(c, b);
+    if (rc) return rc;
+    FG_CUDA(cudaMemcpyAsync(hp + in_bytes, dp + in_bytes, 2 * b_out, cudaMemcpyDeviceToHost, c->stream));
+    FG_CUDA(cudaStreamSynchronize(c->stream));
+    memcpy(lb, hp + in_bytes, sizeof(float) * n);
+    memcpy(ub, hp + in_bytes + b_out, sizeof(float) * n);
+    return FGOICP_OK;
+}
+
+extern "C" int fgoicp_bounds_batch(fgoicp_ctx* c, const float R[9], float rot_span, int fix_rot,
+                                   const float* t_xyz_span, int T, float* lb, float* ub)
+{
+    FG_ARG(R != nullptr, "R is NULL");
+    float rot[4] = { 0.f, 0.f, 0.f, rot_span };
+    return bounds_host(c, rot, R, 1, fix_rot, t_xyz_span, T, lb, ub);
+}
+
+extern "C" int fgoicp_bounds_multi(fgoicp_ctx* c, const float* rot_xyz_span, int Rn, int fix_rot,
+                                   const float* t_xyz_span, int T, float* lb, float* ub)
+{
+    return bounds_host(c, rot_xyz_span, nullptr, Rn, fix_rot, t_xyz_span, T, lb, ub);
+}
+
+extern "C" int fgoicp_bounds_multi_dev(fgoicp_ctx* c, const float* d_rot_xyz_span, int Rn, int fix_rot,
+                                       const float* d_t_xyz_span, int T, float* d_lb, float* d_ub,
+                                       float* d_best_ub)
+{
+    FG_ARG(c && d_rot_xyz_span && d_t_xyz_span && d_lb && d_ub, "NULL pointer");
+    FG_ARG(Rn > 0 && T > 0, "Rn and T must be positive");
+    FG_CUDA(cudaSetDevice(c->device));
+    int S = pick_slices(c, Rn);
+    BoundsLaunch b;
+    b.d_rot = (const float4*)d_rot_xyz_span; b.d_Rmats = nullptr; b.Rn = Rn; b.fix_rot = fix_rot;
+    b.d_tc = (const float4*)d_t_xyz_span; b.T = T; b.d_lb = d_lb; b.d_ub = d_ub; b.d_best_ub = d_best_ub;
+    b.d_partial = nullptr; b.S = S;
+    if (S > 1)
+    {
+        int rc = fg::ensure_scratch(c, sizeof(double) * 2 * (size_t)Rn * T * S);
+        if (rc) return rc;
+        b.d_partial = (double*)c->d_scratch;
+    }
+    return run_bounds(c, b);
+}
+
+extern "C" int fgoicp_lut_sample(fgoicp_ctx* c, const float* q_xyz, size_t n, int sampler, float* out_d2)
+{
+    FG_ARG(c && q_xyz && out_d2, "NULL pointer");
+    if (n == 0) return FGOICP_OK;
+    FG_ARG(sampler >= 0 && sampler <= 2, "unknown sampler");
+    if (sampler == FGOICP_SAMPLER_PACKED && !c->d_packed) { fg::set_error("packed grid was not built"); return FGOICP_ERR_STATE; }
+    if (sampler == FGOICP_SAMPLER_TEX && !c->lut.tex) { fg::set_error("texture was not built"); return FGOICP_ERR_STATE; }
+    FG_CUDA(cudaSetDevice(c->device));
+    size_t b_in = align256(sizeof(float) * 3 * n);
+    int rc = fg::ensure_scratch(c, b_in + sizeof(float) * n);
+    if (rc) return rc;
+    char* dp = (char*)c->d_scratch;
+    FG_CUDA(cudaMemcpyAsync(dp, q_xyz, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, c->stream));
+    unsigned blocks = (unsigned)((n + 255) / 256);
+    switch (sampler)
+    {
+    case FGOICP_SAMPLER_PACKED: k_lut_sample<FGOICP_SAMPLER_PACKED><<<blocks, 256, 0, c->stream>>>(c->lut, (const float*)dp, n, (float*)(dp + b_in)); break;
+    case FGOICP_SAMPLER_TEX:    k_lut_sample<FGOICP_SAMPLER_TEX><<<blocks, 256, 0, c->stream>>>(c->lut, (const float*)dp, n, (float*)(dp + b_in)); break;
+    default:                    k_lut_sample<FGOICP_SAMPLER_GRID><<<blocks, 256, 0, c->stream>>>(c->lut, (const float*)dp, n, (float*)(dp + b_in)); break;
+    }
+    FG_CUDA(cudaGetLastError());
+    FG_CUDA(cudaMemcpyAsync(out_d2, dp + b_in, sizeof(float) * n, cudaMemcpyDeviceToHost, c->stream));
+    FG_CUDA(cudaStreamSynchronize(c->stream));
+    return FGOICP_OK;
+}
+
+extern "C" int fgoicp_rot_sin(fgoicp_ctx* c, const float* spans, int n, float* out)
+{
+    FG_ARG(c && spans && out && n > 0, "bad arguments");
+    FG_CUDA(cudaSetDevice(c->device));
+    int rc = fg::ensure_scratch(c, sizeof(float) * 2 * n);
+    if (rc) return rc;
+    float* d = (float*)c->d_scratch;
+    FG_CUDA(cudaMemcpyAsync(d, spans, sizeof(float) * n, cudaMemcpyHostToDevice, c->stream));
+    k_rot_sin<<<(n + 127) / 128, 128, 0, c->stream>>>(d, n, d + n);
+    FG_CUDA(cudaGetLastError());
+    FG_CUDA(cudaMemcpyAsync(out, d + n, sizeof(float) * n, cudaMemcpyDeviceToHost, c->stream));
+    FG_CUDA(cudaStreamSynchronize(c->stream));
+    return FGOICP_OK;
+}

@@ -1,0 +1,266 @@
+// common.cuh -- context, error plumbing and the canonical device arithmetic shared by every
+// kernel of the B200 Go-ICP hot path.
+//
+// "Canonical arithmetic": every floating-point expression that the reference evaluates in
+// device code is written here with explicit round-to-nearest intrinsics in exactly the
+// association nvcc 12.9 gives the reference's own kernels on sm_100 (read from their SASS, see
+// DESIGN.md).  That makes per-point values bit-identical between these kernels, the CPU oracle
+// (tests only) and -- up to the texture unit's internal filter -- the reference itself.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/fgoicp_c.h"
+
+#define FG_SQRT3 1.732050807568877f     // reference fgoicp/common.hpp:19
+#define FG_PI    3.141592653589793f     // reference fgoicp/common.hpp:17
+#define FG_INF   1E+10f                 // reference fgoicp/common.hpp:18
+
+namespace fg
+{
+    void set_error(const std::string& msg);
+    int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+}
+
+#define FG_CUDA(call)                                                                   \
+    do {                                                                                \
+        cudaError_t fg_err__ = (call);                                                  \
+        if (fg_err__ != cudaSuccess)                                                    \
+            return fg::cuda_fail(fg_err__, #call, __FILE__, __LINE__);                  \
+    } while (0)
+
+#define FG_ARG(cond, msg)                                                               \
+    do {                                                                                \
+        if (!(cond)) { fg::set_error(std::string("bad argument: ") + (msg)); return FGOICP_ERR_ARG; } \
+    } while (0)
+
+// Device-side view of the nearest-squared-distance grid in its three physical layouts.
+struct LutDev
+{
+    const float* grid;        // dense, x fastest: grid[(z*dy + y)*dx + x]             (HBM)
+    const float* packed;      // corner-packed cells, 8 floats (32 B) per cell, cell index
+                              // (cx,cy,cz) in [0,dx]x[0,dy]x[0,dz] <-> texel i = c-1     (HBM)
+    cudaTextureObject_t tex;  // cudaArray + linear filter + clamp (the reference's own setup)
+    int dx, dy, dz;
+    float scale;              // 1 / resolution
+    float ox, oy, oz;         // -bbox_min
+};
+
+struct fgoicp_ctx
+{
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+    size_t nt = 0, ns = 0;
+    float4* d_model = nullptr;     // (x, y, z, index-as-bits)   [nt]
+    float4* d_data = nullptr;      // (x, y, z, |p|^2)           [ns]
+
+    float res = 0.f;
+    float bbox_min[3] = { 0, 0, 0 }, bbox_max[3] = { 0, 0, 0 };
+    LutDev lut{};
+    float* d_grid = nullptr;
+    float* d_packed = nullptr;
+    cudaArray_t arr = nullptr;
+    int sampler = FGOICP_SAMPLER_GRID;
+    float build_ms = 0.f;
+
+    // scratch (grown on demand, never shrunk)
+    void* d_scratch = nullptr;
+    size_t scratch_bytes = 0;
+    void* h_pinned = nullptr;
+    size_t pinned_bytes = 0;
+
+    // ICP state
+    float4* d_work = nullptr;                 // working copy W  [ns]
+    unsigned long long* d_nnkey = nullptr;    // packed (value bits << 32 | index) [ns]
+    double* d_icp = nullptr;                  // small state block, see nn_icp.cu
+};
+
+namespace fg
+{
+    int ensure_scratch(fgoicp_ctx* c, size_t bytes);
+    int ensure_pinned(fgoicp_ctx* c, size_t bytes);
+}
+
+// ---------------------------------------------------------------------------------------------
+// canonical device arithmetic
+// ---------------------------------------------------------------------------------------------
+
+// dx*dx + dy*dy + dz*dz  ->  FMUL, FFMA, FFMA   (reference registration.cu:154-160, 248-254)
+__device__ __forceinline__ float fg_sq3(float dx, float dy, float dz)
+{
+    return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+}
+
+// glm mat3 * vec3 (column-major R) -> FMUL, FFMA, FFMA per component (registration.cu:20, 34)
+__device__ __forceinline__ float3 fg_rotate(const float* R, float px, float py, float pz)
+{
+    float3 q;
+    q.x = __fmaf_rn(R[6], pz, __fmaf_rn(R[3], py, __fmul_rn(R[0], px)));
+    q.y = __fmaf_rn(R[7], pz, __fmaf_rn(R[4], py, __fmul_rn(R[1], px)));
+    q.z = __fmaf_rn(R[8], pz, __fmaf_rn(R[5], py, __fmul_rn(R[2], px)));
+    return q;
+}
+
+// Rotation(x, y, z) constructor, reference common.hpp:37-57.  This is HOST arithmetic in the
+// reference (no contraction), so every operation is an explicit unfused intrinsic.  Writes the
+// column-major matrix; returns Rotation::r.
+__device__ __forceinline__ float fg_rotation_matrix(float x, float y, float z, float* R)
+{
+    float r = __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
+    R[0] = 1.f; R[1] = 0.f; R[2] = 0.f; R[3] = 0.f; R[4] = 1.f; R[5] = 0.f; R[6] = 0.f; R[7] = 0.f; R[8] = 1.f;
+    if (r > 1.0f) return r;
+    float ww = __fsub_rn(1.0f, r);
+    float w = __fsqrt_rn(ww);
+    float wx = __fmul_rn(w, x), xx = __fmul_rn(x, x);
+    float wy = __fmul_rn(w, y), xy = __fmul_rn(x, y), yy = __fmul_rn(y, y);
+    float wz = __fmul_rn(w, z), xz = __fmul_rn(x, z), yz = __fmul_rn(y, z), zz = __fmul_rn(z, z);
+    R[0] = __fsub_rn(__fsub_rn(__fadd_rn(ww, xx), yy), zz);
+    R[1] = __fmul_rn(2.f, __fsub_rn(xy, wz));
+    R[2] = __fmul_rn(2.f, __fadd_rn(xz, wy));
+    R[3] = __fmul_rn(2.f, __fadd_rn(xy, wz));
+    R[4] = __fsub_rn(__fadd_rn(__fsub_rn(ww, xx), yy), zz);
+    R[5] = __fmul_rn(2.f, __fsub_rn(yz, wx));
+    R[6] = __fmul_rn(2.f, __fsub_rn(xz, wy));
+    R[7] = __fmul_rn(2.f, __fadd_rn(yz, wx));
+    R[8] = __fadd_rn(__fsub_rn(__fsub_rn(ww, xx), yy), zz);
+    return __fsqrt_rn(r);
+}
+
+// sin(span * sqrt3 * pi / 2) exactly as the reference's kernel evaluates it per thread
+// (registration.cu:41-42; SASS: FMUL, FMUL.D2, then libdevice sinf).
+__device__ __forceinline__ float fg_rot_sin(float span)
+{
+    float half_angle = __fmul_rn(__fmul_rn(__fmul_rn(span, FG_SQRT3), FG_PI), 0.5f);
+    return sinf(half_angle);
+}
+
+// ---------------------------------------------------------------------------------------------
+// grid sampling: the reference's tex3D semantics (registration.cu:214-234, 320-328)
+//   u = (q + offset) * scale ; uB = u - 0.5 ; i = floor(uB) ; alpha = frac(uB) in 1.8 fixed point ;
+//   texel indices clamped to [0, dim-1] ; tri-linear blend of SQUARED distances.
+// FG_WEIGHT_TRUNC / FG_INTERP_WSUM select the alternatives probed by the texture conformance
+// test; the defaults are the ones that match tex3D on B200 best.
+// ---------------------------------------------------------------------------------------------
+#ifndef FG_WEIGHT_TRUNC
+#define FG_WEIGHT_TRUNC 0
+#endif
+#ifndef FG_INTERP_WSUM
+#define FG_INTERP_WSUM 0
+#endif
+
+__device__ __forceinline__ void fg_tex_axis(float u, int dim, int& i, float& alpha)
+{
+    u = fmaxf(u, -2.0f);                       // also maps NaN to -2
+    u = fminf(u, (float)dim + 2.0f);
+#if FG_WEIGHT_TRUNC
+    int xf = __float2int_rd(__fmul_rn(u, 256.0f)) - 128;
+#else
+    int xf = __float2int_rn(__fmul_rn(u, 256.0f)) - 128;
+#endif
+    i = xf >> 8;
+    alpha = __fmul_rn((float)(xf & 255), 1.0f / 256.0f);
+}
+
+__device__ __forceinline__ float fg_trilerp(float a, float b, float c,
+                                            float t000, float t100, float t010, float t110,
+                                            float t001, float t101, float t011, float t111)
+{
+#if FG_INTERP_WSUM
+    float a0 = __fsub_rn(1.0f, a), b0 = __fsub_rn(1.0f, b), c0 = __fsub_rn(1.0f, c);
+    float acc = __fmul_rn(__fmul_rn(__fmul_rn(a0, b0), c0), t000);
+    acc = __fmaf_rn(__fmul_rn(__fmul_rn(a, b0), c0), t100, acc);
+    acc = __fmaf_rn(__fmul_rn(__fmul_rn(a0, b), c0), t010, acc);
+    acc = __fmaf_rn(__fmul_rn(__fmul_rn(a, b), c0), t110, acc);
+    acc = __fmaf_rn(__fmul_rn(__fmul_rn(a0, b0), c), t001, acc);
+    acc = __fmaf_rn(__fmul_rn(__fmul_rn(a, b0), c), t101, acc);
+    acc = __fmaf_rn(__fmul_rn(__fmul_rn(a0, b), c), t011, acc);
+    acc = __fmaf_rn(__fmul_rn(__fmul_rn(a, b), c), t111, acc);
+    return acc;
+#else
+    float c00 = __fmaf_rn(a, __fsub_rn(t100, t000), t000);
+    float c10 = __fmaf_rn(a, __fsub_rn(t110, t010), t010);
+    float c01 = __fmaf_rn(a, __fsub_rn(t101, t001), t001);
+    float c11 = __fmaf_rn(a, __fsub_rn(t111, t011), t011);
+    float c0 = __fmaf_rn(b, __fsub_rn(c10, c00), c00);
+    float c1 = __fmaf_rn(b, __fsub_rn(c11, c01), c01);
+    return __fmaf_rn(c, __fsub_rn(c1, c0), c0);
+#endif
+}
+
+// one 256-bit read-only load (sm_100+): the whole corner-packed cell in a single request
+__device__ __forceinline__ void fg_ld256(const float* p, float (&v)[8])
+{
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]),
+                   "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                 : "l"(p));
+}
+
+template <int SAMPLER>
+__device__ __forceinline__ float fg_sample(const LutDev& L, float qx, float qy, float qz)
+{
+    // NearestNeighborLUT::search: (query + offset) * scale   (FADD then FMUL in the SASS)
+    float ux = __fmul_rn(__fadd_rn(qx, L.ox), L.scale);
+    float uy = __fmul_rn(__fadd_rn(qy, L.oy), L.scale);
+    float uz = __fmul_rn(__fadd_rn(qz, L.oz), L.scale);
+    if (SAMPLER == FGOICP_SAMPLER_TEX)
+    {
+        return tex3D<float>(L.tex, ux, uy, uz);
+    }
+    int ix, iy, iz;
+    float a, b, c;
+    fg_tex_axis(ux, L.dx, ix, a);
+    fg_tex_axis(uy, L.dy, iy, b);
+    fg_tex_axis(uz, L.dz, iz, c);
+    if (SAMPLER == FGOICP_SAMPLER_PACKED)
+    {
+        // cell c = clamp(i, -1, dim-1) + 1 holds the 8 clamped corner texels of texel index i
+        int cx = min(max(ix, -1), L.dx - 1) + 1;
+        int cy = min(max(iy, -1), L.dy - 1) + 1;
+        int cz = min(max(iz, -1), L.dz - 1) + 1;
+        size_t cell = ((size_t)cz * (size_t)(L.dy + 1) + (size_t)cy) * (size_t)(L.dx + 1) + (size_t)cx;
+        float v[8];
+        fg_ld256(L.packed + cell * 8, v);
+        return fg_trilerp(a, b, c, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
+    }
+    else
+    {
+        int x0 = min(max(ix, 0), L.dx - 1), x1 = min(max(ix + 1, 0), L.dx - 1);
+        int y0 = min(max(iy, 0), L.dy - 1), y1 = min(max(iy + 1, 0), L.dy - 1);
+        int z0 = min(max(iz, 0), L.dz - 1), z1 = min(max(iz + 1, 0), L.dz - 1);
+        size_t sy = (size_t)L.dx, sz = (size_t)L.dx * (size_t)L.dy;
+        const float* g = L.grid;
+        float t000 = __ldg(g + x0 + y0 * sy + z0 * sz), t100 = __ldg(g + x1 + y0 * sy + z0 * sz);
+        float t010 = __ldg(g + x0 + y1 * sy + z0 * sz), t110 = __ldg(g + x1 + y1 * sy + z0 * sz);
+        float t001 = __ldg(g + x0 + y0 * sy + z1 * sz), t101 = __ldg(g + x1 + y0 * sy + z1 * sz);
+        float t011 = __ldg(g + x0 + y1 * sy + z1 * sz), t111 = __ldg(g + x1 + y1 * sy + z1 * sz);
+        return fg_trilerp(a, b, c, t000, t100, t010, t110, t001, t101, t011, t111);
+    }
+}
+
+// Per-point body of kernComputeBounds (reference registration.cu:27-60) after the sample:
+// d = sqrt(d2); if (!fix_rot) d -= rot_r; ub = d>0 ? d*d : 0; e = fma(span_t, -sqrt3, d);
+// lb = e>0 ? e*e : 0.
+__device__ __forceinline__ void fg_bound_terms(float d2, float rot_r, bool fix_rot, float span_t,
+                                               float& ub, float& lb)
+{
+    float d = __fsqrt_rn(d2);
+    if (!fix_rot) d = __fsub_rn(d, rot_r);
+    ub = d > 0.0f ? __fmul_rn(d, d) : 0.0f;
+    float e = __fmaf_rn(span_t, -FG_SQRT3, d);
+    lb = e > 0.0f ? __fmul_rn(e, e) : 0.0f;
+}
+
+__device__ __forceinline__ double fg_warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}

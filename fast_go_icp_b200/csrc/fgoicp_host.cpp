@@ -1,0 +1,306 @@
+// fgoicp_host.cpp -- icp::FastGoICP: host driver of the Go-ICP search over the C ABI.
+//
+// Mirrors the behaviour of the reference's fgoicp/fgoicp.cpp (run(), branch_and_bound_SO3(),
+// preprocessing) but owns no CUDA code: every device operation goes through <fgoicp_c.h>.
+// Two schedules of the outer SO(3) search are provided:
+//   Level     -- level-synchronous frontier; all surviving cubes of a level run their inner searches
+//                concurrently on the GPU (one thread block each).  This is the production path and
+//                the one that shards across GPUs (see fast_go_icp_b200/driver.py).
+//   BestFirst -- the reference's serial order (fgoicp.cpp:32-100), for side-by-side parity runs.
+#include <fgoicp/fgoicp.hpp>
+#include <fgoicp_c.h>
+
+#include <chrono>
+#include <cstdlib>
+#include <cstring>
+#include <queue>
+
+namespace icp
+{
+    namespace
+    {
+        struct ApiError : std::runtime_error
+        {
+            explicit ApiError(const std::string& what) : std::runtime_error(what) {}
+        };
+
+        void check(int rc, const char* what)
+        {
+            if (rc != FGOICP_OK)
+                throw ApiError(std::string(what) + ": " + fgoicp_last_error());
+        }
+
+        void to_array(const glm::mat3& R, float* out)
+        {
+            for (int c = 0; c < 3; ++c)
+                for (int r = 0; r < 3; ++r) out[c * 3 + r] = R[c][r];
+        }
+
+        glm::mat3 to_mat3(const float* a)
+        {
+            return glm::mat3(a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8]);
+        }
+
+        double now_ms()
+        {
+            using clk = std::chrono::steady_clock;
+            return std::chrono::duration<double, std::milli>(clk::now().time_since_epoch()).count();
+        }
+    }
+
+    FastGoICP::FastGoICP(std::vector<glm::vec3> _pct, std::vector<glm::vec3> _pcs, float _lut_resolution, float _mse_threshold)
+        : FastGoICP(std::move(_pct), std::move(_pcs), _lut_resolution, _mse_threshold, Options())
+    {}
+
+    // Member order and preprocessing order follow the reference constructor (fgoicp.hpp:13-25):
+    // centre source, centre target, scale both by the SOURCE's factor, bounding box of the target.
+    FastGoICP::FastGoICP(std::vector<glm::vec3> _pct, std::vector<glm::vec3> _pcs, float _lut_resolution, float _mse_threshold,
+                         const Options& options)
+        : pcs(std::move(_pcs)), pct(std::move(_pct)), ns{ pcs.size() }, nt{ pct.size() },
+          offset_pcs(center_point_cloud(pcs)),
+          offset_pct(center_point_cloud(pct)),
+          scaling_factor(scale_point_clouds(pct, pcs)),
+          target_bounds(get_point_cloud_ranges(pct)),
+          best_sse(M_INF), best_rotation(1.0f), best_translation(0.0f),
+          mse_threshold(_mse_threshold),
+          sse_threshold(ns * mse_threshold),
+          options_(options)
+    {
+        if (const char* s = std::getenv("FGOICP_SCHEDULE"))
+        {
+            if (std::strcmp(s, "bestfirst") == 0) options_.schedule = Schedule::BestFirst;
+            if (std::strcmp(s, "level") == 0) options_.schedule = Schedule::Level;
+        }
+        if (const char* s = std::getenv("FGOICP_SAMPLER")) options_.sampler = std::atoi(s);
+        if (const char* s = std::getenv("FGOICP_DEVICE")) options_.device = std::atoi(s);
+        init(_lut_resolution);
+    }
+
+    void FastGoICP::init(float lut_resolution)
+    {
+        double t0 = now_ms();
+        float bmin[3] = { target_bounds[0].first, target_bounds[1].first, target_bounds[2].first };
+        float bmax[3] = { target_bounds[0].second, target_bounds[1].second, target_bounds[2].second };
+        static_assert(sizeof(glm::vec3) == 3 * sizeof(float), "glm::vec3 must be three packed floats");
+        unsigned flags = FGOICP_BUILD_PACKED;
+        if (options_.sampler == FGOICP_SAMPLER_TEX) flags |= FGOICP_BUILD_TEX;
+        check(fgoicp_ctx_create(reinterpret_cast<const float*>(pct.data()), nt,
+                                reinterpret_cast<const float*>(pcs.data()), ns,
+                                bmin, bmax, lut_resolution, options_.device, flags, &ctx_),
+              "fgoicp_ctx_create");
+        if (options_.sampler >= 0) check(fgoicp_set_sampler(ctx_, options_.sampler), "fgoicp_set_sampler");
+        fgoicp_info info;
+        check(fgoicp_ctx_info(ctx_, &info), "fgoicp_ctx_info");
+        if (info.dims[0] >= 1024 || info.dims[1] >= 1024 || info.dims[2] >= 1024)
+            Logger(LogLevel::Warning) << "Dims " << info.dims[0] << ", " << info.dims[1] << ", " << info.dims[2]
+                                      << " is large, consider a lower LUT resolution";
+        stats_.lut_build_ms = info.build_ms;
+        stats_.ctor_ms = static_cast<float>(now_ms() - t0);
+    }
+
+    FastGoICP::~FastGoICP()
+    {
+        fgoicp_ctx_destroy(ctx_);
+    }
+
+    float FastGoICP::icp(int max_iter, float thr, const glm::mat3& R0, const glm::vec3& t0, glm::mat3& R, glm::vec3& t)
+    {
+        float r0[9], tt0[3] = { t0.x, t0.y, t0.z }, r[9], tt[3], sse = 0.f;
+        int iters = 0;
+        to_array(R0, r0);
+        check(fgoicp_icp(ctx_, r0, tt0, max_iter, thr, &sse, r, tt, &iters), "fgoicp_icp");
+        R = to_mat3(r);
+        t = glm::vec3(tt[0], tt[1], tt[2]);
+        stats_.icp_runs += 1;
+        stats_.icp_iters += static_cast<std::uint32_t>(iters);
+        return sse;
+    }
+
+    // reference fgoicp.cpp:10-30
+    FastGoICP::Result_t FastGoICP::run()
+    {
+        double t0 = now_ms();
+        glm::mat3 icp_R; glm::vec3 icp_t;
+        // Initial ICP from the identity; only its error is kept (fgoicp.cpp:12-14)
+        best_sse = icp(100, 0.05, glm::mat3(1.0f), glm::vec3(0.0f), icp_R, icp_t);
+        Logger(LogLevel::Info) << "Initial ICP best error: " << best_sse
+                               << "\n\tRotation:\n" << icp_R
+                               << "\n\tTranslation: " << icp_t;
+
+        if (options_.schedule == Schedule::BestFirst) search_best_first();
+        else search_level_synchronous();
+
+        // Refine the best transform (fgoicp.cpp:22-23)
+        glm::mat3 R; glm::vec3 t;
+        best_sse = icp(100, 0.0005, best_rotation, best_translation, R, t);
+        best_rotation = R; best_translation = t;
+
+        Logger(LogLevel::Info) << "Searching over! Best Error: " << best_sse
+                               << "\n\tRotation:\n" << best_rotation
+                               << "\n\tTranslation: " << restore_translation(best_rotation, best_translation);
+        stats_.run_ms = static_cast<float>(now_ms() - t0);
+        return { best_rotation, restore_translation(best_rotation, best_translation) };
+    }
+
+    // Level-synchronous form of branch_and_bound_SO3 (fgoicp.cpp:32-100).  Per level:
+    //   1. nodes with best_sse - lb <= sse_threshold are finished (the reference's stop rule :44 applies to
+    //      the smallest lb first, hence to every node it would still hold);
+    //   2. spawn the 8 octants (:49-59), drop cubes missing the unit ball (:61), pass cubes whose centre is
+    //      outside the ball on unevaluated (:62-66);
+    //   3. inner search with the rotation fixed for ALL remaining children at once -> ub, t* (:69),
+    //      ICP from (R, t*) where ub < 1.8 best_sse (:74-88);
+    //   4. inner search with rotation uncertainty for all children -> lb (:90), drop lb >= best_sse (:92).
+    void FastGoICP::search_level_synchronous()
+    {
+        std::vector<RotNode> frontier;
+        frontier.emplace_back(0.0f, 0.0f, 0.0f, 1.0f, 0.0f, best_sse);
+        while (!frontier.empty())
+        {
+            std::vector<RotNode> open;
+            for (const RotNode& n : frontier)
+                if (!(best_sse - n.lb <= sse_threshold)) open.push_back(n);
+            if (open.empty()) break;
+            float span = open.front().span / 2.0f;
+            if (span < 0.05f) break;
+
+            std::vector<RotNode> next, eval;
+            for (const RotNode& n : open)
+                for (char j = 0; j < 8; ++j)
+                {
+                    RotNode child(n.q.x - span + (j >> 0 & 1) * n.span,
+                                  n.q.y - span + (j >> 1 & 1) * n.span,
+                                  n.q.z - span + (j >> 2 & 1) * n.span,
+                                  span, n.lb, n.ub);
+                    if (!child.overlaps_SO3()) continue;
+                    if (!child.q.in_SO3()) { next.push_back(child); continue; }
+                    eval.push_back(child);
+                }
+            const int n = static_cast<int>(eval.size());
+            std::vector<float> cubes(4 * static_cast<size_t>(n)), ub(n), bt(3 * static_cast<size_t>(n)), lb(n);
+            for (int i = 0; i < n; ++i)
+            {
+                cubes[4 * i] = eval[i].q.x; cubes[4 * i + 1] = eval[i].q.y; cubes[4 * i + 2] = eval[i].q.z;
+                cubes[4 * i + 3] = eval[i].span;
+            }
+            float bR[9], bT[3] = { best_translation.x, best_translation.y, best_translation.z };
+            to_array(best_rotation, bR);
+            float level_best = best_sse;
+            fgoicp_level_stats st_ub{}, st_lb{};
+            check(fgoicp_so3_level_ub(ctx_, cubes.data(), n, best_sse, sse_threshold, ub.data(), bt.data(),
+                                      &level_best, bR, bT, &st_ub), "fgoicp_so3_level_ub");
+            if (level_best < best_sse)
+            {
+                best_sse = level_best;
+                best_rotation = to_mat3(bR);
+                best_translation = glm::vec3(bT[0], bT[1], bT[2]);
+                Logger(LogLevel::Debug) << "New best error: " << best_sse
+                                        << "\n\tRotation:\n" << best_rotation
+                                        << "\n\tTranslation: " << restore_translation(best_rotation, best_translation);
+            }
+            check(fgoicp_so3_level_lb(ctx_, cubes.data(), n, best_sse, sse_threshold, lb.data(), &st_lb),
+                  "fgoicp_so3_level_lb");
+            for (int i = 0; i < n; ++i)
+            {
+                if (lb[i] >= best_sse) continue;
+                eval[i].lb = lb[i];
+                eval[i].ub = ub[i];
+                next.push_back(eval[i]);
+            }
+            if (n > 0)
+            {
+                last_rotation = eval[n - 1].q.R;
+                last_translation = glm::vec3(bt[3 * (n - 1)], bt[3 * (n - 1) + 1], bt[3 * (n - 1) + 2]);
+            }
+            stats_.levels += 1;
+            stats_.rot_cubes += static_cast<std::uint32_t>(n);
+            stats_.bound_evals += st_ub.evals + st_lb.evals;
+            stats_.icp_runs += st_ub.n_icp;
+            stats_.icp_iters += st_ub.icp_iters;
+            stats_.ms_bnb_ub += st_ub.ms_bnb_ub; stats_.ms_icp += st_ub.ms_icp; stats_.ms_bnb_lb += st_lb.ms_bnb_lb;
+            if (options_.verbose_levels || Logger::verbose())
+                Logger(LogLevel::Debug) << "level span " << span << ": " << n << " cubes, " << st_ub.n_icp << " ICPs, "
+                                        << (st_ub.evals + st_lb.evals) << " bound evals, best " << best_sse
+                                        << ", survivors " << next.size();
+            frontier.swap(next);
+        }
+    }
+
+    // The reference's own serial order (fgoicp.cpp:32-100); std::priority_queue<RotNode> as there.
+    void FastGoICP::search_best_first()
+    {
+        std::priority_queue<RotNode> rcandidates;
+        rcandidates.push(RotNode(0.0f, 0.0f, 0.0f, 1.0f, 0.0f, best_sse));
+        while (!rcandidates.empty())
+        {
+            RotNode rnode = rcandidates.top();
+            rcandidates.pop();
+            if (best_sse - rnode.lb <= sse_threshold) break;
+            float span = rnode.span / 2.0f;
+            for (char j = 0; j < 8; ++j)
+            {
+                if (span < 0.05f) continue;
+                RotNode child(rnode.q.x - span + (j >> 0 & 1) * rnode.span,
+                              rnode.q.y - span + (j >> 1 & 1) * rnode.span,
+                              rnode.q.z - span + (j >> 2 & 1) * rnode.span,
+                              span, rnode.lb, rnode.ub);
+                if (!child.overlaps_SO3()) continue;
+                if (!child.q.in_SO3()) { rcandidates.push(child); continue; }
+
+                float cube[4] = { child.q.x, child.q.y, child.q.z, child.span };
+                float ub = 0.f, bt[3] = { 0, 0, 0 }, lb = 0.f, dummy[3];
+                std::uint64_t ev = 0;
+                check(fgoicp_bnb_r3(ctx_, cube, 1, best_sse, sse_threshold, &ub, bt, &ev), "fgoicp_bnb_r3");
+                stats_.bound_evals += ev; stats_.rot_cubes += 1;
+                last_rotation = child.q.R;
+                last_translation = glm::vec3(bt[0], bt[1], bt[2]);
+                if (ub < best_sse * 1.8)
+                {
+                    glm::mat3 R; glm::vec3 t;
+                    float e = icp(100, 0.005, child.q.R, last_translation, R, t);
+                    if (e < best_sse) { best_sse = e; best_rotation = R; best_translation = t; }
+                }
+                check(fgoicp_bnb_r3(ctx_, cube, 0, best_sse, sse_threshold, &lb, dummy, &ev), "fgoicp_bnb_r3");
+                stats_.bound_evals += ev;
+                if (lb >= best_sse) continue;
+                child.lb = lb; child.ub = ub;
+                rcandidates.push(child);
+            }
+        }
+    }
+
+    // reference fgoicp.cpp:176-195: serial fp32 sum in index order, returns -centroid
+    glm::vec3 FastGoICP::center_point_cloud(PointCloud& pc)
+    {
+        glm::vec3 centroid(0.0f);
+        for (size_t i = 0; i < pc.size(); ++i) centroid += pc[i];
+        centroid /= static_cast<float>(pc.size());
+        for (size_t i = 0; i < pc.size(); ++i) pc[i] -= centroid;
+        return -centroid;
+    }
+
+    // reference fgoicp.cpp:197-220, 271-287: 1 / max |coordinate| of the SOURCE, applied to both clouds
+    float FastGoICP::scale_point_clouds(PointCloud& target, PointCloud& source)
+    {
+        float max_abs = std::numeric_limits<float>::lowest();
+        for (const auto& p : source)
+            max_abs = std::max(max_abs, std::max(std::abs(p.x), std::max(std::abs(p.y), std::abs(p.z))));
+        float s = 1.0f / max_abs;
+        for (auto& p : source) p *= s;
+        for (auto& p : target) p *= s;
+        return s;
+    }
+
+    // reference fgoicp.cpp:222-268
+    std::array<std::pair<float, float>, 3> FastGoICP::get_point_cloud_ranges(PointCloud& pc)
+    {
+        std::array<std::pair<float, float>, 3> ranges;
+        for (auto& r : ranges) r = std::make_pair(std::numeric_limits<float>::max(), std::numeric_limits<float>::lowest());
+        for (const auto& p : pc)
+            for (int a = 0; a < 3; ++a)
+            {
+                ranges[a].first = std::min(ranges[a].first, p[a]);
+                ranges[a].second = std::max(ranges[a].second, p[a]);
+            }
+        return ranges;
+    }
+}

@@ -1,0 +1,470 @@
+// nn_icp.cu -- exact nearest-neighbour search, exact SSE and the nested ICP refinement.
+//
+// Replaces, from the reference:
+//   kernComputeClosestError + brute_force_find_nearest_neighbor + thrust::reduce
+//       (fgoicp/registration.cu:14-25, 62-86, 154-174)                     -> fgoicp_sse
+//   kernFindNearestNeighbor (fgoicp/icp3d.cu:11-28)                         -> NN with rooted compare
+//   IterativeClosestPoint3D::{ctor, run, procrustes} (fgoicp/icp3d.cu:55-172) -> fgoicp_icp
+// The reference allocates six buffers and uploads both clouds per ICP instance, launches six
+// small kernels and four blocking reductions per iteration and does the 3x3 SVD on the host.
+// Here the clouds stay resident, the loop state lives in device memory, the SVD runs in a device
+// thread, and the host only polls a "done" flag.
+//
+// Tie rules kept bit-exact:
+//   squared compare (K5): strict <, ascending j  -> lowest index among equal d2 wins;
+//   rooted compare  (K7): strict >, on sqrtf(d2) -> lowest index among equal sqrtf(d2) wins.
+// Both are order-independent once phrased as a lexicographic min over (value, index), which is
+// what lets the model cloud be split across thread blocks and merged with a 64-bit atomicMin.
+#include "common.cuh"
+#include "svd3_device.cuh"
+
+#include <algorithm>
+#include <cstring>
+
+#define NN_THREADS 256
+#define NN_QPT     2                       // queries per thread
+#define NN_TILE    1024                    // model points staged in shared memory
+
+struct IcpState
+{
+    float R[9], t[3];            // current pose (must stay first: kernels read pose = (R, t))
+    float lastR[9], lastT[3];
+    float Rd[9], td[3];          // last increment
+    float abar[3], bbar[3];
+    float sse, last_sse;
+    float thr;
+    int iter, max_iter, done;
+    float out_sse, outR[9], outT[3];
+    int out_iters;
+    double sums[16];
+};
+
+// smallest float x with sqrtf(x) == s  (so that  sqrtf(d) < s  <=>  d < lo(s))
+__device__ __forceinline__ float fg_sqrt_preimage_lo(float s)
+{
+    float x = __fmul_rn(s, s);
+    for (int it = 0; it < 4; ++it)
+    {
+        if (!(x > 0.0f)) break;
+        float xm = __uint_as_float(__float_as_uint(x) - 1u);
+        if (__fsqrt_rn(xm) == s) x = xm; else break;
+    }
+    for (int it = 0; it < 4; ++it)
+    {
+        if (__fsqrt_rn(x) < s) x = __uint_as_float(__float_as_uint(x) + 1u); else break;
+    }
+    return x;
+}
+
+// One block: NN_THREADS*NN_QPT queries against one chunk of the model cloud.
+template <int ROOTED>
+__global__ void __launch_bounds__(NN_THREADS)
+k_nn_brute(const float4* __restrict__ model, int nt, int chunk,
+           const float4* __restrict__ src, int ns, const float* __restrict__ pose,
+           unsigned long long* __restrict__ keys, const int* __restrict__ done_flag)
+{
+    __shared__ float4 tile[NN_TILE];
+    if (done_flag && *done_flag) return;
+
+    float qx[NN_QPT], qy[NN_QPT], qz[NN_QPT];
+    float best[NN_QPT], thr[NN_QPT];
+    int bi[NN_QPT];
+    int q0 = blockIdx.x * (NN_THREADS * NN_QPT) + threadIdx.x;
+    float R[9], t[3];
+    if (pose)
+    {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) R[k] = pose[k];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) t[k] = pose[9 + k];
+    }
+#pragma unroll
+    for (int k = 0; k < NN_QPT; ++k)
+    {
+        int i = min(q0 + k * NN_THREADS, ns - 1);
+        float4 p = src[i];
+        if (pose)
+        {
+            // query = R * p + t   (registration.cu:20; SASS: FMUL, FFMA, FFMA, FADD)
+            float3 rp = fg_rotate(R, p.x, p.y, p.z);
+            qx[k] = __fadd_rn(rp.x, t[0]); qy[k] = __fadd_rn(rp.y, t[1]); qz[k] = __fadd_rn(rp.z, t[2]);
+        }
+        else { qx[k] = p.x; qy[k] = p.y; qz[k] = p.z; }
+        best[k] = FG_INF;                                        // M_INF seed (registration.cu:164, icp3d.cu:16)
+        thr[k] = ROOTED ? fg_sqrt_preimage_lo(FG_INF) : FG_INF;
+        bi[k] = -1;
+    }
+
+    int j0 = blockIdx.y * chunk;
+    int j1 = min(nt, j0 + chunk);
+    for (int base = j0; base < j1; base += NN_TILE)
+    {
+        int cnt = min(NN_TILE, j1 - base);
+        __syncthreads();
+        for (int i = threadIdx.x; i < cnt; i += NN_THREADS) tile[i] = model[base + i];
+        __syncthreads();
+#pragma unroll 4
+        for (int j = 0; j < cnt; ++j)
+        {
+            float4 m = tile[j];
+#pragma unroll
+            for (int k = 0; k < NN_QPT; ++k)
+            {
+                float d = fg_sq3(__fsub_rn(qx[k], m.x), __fsub_rn(qy[k], m.y), __fsub_rn(qz[k], m.z));
+                if (d < thr[k])
+                {
+                    if (ROOTED)
+                    {
+                        float s = __fsqrt_rn(d);                 // glm::distance (icp3d.cu:20)
+                        best[k] = s;
+                        thr[k] = fg_sqrt_preimage_lo(s);
+                    }
+                    else { best[k] = d; thr[k] = d; }
+                    bi[k] = __float_as_int(m.w);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < NN_QPT; ++k)
+    {
+        int i = q0 + k * NN_THREADS;
+        if (i < ns && bi[k] >= 0)
+        {
+            unsigned long long key = ((unsigned long long)__float_as_uint(best[k]) << 32) | (unsigned int)bi[k];
+            atomicMin(&keys[i], key);
+        }
+    }
+}
+
+// keys -> (idx, d2 of the winner recomputed with the canonical formula)
+__global__ void k_nn_finish(const unsigned long long* __restrict__ keys, const float4* __restrict__ model,
+                            const float4* __restrict__ src, int ns, const float* __restrict__ pose,
+                            int* __restrict__ idx, float* __restrict__ d2)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ns) return;
+    unsigned int j = (unsigned int)(keys[i] & 0xffffffffull);
+    int ji = (j == 0xffffffffu) ? -1 : (int)j;
+    if (idx) idx[i] = ji;
+    if (d2)
+    {
+        if (ji < 0) { d2[i] = FG_INF; return; }
+        float4 p = src[i];
+        float qx = p.x, qy = p.y, qz = p.z;
+        if (pose)
+        {
+            float R[9];
+            for (int k = 0; k < 9; ++k) R[k] = pose[k];
+            float3 rp = fg_rotate(R, p.x, p.y, p.z);
+            qx = __fadd_rn(rp.x, pose[9]); qy = __fadd_rn(rp.y, pose[10]); qz = __fadd_rn(rp.z, pose[11]);
+        }
+        float4 m = model[ji];
+        d2[i] = fg_sq3(__fsub_rn(qx, m.x), __fsub_rn(qy, m.y), __fsub_rn(qz, m.z));
+    }
+}
+
+// deterministic single-block sum helpers ---------------------------------------------------------
+template <int N>
+__device__ __forceinline__ void fg_block_sum(double (&v)[N], double* out /* shared or global, N values */)
+{
+    __shared__ double s_w[32][N];
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+    for (int k = 0; k < N; ++k) v[k] = fg_warp_sum(v[k]);
+    if (lane == 0)
+#pragma unroll
+        for (int k = 0; k < N; ++k) s_w[w][k] = v[k];
+    __syncthreads();
+    if (threadIdx.x < N)
+    {
+        double a = 0.0;
+        for (int q = 0; q < nw; ++q) a += s_w[q][threadIdx.x];
+        out[threadIdx.x] = a;
+    }
+    __syncthreads();
+}
+
+// SSE = sum of the winning squared distances (keys carry d2 bits in the high word), fp64 -> float
+__global__ void __launch_bounds__(1024)
+k_sse_reduce(const unsigned long long* __restrict__ keys, int ns, IcpState* st, float* out)
+{
+    if (st && st->done) return;
+    __shared__ double s_out[1];
+    double v[1] = { 0.0 };
+    for (int i = threadIdx.x; i < ns; i += blockDim.x)
+        v[0] += (double)__uint_as_float((unsigned int)(keys[i] >> 32));
+    fg_block_sum<1>(v, s_out);
+    if (threadIdx.x == 0)
+    {
+        float sse = (float)s_out[0];
+        if (st) st->sse = sse;
+        if (out) *out = sse;
+    }
+}
+
+// ---- ICP -----------------------------------------------------------------------------------
+
+__global__ void k_icp_init(IcpState* st, const float* __restrict__ pose0, int max_iter, float thr)
+{
+    for (int k = 0; k < 9; ++k) { st->R[k] = pose0[k]; st->lastR[k] = pose0[k]; }
+    for (int k = 0; k < 3; ++k) { st->t[k] = pose0[9 + k]; st->lastT[k] = pose0[9 + k]; }
+    st->sse = FG_INF; st->last_sse = __fmul_rn(2.0f, FG_INF);      // icp3d.cu:89-90
+    st->thr = thr; st->iter = 0; st->max_iter = max_iter; st->done = 0;
+    st->out_iters = 0;
+}
+
+// W_i = R * p_i + t  (icp3d.cu:85 with the seed pose; :100 with the increment)
+__global__ void k_icp_transform(const float4* src, float4* dst, int ns,   /* may alias: in-place update */
+                                const float* __restrict__ pose, const int* __restrict__ done_flag)
+{
+    if (done_flag && *done_flag) return;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ns) return;
+    float R[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) R[k] = pose[k];
+    float4 p = src[i];
+    float3 rp = fg_rotate(R, p.x, p.y, p.z);
+    dst[i] = make_float4(__fadd_rn(rp.x, pose[9]), __fadd_rn(rp.y, pose[10]), __fadd_rn(rp.z, pose[11]), p.w);
+}
+
+// loop head: while (iter++ < max_iter && (last_sse - sse) > thr * last_sse)   (icp3d.cu:94-98)
+__global__ void k_icp_begin(IcpState* st)
+{
+    if (st->done) return;
+    bool go = (st->iter++ < st->max_iter) &&
+              (__fsub_rn(st->last_sse, st->sse) > __fmul_rn(st->thr, st->last_sse));
+    if (!go)
+    {
+        st->done = 1;
+        st->out_iters = st->iter - 1;
+        // return sse < last_sse ? (sse, R, t) : (last_sse, last_R, last_t)   (icp3d.cu:106-107)
+        bool cur = st->sse < st->last_sse;
+        st->out_sse = cur ? st->sse : st->last_sse;
+        for (int k = 0; k < 9; ++k) st->outR[k] = cur ? st->R[k] : st->lastR[k];
+        for (int k = 0; k < 3; ++k) st->outT[k] = cur ? st->t[k] : st->lastT[k];
+        return;
+    }
+    st->last_sse = st->sse;
+    for (int k = 0; k < 9; ++k) st->lastR[k] = st->R[k];
+    for (int k = 0; k < 3; ++k) st->lastT[k] = st->t[k];
+}
+
+// centroids of the working cloud and of its correspondences (icp3d.cu:150-156)
+__global__ void __launch_bounds__(1024)
+k_icp_centroids(const float4* __restrict__ W, const unsigned long long* __restrict__ keys,
+                const float4* __restrict__ model, int ns, IcpState* st)
+{
+    if (st->done) return;
+    __shared__ double s_out[6];
+    double v[6] = { 0, 0, 0, 0, 0, 0 };
+    for (int i = threadIdx.x; i < ns; i += blockDim.x)
+    {
+        float4 a = W[i];
+        float4 b = model[(unsigned int)(keys[i] & 0xffffffffull)];
+        v[0] += (double)a.x; v[1] += (double)a.y; v[2] += (double)a.z;
+        v[3] += (double)b.x; v[4] += (double)b.y; v[5] += (double)b.z;
+    }
+    fg_block_sum<6>(v, s_out);
+    if (threadIdx.x < 3)
+    {
+        st->abar[threadIdx.x] = __fdiv_rn((float)s_out[threadIdx.x], (float)ns);
+        st->bbar[threadIdx.x] = __fdiv_rn((float)s_out[3 + threadIdx.x], (float)ns);
+    }
+}
+
+// cross-covariance of the centred clouds, closest rotation, pose update (icp3d.cu:158-172, 101-102)
+__global__ void __launch_bounds__(1024)
+k_icp_procrustes(const float4* __restrict__ W, const unsigned long long* __restrict__ keys,
+                 const float4* __restrict__ model, int ns, IcpState* st)
+{
+    if (st->done) return;
+    __shared__ double s_out[9];
+    float ab[3] = { st->abar[0], st->abar[1], st->abar[2] };
+    float bb[3] = { st->bbar[0], st->bbar[1], st->bbar[2] };
+    double v[9] = { 0, 0, 0, 0, 0, 0, 0, 0, 0 };
+    for (int i = threadIdx.x; i < ns; i += blockDim.x)
+    {
+        float4 w4 = W[i];
+        float4 m4 = model[(unsigned int)(keys[i] & 0xffffffffull)];
+        float a[3] = { __fsub_rn(w4.x, ab[0]), __fsub_rn(w4.y, ab[1]), __fsub_rn(w4.z, ab[2]) };   // icp3d.cu:43
+        float b[3] = { __fsub_rn(m4.x, bb[0]), __fsub_rn(m4.y, bb[1]), __fsub_rn(m4.z, bb[2]) };
+        // glm::outerProduct(a, b)[c][r] = a[r] * b[c]   (icp3d.cu:51)
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+                v[c * 3 + r] += (double)__fmul_rn(a[r], b[c]);
+    }
+    fg_block_sum<9>(v, s_out);
+    if (threadIdx.x == 0)
+    {
+        float ABt[9], Rd[9], td[3], Rn[9], tn[3];
+        for (int k = 0; k < 9; ++k) ABt[k] = (float)s_out[k];
+        fg_closest_rotation(ABt, Rd);
+        // host-side glm arithmetic in the reference: unfused, left to right
+        for (int r = 0; r < 3; ++r)
+        {
+            float ra = __fadd_rn(__fadd_rn(__fmul_rn(Rd[r], ab[0]), __fmul_rn(Rd[3 + r], ab[1])), __fmul_rn(Rd[6 + r], ab[2]));
+            td[r] = __fsub_rn(bb[r], ra);                                                   // icp3d.cu:169
+        }
+        for (int c = 0; c < 3; ++c)
+            for (int r = 0; r < 3; ++r)
+                Rn[c * 3 + r] = __fadd_rn(__fadd_rn(__fmul_rn(Rd[r], st->R[c * 3]), __fmul_rn(Rd[3 + r], st->R[c * 3 + 1])),
+                                          __fmul_rn(Rd[6 + r], st->R[c * 3 + 2]));          // R = R_ * R  (icp3d.cu:101)
+        for (int r = 0; r < 3; ++r)
+        {
+            float rt = __fadd_rn(__fadd_rn(__fmul_rn(Rd[r], st->t[0]), __fmul_rn(Rd[3 + r], st->t[1])), __fmul_rn(Rd[6 + r], st->t[2]));
+            tn[r] = __fadd_rn(rt, td[r]);                                                   // t = R_ * t + t_  (icp3d.cu:102)
+        }
+        for (int k = 0; k < 9; ++k) { st->Rd[k] = Rd[k]; st->R[k] = Rn[k]; }
+        for (int k = 0; k < 3; ++k) { st->td[k] = td[k]; st->t[k] = tn[k]; }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+
+static void nn_geometry(const fgoicp_ctx* c, dim3& grid, int& chunk)
+{
+    int qtiles = (int)((c->ns + NN_THREADS * NN_QPT - 1) / (NN_THREADS * NN_QPT));
+    int want_chunks = std::max(1, (4 * c->sm_count + qtiles - 1) / qtiles);
+    chunk = (int)((c->nt + want_chunks - 1) / want_chunks);
+    chunk = ((chunk + NN_TILE - 1) / NN_TILE) * NN_TILE;
+    int nchunks = (int)((c->nt + chunk - 1) / chunk);
+    grid = dim3(qtiles, nchunks);
+}
+
+// enqueue: keys := NN of (pose ? pose*src : src)
+static int enqueue_nn(fgoicp_ctx* c, const float4* d_src, const float* d_pose, int rooted, const int* d_done)
+{
+    dim3 grid; int chunk;
+    nn_geometry(c, grid, chunk);
+    FG_CUDA(cudaMemsetAsync(c->d_nnkey, 0xff, sizeof(unsigned long long) * c->ns, c->stream));
+    if (rooted)
+        k_nn_brute<1><<<grid, NN_THREADS, 0, c->stream>>>(c->d_model, (int)c->nt, chunk, d_src, (int)c->ns, d_pose, c->d_nnkey, d_done);
+    else
+        k_nn_brute<0><<<grid, NN_THREADS, 0, c->stream>>>(c->d_model, (int)c->nt, chunk, d_src, (int)c->ns, d_pose, c->d_nnkey, d_done);
+    FG_CUDA(cudaGetLastError());
+    return FGOICP_OK;
+}
+
+static int upload_pose(fgoicp_ctx* c, const float R[9], const float t[3], float** d_pose_out)
+{
+    int rc = fg::ensure_pinned(c, 256);
+    if (rc) return rc;
+    float* hp = (float*)c->h_pinned;
+    memcpy(hp, R, 9 * sizeof(float));
+    memcpy(hp + 9, t, 3 * sizeof(float));
+    // pose staging area: the tail of the ICP state block (beyond IcpState)
+    float* d_pose = (float*)((char*)c->d_icp + 1024);
+    FG_CUDA(cudaMemcpyAsync(d_pose, hp, 12 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    *d_pose_out = d_pose;
+    return FGOICP_OK;
+}
+
+static_assert(sizeof(IcpState) <= 1024, "IcpState must fit the first KiB of the state block");
+
+extern "C" int fgoicp_sse(fgoicp_ctx* c, const float R[9], const float t[3], float* sse)
+{
+    FG_ARG(c && R && t && sse, "NULL pointer");
+    FG_CUDA(cudaSetDevice(c->device));
+    float* d_pose = nullptr;
+    int rc = upload_pose(c, R, t, &d_pose);
+    if (rc) return rc;
+    rc = enqueue_nn(c, c->d_data, d_pose, 0, nullptr);
+    if (rc) return rc;
+    float* d_out = d_pose + 16;
+    k_sse_reduce<<<1, 1024, 0, c->stream>>>(c->d_nnkey, (int)c->ns, nullptr, d_out);
+    FG_CUDA(cudaGetLastError());
+    float* hp = (float*)c->h_pinned;
+    FG_CUDA(cudaMemcpyAsync(hp + 32, d_out, sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    FG_CUDA(cudaStreamSynchronize(c->stream));
+    *sse = hp[32];
+    return FGOICP_OK;
+}
+
+extern "C" int fgoicp_nn(fgoicp_ctx* c, const float R[9], const float t[3], int rooted, int32_t* idx, float* d2)
+{
+    FG_ARG(c && R && t, "NULL pointer");
+    FG_CUDA(cudaSetDevice(c->device));
+    float* d_pose = nullptr;
+    int rc = upload_pose(c, R, t, &d_pose);
+    if (rc) return rc;
+    rc = enqueue_nn(c, c->d_data, d_pose, rooted, nullptr);
+    if (rc) return rc;
+    size_t ns = c->ns;
+    rc = fg::ensure_scratch(c, ns * 8);
+    if (rc) return rc;
+    int* d_idx = (int*)c->d_scratch;
+    float* d_d2 = (float*)c->d_scratch + ns;
+    k_nn_finish<<<(unsigned)((ns + 255) / 256), 256, 0, c->stream>>>(c->d_nnkey, c->d_model, c->d_data, (int)ns, d_pose, d_idx, d_d2);
+    FG_CUDA(cudaGetLastError());
+    if (idx) FG_CUDA(cudaMemcpyAsync(idx, d_idx, ns * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (d2) FG_CUDA(cudaMemcpyAsync(d2, d_d2, ns * 4, cudaMemcpyDeviceToHost, c->stream));
+    FG_CUDA(cudaStreamSynchronize(c->stream));
+    return FGOICP_OK;
+}
+
+// Runs one ICP to completion on the context stream; results stay in the device state block and
+// are copied to the pinned area.  Used by fgoicp_icp and by the level driver in bnb.cu.
+int fg_icp_run(fgoicp_ctx* c, const float R0[9], const float t0[3], int max_iter, float thr,
+               float* sse, float R[9], float t[3], int* iters)
+{
+    float* d_pose0 = nullptr;
+    int rc = upload_pose(c, R0, t0, &d_pose0);
+    if (rc) return rc;
+    IcpState* st = (IcpState*)c->d_icp;
+    int ns = (int)c->ns;
+    unsigned pb = (unsigned)((ns + 255) / 256);
+    k_icp_init<<<1, 1, 0, c->stream>>>(st, d_pose0, max_iter, thr);
+    k_icp_transform<<<pb, 256, 0, c->stream>>>(c->d_data, c->d_work, ns, d_pose0, nullptr);      // icp3d.cu:85
+    FG_CUDA(cudaGetLastError());
+    IcpState* hst = (IcpState*)((char*)c->h_pinned + 512);
+    rc = fg::ensure_pinned(c, 512 + sizeof(IcpState));
+    if (rc) return rc;
+    hst = (IcpState*)((char*)c->h_pinned + 512);
+    const int* d_done = &st->done;
+    const int burst = 4;     // iterations enqueued between polls of the done flag
+    for (int guard = 0; guard <= max_iter + burst; guard += burst)
+    {
+        for (int b = 0; b < burst; ++b)
+        {
+            k_icp_begin<<<1, 1, 0, c->stream>>>(st);
+            rc = enqueue_nn(c, c->d_work, nullptr, 1, d_done);                                   // icp3d.cu:146
+            if (rc) return rc;
+            k_icp_centroids<<<1, 1024, 0, c->stream>>>(c->d_work, c->d_nnkey, c->d_model, ns, st);
+            k_icp_procrustes<<<1, 1024, 0, c->stream>>>(c->d_work, c->d_nnkey, c->d_model, ns, st);
+            k_icp_transform<<<pb, 256, 0, c->stream>>>(c->d_work, c->d_work, ns, st->Rd, d_done);  // icp3d.cu:100
+            rc = enqueue_nn(c, c->d_data, st->R, 0, d_done);                                     // icp3d.cu:103
+            if (rc) return rc;
+            k_sse_reduce<<<1, 1024, 0, c->stream>>>(c->d_nnkey, ns, st, nullptr);
+            FG_CUDA(cudaGetLastError());
+        }
+        FG_CUDA(cudaMemcpyAsync(hst, st, sizeof(IcpState), cudaMemcpyDeviceToHost, c->stream));
+        FG_CUDA(cudaStreamSynchronize(c->stream));
+        if (hst->done) break;
+    }
+    if (!hst->done)
+    {
+        // the loop above always reaches the head once more after max_iter iterations
+        k_icp_begin<<<1, 1, 0, c->stream>>>(st);
+        FG_CUDA(cudaMemcpyAsync(hst, st, sizeof(IcpState), cudaMemcpyDeviceToHost, c->stream));
+        FG_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    if (!hst->done) { fg::set_error("ICP loop did not terminate"); return FGOICP_ERR_STATE; }
+    if (sse) *sse = hst->out_sse;
+    if (R) memcpy(R, hst->outR, 9 * sizeof(float));
+    if (t) memcpy(t, hst->outT, 3 * sizeof(float));
+    if (iters) *iters = hst->out_iters;
+    return FGOICP_OK;
+}
+
+extern "C" int fgoicp_icp(fgoicp_ctx* c, const float R0[9], const float t0[3], int max_iter, float thr,
+                          float* sse, float R[9], float t[3], int* iters)
+{
+    FG_ARG(c && R0 && t0, "NULL pointer");
+    FG_ARG(max_iter >= 0, "max_iter must be non-negative");
+    FG_CUDA(cudaSetDevice(c->device));
+    return fg_icp_run(c, R0, t0, max_iter, thr, sse, R, t, iters);
+}

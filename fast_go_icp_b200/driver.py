@@ -1,0 +1,256 @@
+"""Host-side mirror of icp::FastGoICP over the C ABI, with the per-level rotation frontier sharded
+across ranks (one process per GPU, torch.distributed for the exchange).
+
+Same algorithm as fast_go_icp_b200/csrc/fgoicp_host.cpp (level-synchronous form of the reference's
+fgoicp/fgoicp.cpp:10-100); the C++ class is the drop-in for src/main.cpp, this module is what
+bench.py and the multi-GPU tests drive.  All host arithmetic that the reference does in fp32 on the
+host (preprocessing, Rotation, overlaps_SO3, restore_translation) is done here in np.float32 with
+the same operation order, so C++ and Python drivers agree bit for bit.
+
+Sharding: at each level the children to evaluate are dealt round-robin to the
+ranks; after the fixed-rotation phase the best SSE is MIN-reduced (all_reduce on a packed
+(sse bits, child index) key -- NCCL over NVLink on GPUs) and the winner's pose broadcast; per-cube
+results are all-gathered so that every rank rebuilds the identical next frontier.  Results are
+independent of the number of ranks by construction.
+"""
+import time
+
+import numpy as np
+
+from . import capi
+
+F = np.float32
+M_INF = F(1e10)
+
+
+def rotation_matrix(x, y, z):
+    """Rotation(x, y, z) of the reference (fgoicp/common.hpp:37-57) in fp32.
+    Returns (R as 9 floats column-major, r)."""
+    x, y, z = F(x), F(y), F(z)
+    r = F(F(F(x * x) + F(y * y)) + F(z * z))
+    R = np.array([1, 0, 0, 0, 1, 0, 0, 0, 1], F)
+    if r > F(1.0):
+        return R, r
+    ww = F(F(1.0) - r)
+    w = F(np.sqrt(ww))
+    wx, xx = F(w * x), F(x * x)
+    wy, xy, yy = F(w * y), F(x * y), F(y * y)
+    wz, xz, yz, zz = F(w * z), F(x * z), F(y * z), F(z * z)
+    two = F(2.0)
+    R = np.array([
+        F(F(F(ww + xx) - yy) - zz), F(two * F(xy - wz)), F(two * F(xz + wy)),
+        F(two * F(xy + wz)), F(F(F(ww - xx) + yy) - zz), F(two * F(yz - wx)),
+        F(two * F(xz - wy)), F(two * F(yz + wx)), F(F(F(ww - xx) - yy) + zz)], F)
+    return R, F(np.sqrt(r))
+
+
+def in_so3(x, y, z):
+    return rotation_matrix(x, y, z)[1] <= F(1.0)
+
+
+def overlaps_so3(x, y, z, span):
+    """RotNode::overlaps_SO3 (fgoicp/common.hpp:99-103)."""
+    x, y, z, span = F(x), F(y), F(z), F(span)
+    r = rotation_matrix(x, y, z)[1]
+    a = F(F(abs(x) + abs(y)) + abs(z))
+    v = F(F(r - F(F(F(2.0) * span) * a)) + F(F(F(3.0) * span) * span))
+    return v <= F(1.0)
+
+
+def preprocess(target, source):
+    """FastGoICP constructor preprocessing (fgoicp/fgoicp.hpp:13-19, fgoicp.cpp:176-287)."""
+    pcs = np.ascontiguousarray(source, F).reshape(-1, 3).copy()
+    pct = np.ascontiguousarray(target, F).reshape(-1, 3).copy()
+
+    def centre(pc):
+        c = np.cumsum(pc, axis=0, dtype=F)[-1] / F(len(pc))     # sequential fp32 sum, index order
+        pc -= c
+        return -c
+
+    off_s = centre(pcs)
+    off_t = centre(pct)
+    s = F(1.0) / np.abs(pcs).max()
+    pcs *= s
+    pct *= s
+    return dict(model=pct, data=pcs, offset_pcs=off_s.astype(F), offset_pct=off_t.astype(F), scale=F(s),
+                bbox_min=pct.min(axis=0), bbox_max=pct.max(axis=0))
+
+
+def restore_translation(R, t, s, offset_pcs, offset_pct):
+    """fgoicp/fgoicp.hpp:87-90: t / s + R * offset_pcs - offset_pct (fp32, left to right)."""
+    R = np.asarray(R, F).reshape(9)
+    out = np.zeros(3, F)
+    for r in range(3):
+        rp = F(F(F(R[r] * offset_pcs[0]) + F(R[3 + r] * offset_pcs[1])) + F(R[6 + r] * offset_pcs[2]))
+        out[r] = F(F(F(t[r]) / s + rp) - offset_pct[r])
+    return out
+
+
+class _Comm:
+    """Minimal collective layer: torch.distributed when a process group is up, identity otherwise."""
+
+    def __init__(self, group=None):
+        self.dist = None
+        self.rank, self.world = 0, 1
+        try:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                self.dist = dist
+                self.group = group
+                self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        except ImportError:
+            pass
+        if self.dist is not None:
+            import torch
+            self.torch = torch
+            self.dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" \
+                else torch.device("cpu")
+
+    def min_key(self, key):
+        """MIN all-reduce of one int64."""
+        if self.dist is None:
+            return key
+        t = self.torch.tensor([key], dtype=self.torch.int64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN, group=self.group)
+        return int(t.item())
+
+    def bcast_f32(self, arr, src):
+        if self.dist is None:
+            return arr
+        t = self.torch.from_numpy(np.ascontiguousarray(arr, F)).to(self.dev)
+        self.dist.broadcast(t, src=src, group=self.group)
+        return t.cpu().numpy()
+
+    def gather_rows(self, local, n_total):
+        """local: rows of this rank's round-robin shard (global rows rank, rank+world, ...).
+        Returns the full (n_total, k) array on every rank."""
+        if self.dist is None:
+            return local
+        k = local.shape[1]
+        per = (n_total + self.world - 1) // self.world
+        buf = np.full((per, k), np.nan, F)
+        buf[:len(local)] = local
+        t = self.torch.from_numpy(buf).to(self.dev)
+        out = [self.torch.empty_like(t) for _ in range(self.world)]
+        self.dist.all_gather(out, t, group=self.group)
+        full = np.empty((per * self.world, k), F)
+        for r in range(self.world):
+            full[r::self.world] = out[r].cpu().numpy()
+        return full[:n_total]
+
+
+class FastGoICP:
+    """Python mirror of icp::FastGoICP (reference fgoicp/fgoicp.hpp:10-108)."""
+
+    def __init__(self, target, source, lut_resolution, mse_threshold, device=0, sampler=None,
+                 flags=capi.BUILD_PACKED, group=None):
+        t0 = time.perf_counter()
+        self.pp = preprocess(target, source)
+        self.ns, self.nt = len(self.pp["data"]), len(self.pp["model"])
+        self.mse_threshold = F(mse_threshold)
+        self.sse_threshold = F(F(self.ns) * self.mse_threshold)            # fgoicp.hpp:23
+        self.ctx = capi.Context(self.pp["model"], self.pp["data"], self.pp["bbox_min"], self.pp["bbox_max"],
+                                lut_resolution, device=device, flags=flags)
+        if sampler is not None:
+            self.ctx.set_sampler(sampler)
+        self.comm = _Comm(group)
+        self.best_sse = M_INF
+        self.best_R = np.array([1, 0, 0, 0, 1, 0, 0, 0, 1], F)
+        self.best_t = np.zeros(3, F)
+        self.stats = dict(bound_evals=0, rot_cubes=0, icp_runs=0, icp_iters=0, levels=0,
+                          ctor_ms=(time.perf_counter() - t0) * 1e3, lut_build_ms=self.ctx.info().build_ms,
+                          ms_bnb_ub=0.0, ms_icp=0.0, ms_bnb_lb=0.0, level_log=[])
+
+    def close(self):
+        self.ctx.close()
+
+    def get_best_error(self):
+        return float(self.best_sse)
+
+    def get_best_transform(self):
+        return self.best_R.copy(), self.best_t.copy()
+
+    def run(self):
+        """Returns (R 3x3 with y = R @ x + t, t) mapping source -> target in original coordinates."""
+        t0 = time.perf_counter()
+        I = np.array([1, 0, 0, 0, 1, 0, 0, 0, 1], F)
+        e, _, _, it = self.ctx.icp(I, np.zeros(3, F), 100, 0.05)           # fgoicp.cpp:12-14
+        self.best_sse = F(e)
+        self.stats["icp_runs"] += 1
+        self.stats["icp_iters"] += it
+        self.stats["initial_icp_sse"] = float(e)
+        self._search_level_synchronous()
+        e, R, t, it = self.ctx.icp(self.best_R, self.best_t, 100, 0.0005)  # fgoicp.cpp:22-23
+        self.best_sse, self.best_R, self.best_t = F(e), R, t
+        self.stats["icp_runs"] += 1
+        self.stats["icp_iters"] += it
+        self.stats["run_ms"] = (time.perf_counter() - t0) * 1e3
+        t_out = restore_translation(R, t, self.pp["scale"], self.pp["offset_pcs"], self.pp["offset_pct"])
+        return R.reshape(3, 3).T.copy(), t_out
+
+    # -- outer search -----------------------------------------------------------------------------
+    def _search_level_synchronous(self):
+        comm = self.comm
+        thr = self.sse_threshold
+        # frontier rows: x, y, z, span, lb, ub
+        frontier = np.array([[0, 0, 0, 1, 0, self.best_sse]], F)
+        while len(frontier):
+            keep = ~(F(self.best_sse) - frontier[:, 4] <= thr)             # fgoicp.cpp:44
+            frontier = frontier[keep]
+            if not len(frontier):
+                break
+            pspan = frontier[0, 3]
+            span = F(pspan / F(2.0))
+            if span < F(0.05):                                             # fgoicp.cpp:53
+                break
+            nxt, ev = [], []
+            for n in frontier:
+                for j in range(8):
+                    cx = F(F(n[0] - span) + F(F(j >> 0 & 1) * pspan))
+                    cy = F(F(n[1] - span) + F(F(j >> 1 & 1) * pspan))
+                    cz = F(F(n[2] - span) + F(F(j >> 2 & 1) * pspan))
+                    if not overlaps_so3(cx, cy, cz, span):                 # fgoicp.cpp:61
+                        continue
+                    row = [cx, cy, cz, span, n[4], n[5]]
+                    (ev if in_so3(cx, cy, cz) else nxt).append(row)        # fgoicp.cpp:62-66
+            ev = np.array(ev, F).reshape(-1, 6)
+            n_ev = len(ev)
+            mine = ev[comm.rank::comm.world, :4]
+
+            ub_l, bt_l, e_l, R_l, t_l, st = self.ctx.so3_level_ub(mine, self.best_sse, thr, self.best_R, self.best_t)
+            # global best: MIN over (sse bits, global child index); ties -> lowest child index
+            if st.best_icp_index >= 0 and e_l < self.best_sse:
+                gidx = comm.rank + comm.world * st.best_icp_index
+                key = (int(np.array([e_l], F).view(np.uint32)[0]) << 32) | gidx
+            else:
+                key = (int(np.array([self.best_sse], F).view(np.uint32)[0]) << 32) | 0xffffffff
+            gkey = comm.min_key(key)
+            if (gkey & 0xffffffff) != 0xffffffff:
+                owner = (gkey & 0xffffffff) % comm.world
+                pose = comm.bcast_f32(np.concatenate([R_l, t_l]), owner)
+                self.best_sse = np.array([gkey >> 32], np.uint32).view(F)[0]
+                self.best_R, self.best_t = pose[:9].copy(), pose[9:].copy()
+            ubt = comm.gather_rows(np.concatenate([ub_l[:, None], bt_l], axis=1), n_ev)
+
+            lb_l, st2 = self.ctx.so3_level_lb(mine, self.best_sse, thr)
+            lb = comm.gather_rows(lb_l[:, None], n_ev)[:, 0] if n_ev else np.zeros(0, F)
+
+            surv = lb < self.best_sse                                      # fgoicp.cpp:92
+            kept = ev[surv].copy()
+            kept[:, 4] = lb[surv]
+            kept[:, 5] = ubt[surv, 0]
+            frontier = np.concatenate([np.array(nxt, F).reshape(-1, 6), kept], axis=0)
+
+            s = self.stats
+            s["levels"] += 1
+            s["rot_cubes"] += len(mine)
+            s["bound_evals"] += int(st.evals) + int(st2.evals)
+            s["icp_runs"] += int(st.n_icp)
+            s["icp_iters"] += int(st.icp_iters)
+            s["ms_bnb_ub"] += st.ms_bnb_ub
+            s["ms_icp"] += st.ms_icp
+            s["ms_bnb_lb"] += st2.ms_bnb_lb
+            s["level_log"].append(dict(span=float(span), cubes=n_ev, local_cubes=len(mine), icps=int(st.n_icp),
+                                       evals=int(st.evals) + int(st2.evals), best_sse=float(self.best_sse),
+                                       survivors=len(frontier), ms_ub=st.ms_bnb_ub, ms_icp=st.ms_icp,
+                                       ms_lb=st2.ms_bnb_lb))

@@ -1,0 +1,111 @@
+// fgoicp/fgoicp.hpp -- icp::FastGoICP, the registration API of fast-go-icp, backed by the
+// B200-native CUDA hot path behind <fgoicp_c.h>.
+//
+// Drop-in for the reference class of the same name (reference fgoicp/fgoicp.hpp:10-108): same
+// constructor (target first, by-value clouds, lut_resolution, mse_threshold), same run() returning
+// (R, t) that maps source -> target in the caller's original coordinates, same accessors.  The
+// reference's src/main.cpp compiles against this header unchanged.
+#ifndef FGOICP_B200_FGOICP_HPP
+#define FGOICP_B200_FGOICP_HPP
+
+#include "common.hpp"
+#include <cstdint>
+#include <memory>
+
+struct fgoicp_ctx;
+
+namespace icp
+{
+    class FastGoICP
+    {
+    public:
+        // How the outer SO(3) search is scheduled.
+        enum class Schedule
+        {
+            Level,      // level-synchronous frontier: every surviving cube of a level is searched concurrently
+            BestFirst   // the reference's serial best-first order (fgoicp.cpp:32-100), one cube at a time
+        };
+
+        struct Options
+        {
+            Schedule schedule = Schedule::Level;
+            int device = 0;
+            int sampler = -1;        // FGOICP_SAMPLER_*, -1 = library default
+            bool verbose_levels = false;
+        };
+
+        struct Stats
+        {
+            std::uint64_t bound_evals = 0;   // (rotation cube x translation cube x data point) evaluations
+            std::uint32_t rot_cubes = 0;     // rotation cubes whose inner searches were run
+            std::uint32_t icp_runs = 0;
+            std::uint32_t icp_iters = 0;
+            std::uint32_t levels = 0;
+            float ctor_ms = 0.f;             // preprocessing + NN-grid build (the reference builds its LUT here too)
+            float lut_build_ms = 0.f;        // device time of the grid build alone
+            float run_ms = 0.f;              // wall time of run()
+            float ms_bnb_ub = 0.f, ms_icp = 0.f, ms_bnb_lb = 0.f;
+        };
+
+        FastGoICP(std::vector<glm::vec3> _pct, std::vector<glm::vec3> _pcs, float _lut_resolution, float _mse_threshold);
+        FastGoICP(std::vector<glm::vec3> _pct, std::vector<glm::vec3> _pcs, float _lut_resolution, float _mse_threshold,
+                  const Options& options);
+        ~FastGoICP();
+        FastGoICP(const FastGoICP&) = delete;
+        FastGoICP& operator=(const FastGoICP&) = delete;
+
+        using Result_t = std::tuple<glm::mat3, glm::vec3>;
+        Result_t run();
+
+        // Interfaces for visualization (reference fgoicp.hpp:32-43)
+        float get_best_error() const { return best_sse; }                 // SSE in the normalised frame
+        Result_t get_best_transform() const { return { best_rotation, best_translation }; }
+        Result_t get_last_transform() const { return { last_rotation, last_translation }; }
+
+        // Extras (not in the reference)
+        float get_best_mse() const { return best_sse / static_cast<float>(ns); }
+        const Stats& stats() const { return stats_; }
+        float scaling() const { return scaling_factor; }
+        fgoicp_ctx* context() const { return ctx_; }
+        const PointCloud& normalised_source() const { return pcs; }
+        const PointCloud& normalised_target() const { return pct; }
+
+    private:
+        PointCloud pcs;   // source (data) cloud, centred and scaled
+        PointCloud pct;   // target (model) cloud, centred and scaled by the same factor
+        size_t ns, nt;
+
+        glm::vec3 offset_pcs;
+        glm::vec3 offset_pct;
+        float scaling_factor;
+        std::array<std::pair<float, float>, 3> target_bounds;
+
+        float best_sse;
+        glm::mat3 best_rotation;
+        glm::vec3 best_translation;
+        float mse_threshold;
+        float sse_threshold;
+
+        glm::mat3 last_rotation{ 1.0f };
+        glm::vec3 last_translation{ 0.0f };
+
+        Options options_;
+        Stats stats_;
+        fgoicp_ctx* ctx_ = nullptr;
+
+        void init(float lut_resolution);
+        glm::vec3 center_point_cloud(PointCloud& pc);
+        float scale_point_clouds(PointCloud& pct, PointCloud& pcs);
+        std::array<std::pair<float, float>, 3> get_point_cloud_ranges(PointCloud& pc);
+        glm::vec3 restore_translation(glm::mat3 _R, glm::vec3 _t)
+        {
+            return _t / scaling_factor + _R * offset_pcs - offset_pct;     // reference fgoicp.hpp:87-90
+        }
+
+        float icp(int max_iter, float thr, const glm::mat3& R0, const glm::vec3& t0, glm::mat3& R, glm::vec3& t);
+        void search_level_synchronous();
+        void search_best_first();
+    };
+}
+
+#endif // FGOICP_B200_FGOICP_HPP

@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 Go-ICP hot path (contract: see the task statement).
+
+Metric (BASELINE.json): cube x point bound evaluations per second, on the 100k-point / 10k-point
+synthetic workload (W5), plus the end-to-end BnB milliseconds of run().
+
+A "step" = one pass of the fused bound kernel over a fixed, unpruned list of
+n_rot (4096) rotation cubes x 32 translation cubes x ns (10,000) data points per GPU, followed -- when
+more than one rank runs -- by the per-level exchange of the real search: a MIN all-reduce of the best
+upper bound over NCCL.  Ranks hold different cube lists (the frontier is sharded; weak scaling).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (CUDA, C ABI)
+  python bench.py --impl reference [...]                         reference arm
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NT, NS, RES, MSE_THR = 100_000, 10_000, 0.005, 1e-4
+N_ROT, T_CUBES = 4096, 32
+ALGO_BYTES_PER_EVAL = 32.0          # one corner-packed cell (8 fp32 texels) gathered per evaluation
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+class ClockSampler:
+    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def profiled_traffic():
+    """dram bytes per launch of the bound kernel from the committed ncu capture, if any."""
+    p = os.path.join(ROOT, "profiles", "bounds_kernel_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get("dram_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+def build_workload(rank):
+    from fast_go_icp_b200 import workloads
+    w = workloads.synthetic_pair(nt=NT, ns=NS, sigma=0.01, seed=1234)
+    rot, tc = workloads.bound_microbench(N_ROT, T_CUBES, seed=7 + 1000 * rank)
+    return w, rot, tc
+
+
+def cpu_baseline_sample(pp, seconds=12.0):
+    """Oracle (CPU restatement) bound evaluations per second on a bounded sample of the same workload.
+    The dense grid is downloaded from the GPU build (bit-identical to the oracle's own, see tests)."""
+    from oracle import oracle as O
+    from fast_go_icp_b200 import workloads
+    lut, dims = pp["lut"], pp["dims"]
+    rot = workloads.rotation_cube_list(64, seed=99)
+    tc = workloads.translation_cube_list(T_CUBES, level=4, seed=98)
+    evals, t0 = 0, time.perf_counter()
+    k = 0
+    while time.perf_counter() - t0 < seconds and k < len(rot):
+        R, _ = O.rotation(*rot[k, :3])
+        O.bounds(lut, dims, pp["bbox_min"], RES, pp["data"], R, float(rot[k, 3]), False, tc)
+        evals += T_CUBES * len(pp["data"])
+        k += 1
+    dt = time.perf_counter() - t0
+    return {"value": evals / dt, "unit": "evals/s", "cores": O.num_threads(), "kind": "port",
+            "sample": "%d rotation cubes x %d translation cubes x %d points (oracle/fgoicp_oracle.c, OpenMP)" % (k, T_CUBES, len(pp["data"]))}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from fast_go_icp_b200 import capi, driver
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    w, rot, tc = build_workload(rank)
+    t0 = time.perf_counter()
+    pp = driver.preprocess(w["model"], w["data"])
+    ctx = capi.Context(pp["model"], pp["data"], pp["bbox_min"], pp["bbox_max"], RES, device=local,
+                       flags=capi.BUILD_PACKED)
+    ctor_ms = (time.perf_counter() - t0) * 1e3
+    info = ctx.info()
+    sampler = {"grid": capi.SAMPLER_GRID, "packed": capi.SAMPLER_PACKED, "tex": capi.SAMPLER_TEX}[args.sampler]
+    if sampler == capi.SAMPLER_TEX:
+        raise SystemExit("--sampler tex needs a context built with BUILD_TEX (use scripts/sampler_sweep.py)")
+    ctx.set_sampler(sampler)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+
+    d_rot, d_tc = torch.from_numpy(rot).to(dev), torch.from_numpy(tc).to(dev)
+    d_lb = torch.empty(N_ROT, T_CUBES, device=dev)
+    d_ub = torch.empty(N_ROT, T_CUBES, device=dev)
+    d_best = torch.empty(1, device=dev)
+    evals_per_step_rank = N_ROT * T_CUBES * NS
+
+    def step():
+        ctx.bounds_multi_dev(d_rot.data_ptr(), N_ROT, False, d_tc.data_ptr(), T_CUBES, d_lb.data_ptr(),
+                             d_ub.data_ptr(), d_best.data_ptr())
+        if world > 1:
+            dist.all_reduce(d_best, op=dist.ReduceOp.MIN)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clk = clocks.stop() if rank == 0 else None
+    if world > 1:
+        tms = torch.tensor([ms], device=dev)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms.item())
+    ms_per_step = ms / args.steps
+    value = evals_per_step_rank * world / (ms_per_step * 1e-3)
+
+    # kernel-only duration for the roofline (events on the launching stream, kernel alone)
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    k0.record()
+    for _ in range(args.steps):
+        ctx.bounds_multi_dev(d_rot.data_ptr(), N_ROT, False, d_tc.data_ptr(), T_CUBES, d_lb.data_ptr(),
+                             d_ub.data_ptr(), 0)
+    k1.record()
+    torch.cuda.synchronize()
+    kernel_ms = k0.elapsed_time(k1) / args.steps
+    peak, peak_src = measured_peak()
+    achieved = ALGO_BYTES_PER_EVAL * evals_per_step_rank / (kernel_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": profiled_traffic(), "kernel": "k_bounds_multi<%s>" % args.sampler,
+                "kernel_ms": kernel_ms, "algorithmic_bytes_per_eval": ALGO_BYTES_PER_EVAL, "peak_source": peak_src}
+
+    # end to end through the C ABI with host buffers (H2D of the cube lists, D2H of lb/ub per step)
+    ctx.set_stream(0)
+    for _ in range(2):
+        ctx.bounds_multi(rot, False, tc)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        lb_h, ub_h = ctx.bounds_multi(rot, False, tc)
+        if world > 1:
+            b = torch.tensor([float(ub_h.min())], device=dev)
+            dist.all_reduce(b, op=dist.ReduceOp.MIN)
+            b.item()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        te = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_s = float(te.item())
+    e2e = {"value": evals_per_step_rank * world * args.steps / e2e_s, "unit": "evals/s",
+           "h2d_bytes_per_step": int(rot.nbytes + tc.nbytes), "d2h_bytes_per_step": int(lb_h.nbytes + ub_h.nbytes)}
+    ctx.close()
+
+    # end-to-end Go-ICP search (the second half of the metric): run() wall time, frontier sharded over ranks
+    bnb = None
+    if not args.no_bnb:
+        g = driver.FastGoICP(w["model"], w["data"], RES, MSE_THR, device=local, flags=capi.BUILD_PACKED)
+        barrier()
+        R, t = g.run()
+        barrier()
+        st = g.stats
+        err_R = float(np.degrees(np.arccos(np.clip((np.trace(R @ w["R_true"].T) - 1) / 2, -1, 1))))
+        bnb = {"bnb_ms": st["run_ms"], "ctor_ms": st["ctor_ms"], "lut_build_ms": st["lut_build_ms"],
+               "best_mse": float(g.best_sse) / NS, "rot_err_deg": err_R,
+               "t_err": float(np.linalg.norm(t - w["t_true"])), "rot_cubes_local": st["rot_cubes"],
+               "bound_evals_local": st["bound_evals"], "icp_runs_local": st["icp_runs"],
+               "ms_bnb_ub": st["ms_bnb_ub"], "ms_icp": st["ms_icp"], "ms_bnb_lb": st["ms_bnb_lb"],
+               "levels": st["level_log"]}
+        if rank == 0 and world == 1 and not args.no_cpu:
+            lut, dims = g.ctx.lut_download()
+            pp["lut"], pp["dims"] = lut, dims
+        g.close()
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu and "lut" in pp:
+        cpu = cpu_baseline_sample(pp, seconds=args.cpu_seconds)
+
+    if rank == 0:
+        out = {"metric": "cube x point bound evals/s", "value": value, "unit": "evals/s", "n_gpus": world,
+               "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+               "data": "synthetic",
+               "config": {"workload": "W5 synthetic: 100k-point model / 10k-point data, lut_resolution 0.005; "
+                                      "step = %d rotation cubes x %d translation cubes x %d points per GPU, fix_rot=false, "
+                                      "then MIN all-reduce of the best upper bound" % (N_ROT, T_CUBES, NS),
+                          "sampler": args.sampler, "grid_dims": list(info.dims),
+                          "grid_bytes": int(info.packed_bytes if args.sampler == "packed" else info.grid_bytes),
+                          "l2": "gathered grid (%.2f GB) is larger than L2 (126 MB); no flush needed" %
+                                ((info.packed_bytes if args.sampler == "packed" else info.grid_bytes) / 1e9),
+                          "parallelism": "frontier-sharded x%d" % world},
+               "e2e": e2e, "gpu_launches": 2 * args.steps, "clocks": clk, "roofline": roofline,
+               "cpu_baseline": cpu, "ctor_ms": ctor_ms, "lut_build_ms": info.build_ms}
+        if bnb:
+            out["bnb"] = bnb
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_reference(args):
+    """Reference arm.  The reference has NO CPU implementation: its bound operator is
+    Registration::compute_sse_error (CUDA).  When oracle/_ref/libfgoicp_ref.so exists (the unmodified
+    reference sources compiled by oracle/build_ref.py) and a GPU is visible, that operator is timed as it
+    ships -- host loop on one CPU thread, kernels on GPU 0.  Otherwise the oracle port is timed on the
+    host cores.  Each step is a bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from fast_go_icp_b200 import workloads
+    from oracle import ref as REF
+    w = workloads.synthetic_pair(nt=NT, ns=NS, sigma=0.01, seed=1234)
+    n_rot_sample = args.ref_rot
+    rot = workloads.rotation_cube_list(n_rot_sample, seed=7)
+    tc = workloads.translation_cube_list(T_CUBES, level=4, seed=8)
+    evals_per_step = n_rot_sample * T_CUBES * NS
+    kind, cores, sample = None, None, None
+    use_ref = False
+    if REF.available():
+        try:
+            import torch
+            use_ref = torch.cuda.is_available()
+        except Exception:
+            use_ref = False
+    if use_ref:
+        t0 = time.perf_counter()
+        r = REF.Reference(w["model"], w["data"], RES, MSE_THR)
+        ctor_ms = (time.perf_counter() - t0) * 1e3
+
+        def step():
+            for k in range(n_rot_sample):
+                r.bounds(rot[k], False, tc)
+        kind, cores = "reference", 1
+        sample = ("unmodified reference Registration::compute_sse_error (oracle/_ref, CUDA on GPU 0, 1 host thread): "
+                  "%d rotation cubes x %d translation cubes x %d points per step; reference ctor (LUT build) %.0f ms"
+                  % (n_rot_sample, T_CUBES, NS, ctor_ms))
+    else:
+        from oracle import oracle as O
+        pp = O.preprocess(w["model"], w["data"])
+        # a coarser grid keeps the CPU brute-force build bounded; the evaluation cost per point is unchanged
+        lut, dims = O.lut_build(pp["model"][::50], pp["bbox_min"], pp["bbox_max"], 0.02)
+
+        def step():
+            for k in range(n_rot_sample):
+                R, _ = O.rotation(*rot[k, :3])
+                O.bounds(lut, dims, pp["bbox_min"], 0.02, pp["data"], R, float(rot[k, 3]), False, tc)
+        kind, cores = "port", O.num_threads()
+        sample = ("oracle port (oracle/fgoicp_oracle.c, OpenMP, grid 0.02): %d rotation cubes x %d translation "
+                  "cubes x %d points per step" % (n_rot_sample, T_CUBES, NS))
+    for _ in range(max(args.warmup, 1)):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    v = evals_per_step * args.steps / dt
+    out = {"impl": "reference", "metric": "cube x point bound evals/s", "value": v, "unit": "evals/s",
+           "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": max(args.warmup, 1),
+           "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "W5 synthetic: 100k-point model / 10k-point data, lut_resolution 0.005; bounded sample"},
+           "cpu_baseline": {"value": v, "unit": "evals/s", "cores": cores, "kind": kind, "sample": sample},
+           "e2e": {"value": v, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--sampler", default="packed", choices=["packed", "grid", "tex"])
+    ap.add_argument("--no-bnb", action="store_true", help="skip the end-to-end run() measurement")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline sample")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--ref-rot", type=int, default=16, help="rotation cubes per reference-arm step")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,197 @@
+"""GPU parity tests: every C-ABI entry point against the CPU oracle on the same seeded inputs, and --
+when oracle/_ref/libfgoicp_ref.so is present -- against the unmodified reference kernels.
+
+Tolerances (stated per test):
+  * grid cells, NN indices, per-point squared distances: bit-exact;
+  * per-cube bounds and SSE: sums are fp64-accumulated on both sides and rounded once, so they agree
+    to 1 ulp of fp32 (rtol 2.4e-7), far inside BASELINE.json's "stated fp32 tolerance";
+  * against the reference's texture unit and CUB reduction order: rtol 2e-4 on bounds.
+"""
+import numpy as np
+import pytest
+
+from fast_go_icp_b200 import capi, workloads
+from oracle import oracle as O
+from oracle import ref as REF
+
+pytestmark = pytest.mark.gpu
+ULP = 2.4e-7
+
+
+def _lut(pp):
+    return pp["lut"], pp["dims"], pp["bbox_min"], float(pp["res"])
+
+
+def test_grid_build_is_bit_exact(small_problem, gpu_ctx):
+    pp = small_problem
+    got, dims = gpu_ctx.lut_download()
+    assert np.array_equal(dims, pp["dims"])
+    assert np.array_equal(got, pp["lut"])           # hierarchical build == oracle brute force, every cell
+    brute = capi.Context(pp["model"], pp["data"], pp["bbox_min"], pp["bbox_max"], float(pp["res"]),
+                         flags=capi.BUILD_BRUTE_LUT)
+    assert np.array_equal(brute.lut_download()[0], got)
+    brute.close()
+
+
+def test_samplers(small_problem, gpu_ctx):
+    pp = small_problem
+    rng = np.random.default_rng(10)
+    q = rng.uniform(-1.4, 1.4, (20000, 3)).astype(np.float32)
+    want = O.lut_sample(*_lut(pp), q)
+    g = gpu_ctx.lut_sample(q, capi.SAMPLER_GRID)
+    p = gpu_ctx.lut_sample(q, capi.SAMPLER_PACKED)
+    t = gpu_ctx.lut_sample(q, capi.SAMPLER_TEX)
+    assert np.array_equal(g, want)                  # manual filter: bit-exact with the oracle
+    assert np.array_equal(p, g)                     # corner-packed layout: same arithmetic, same bits
+    # hardware filter: same semantics, internal arithmetic differs in the last bits
+    scale = np.maximum(np.abs(want), 1e-6)
+    assert np.max(np.abs(t - want) / scale) < 2e-3
+    assert np.median(np.abs(t - want) / scale) < 1e-6
+
+
+def test_device_sin_table(gpu_ctx):
+    spans = np.array([0.5, 0.25, 0.125, 0.0625], np.float32)
+    dev = gpu_ctx.rot_sin(spans)
+    host = np.sin((spans * np.float32(1.732050807568877)) * np.float32(3.141592653589793) / np.float32(2)).astype(np.float32)
+    assert np.max(np.abs(dev - host)) <= 2 * np.spacing(np.float32(1.0))
+
+
+@pytest.mark.parametrize("fix_rot", [True, False])
+@pytest.mark.parametrize("sampler", [capi.SAMPLER_GRID, capi.SAMPLER_PACKED])
+def test_bounds_batch_vs_oracle(small_problem, gpu_ctx, fix_rot, sampler):
+    pp = small_problem
+    gpu_ctx.set_sampler(sampler)
+    for k, (rot, span) in enumerate([((0.1, -0.2, 0.05), 0.125), ((0.5, 0.5, -0.5), 0.5), ((0, 0, 0), 0.0625)]):
+        R, _ = O.rotation(*np.float32(rot))
+        for T in (1, 7, 32, 45):
+            tc = workloads.translation_cube_list(T, level=1 + (k + T) % 4, seed=T)
+            lb, ub = gpu_ctx.bounds_batch(R, span, fix_rot, tc)
+            wl, wu = O.bounds(*_lut(pp), pp["data"], R, span, fix_rot, tc)
+            assert np.allclose(ub, wu, rtol=ULP, atol=0) and np.allclose(lb, wl, rtol=ULP, atol=0)
+    gpu_ctx.set_sampler(capi.SAMPLER_PACKED)
+
+
+def test_bounds_multi_matches_batch_and_is_deterministic(small_problem, gpu_ctx):
+    rot = workloads.rotation_cube_list(40, seed=3)
+    rot[:10, 3] = 0.25
+    _, tc = workloads.bound_microbench(40, 32, seed=5)
+    for fix_rot in (True, False):
+        lb, ub = gpu_ctx.bounds_multi(rot, fix_rot, tc)
+        lb2, ub2 = gpu_ctx.bounds_multi(rot, fix_rot, tc)
+        assert np.array_equal(lb, lb2) and np.array_equal(ub, ub2)
+        for r in (0, 9, 39):
+            R, _ = O.rotation(*rot[r, :3])
+            l1, u1 = gpu_ctx.bounds_batch(R, float(rot[r, 3]), fix_rot, tc[r])
+            assert np.allclose(l1, lb[r], rtol=ULP) and np.allclose(u1, ub[r], rtol=ULP)
+
+
+def test_bounds_multi_dev_and_best_ub(small_problem, gpu_ctx):
+    import torch
+    rot = workloads.rotation_cube_list(300, seed=8)
+    _, tc = workloads.bound_microbench(300, 32, seed=9)
+    lb, ub = gpu_ctx.bounds_multi(rot, True, tc)
+    d_rot, d_tc = torch.from_numpy(rot).cuda(), torch.from_numpy(tc).cuda()
+    d_lb, d_ub = torch.empty(300, 32, device="cuda"), torch.empty(300, 32, device="cuda")
+    d_best = torch.empty(1, device="cuda")
+    gpu_ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    gpu_ctx.bounds_multi_dev(d_rot.data_ptr(), 300, True, d_tc.data_ptr(), 32, d_lb.data_ptr(), d_ub.data_ptr(),
+                             d_best.data_ptr())
+    torch.cuda.synchronize()
+    gpu_ctx.set_stream(0)
+    assert np.array_equal(d_lb.cpu().numpy(), lb) and np.array_equal(d_ub.cpu().numpy(), ub)
+    assert float(d_best.item()) == float(ub.min())
+
+
+def test_nn_indices_bit_exact(small_problem, gpu_ctx):
+    pp = small_problem
+    for rot, t in [((0.2, 0.1, -0.1), (0.05, -0.02, 0.01)), ((0, 0, 0), (0, 0, 0)), ((-0.4, 0.3, 0.2), (0.4, 0.3, -0.5))]:
+        R, _ = O.rotation(*np.float32(rot))
+        t = np.float32(t)
+        for rooted in (False, True):
+            idx, d2 = gpu_ctx.nn(R, t, rooted)
+            widx, wd2 = O.nn(pp["model"], pp["data"], R, t, rooted)
+            assert np.array_equal(idx, widx)
+            assert np.array_equal(d2, wd2)
+        sse = gpu_ctx.sse(R, t)
+        assert sse == O.sse(pp["model"], pp["data"], R, t)
+
+
+def test_nn_duplicate_points_lowest_index_wins():
+    rng = np.random.default_rng(12)
+    base = rng.uniform(-0.8, 0.8, (700, 3)).astype(np.float32)
+    model = np.concatenate([base, base[::-1], base])          # every point three times
+    data = base[:257] + np.float32(1e-3)
+    ctx = capi.Context(model, data, model.min(0), model.max(0), 0.1, flags=0)
+    I = np.eye(3, dtype=np.float32).ravel()
+    for rooted in (False, True):
+        idx, _ = ctx.nn(I, np.zeros(3, np.float32), rooted)
+        widx, _ = O.nn(model, data, I, np.zeros(3, np.float32), rooted)
+        assert np.array_equal(idx, widx) and np.all(idx < 700)
+    ctx.close()
+
+
+def test_icp_vs_oracle(small_problem, gpu_ctx):
+    pp = small_problem
+    I = np.eye(3, dtype=np.float32).ravel()
+    for R0, t0, thr in [(I, np.zeros(3, np.float32), 0.05), (O.rotation(0.3, 0.1, -0.2)[0], np.float32([0.1, 0, -0.1]), 0.005),
+                        (O.rotation(-0.1, 0.05, 0.1)[0], np.float32([0.02, 0.03, 0.0]), 0.0005)]:
+        e, R, t, it = gpu_ctx.icp(R0, t0, 100, thr)
+        we, wR, wt, wit = O.icp(pp["model"], pp["data"], 100, thr, R0, t0)
+        assert it == wit
+        assert abs(e - we) <= 1e-6 * we                        # BASELINE.json: MSE within 1e-6 relative
+        assert np.allclose(R, wR, atol=2e-6) and np.allclose(t, wt, atol=2e-6)
+    e, R, t, it = gpu_ctx.icp(I, np.zeros(3, np.float32), 0, 0.05)   # max_iter = 0: returns the seed state
+    assert it == 0
+
+
+@pytest.mark.parametrize("fix_rot", [True, False])
+def test_bnb_r3_vs_oracle(small_problem, gpu_ctx, fix_rot):
+    pp = small_problem
+    thr = len(pp["data"]) * 1e-4
+    cubes = np.float32([[0.25, -0.25, 0.25, 0.25], [0.0625, 0.1875, -0.0625, 0.0625], [-0.5, 0.5, 0.5, 0.5],
+                        [0.125, 0.125, 0.125, 0.125], [-0.1875, 0.0625, 0.3125, 0.0625]])
+    for best_sse in (1e10, 5.0, 0.5):
+        ub, bt, ev = gpu_ctx.bnb_r3_batch(cubes, fix_rot, best_sse, thr)
+        for i, c in enumerate(cubes):
+            wub, wbt, wev, _ = O.bnb_r3(pp["model"], pp["data"], *_lut(pp), c, fix_rot, best_sse, thr)
+            assert ev[i] == wev, (i, best_sse)                 # same traversal: same number of evaluations
+            assert np.isclose(ub[i], wub, rtol=ULP, atol=0) and np.array_equal(bt[i], wbt)
+        u1, t1, e1 = gpu_ctx.bnb_r3(cubes[1], fix_rot, best_sse, thr)
+        assert u1 == ub[1] and np.array_equal(t1, bt[1]) and e1 == ev[1]
+
+
+@pytest.mark.skipif(not REF.available(), reason="oracle/_ref not built")
+def test_against_unmodified_reference_kernels(small_problem, gpu_ctx):
+    """The reference's own CUDA code (real tex3D, per-cube launches, thrust reductions) on the same clouds."""
+    pp = small_problem
+    raw = pp["raw"]
+    ref = REF.Reference(raw["model"], raw["data"], float(pp["res"]), 1e-4)
+    rp = ref.preprocessed()
+    for k in ("model", "data", "offset_pcs", "offset_pct", "bbox_min", "bbox_max"):
+        assert np.array_equal(rp[k], pp[k]), k                 # preprocessing: bit-exact
+    assert rp["scale"] == pp["scale"]
+    rlut, rdims = ref.lut()
+    assert np.array_equal(rdims, pp["dims"])
+    assert np.array_equal(rlut, pp["lut"])                     # every LUT cell bit-exact vs the reference kernel
+    rng = np.random.default_rng(21)
+    q = rng.uniform(-1.2, 1.2, (20000, 3)).astype(np.float32)
+    assert np.array_equal(ref.lut_sample(q), gpu_ctx.lut_sample(q, capi.SAMPLER_TEX))   # same hardware path
+    # bounds: reference (texture + CUB fp32 tree) vs ours (manual filter + fp64 sums)
+    gpu_ctx.set_sampler(capi.SAMPLER_PACKED)
+    for rot in ([0.25, -0.25, 0.25, 0.25], [0.0625, 0.1875, -0.0625, 0.0625]):
+        rot = np.float32(rot)
+        R, _ = O.rotation(*rot[:3])
+        tc = workloads.translation_cube_list(32, level=3, seed=4)
+        for fix_rot in (True, False):
+            rl, ru = ref.bounds(rot, fix_rot, tc)
+            l, u = gpu_ctx.bounds_batch(R, float(rot[3]), fix_rot, tc)
+            assert np.allclose(u, ru, rtol=2e-4, atol=1e-5) and np.allclose(l, rl, rtol=2e-4, atol=1e-5)
+    # exact SSE and ICP
+    R, _ = O.rotation(0.2, 0.1, -0.1)
+    t = np.float32([0.05, -0.02, 0.01])
+    assert abs(ref.sse(R, t) - gpu_ctx.sse(R, t)) <= 2e-6 * gpu_ctx.sse(R, t)
+    I = np.eye(3, dtype=np.float32).ravel()
+    re_, rR, rt = ref.icp(I, np.zeros(3, np.float32), 100, 0.05)
+    e, R1, t1, _ = gpu_ctx.icp(I, np.zeros(3, np.float32), 100, 0.05)
+    assert abs(re_ - e) <= 1e-5 * e and np.allclose(rR, R1, atol=1e-5) and np.allclose(rt, t1, atol=1e-5)
+    ref.close()

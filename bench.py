@@ -159,7 +159,11 @@ def run_ours(args):
     if sampler == capi.SAMPLER_TEX:
         raise SystemExit("--sampler tex needs a context built with BUILD_TEX (use scripts/sampler_sweep.py)")
     ctx.set_sampler(sampler)
-    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    # our kernels and torch's events/collectives must share one stream: a dedicated non-default stream
+    # (the legacy default stream has handle 0, which the C ABI reads as "use the context's own stream")
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)
 
     d_rot, d_tc = torch.from_numpy(rot).to(dev), torch.from_numpy(tc).to(dev)
     d_lb = torch.empty(N_ROT, T_CUBES, device=dev)

@@ -92,19 +92,22 @@ namespace fg
 // canonical device arithmetic
 // ---------------------------------------------------------------------------------------------
 
-// dx*dx + dy*dy + dz*dz  ->  FMUL, FFMA, FFMA   (reference registration.cu:154-160, 248-254)
+// dx*dx + dy*dy + dz*dz  (reference registration.cu:154-160, 248-254; glm::dot in icp3d.cu:20).
+// SASS of every reference kernel: FMUL dy,dy ; FFMA dx,dx,. ; FFMA dz,dz,.  -- nvcc keeps the SECOND
+// product as the plain multiply and fuses the first and third.
 __device__ __forceinline__ float fg_sq3(float dx, float dy, float dz)
 {
-    return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+    return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
 }
 
-// glm mat3 * vec3 (column-major R) -> FMUL, FFMA, FFMA per component (registration.cu:20, 34)
+// glm mat3 * vec3 (column-major R), reference registration.cu:20, 34 and icp3d.cu:35.
+// SASS: FMUL m1r,p.y ; FFMA m0r,p.x,. ; FFMA m2r,p.z,.  (same association as fg_sq3)
 __device__ __forceinline__ float3 fg_rotate(const float* R, float px, float py, float pz)
 {
     float3 q;
-    q.x = __fmaf_rn(R[6], pz, __fmaf_rn(R[3], py, __fmul_rn(R[0], px)));
-    q.y = __fmaf_rn(R[7], pz, __fmaf_rn(R[4], py, __fmul_rn(R[1], px)));
-    q.z = __fmaf_rn(R[8], pz, __fmaf_rn(R[5], py, __fmul_rn(R[2], px)));
+    q.x = __fmaf_rn(R[6], pz, __fmaf_rn(R[0], px, __fmul_rn(R[3], py)));
+    q.y = __fmaf_rn(R[7], pz, __fmaf_rn(R[1], px, __fmul_rn(R[4], py)));
+    q.z = __fmaf_rn(R[8], pz, __fmaf_rn(R[2], px, __fmul_rn(R[5], py)));
     return q;
 }
 

@@ -540,7 +540,7 @@ extern "C" int fgoicp_ctx_create(const float* model_xyz, size_t nt, const float*
     for (size_t i = 0; i < ns; ++i)
     {
         float x = data_xyz[3 * i], y = data_xyz[3 * i + 1], z = data_xyz[3 * i + 2];
-        float r2 = fmaf(z, z, fmaf(y, y, x * x));     // registration.cu:37-39 (SASS: FMUL, FFMA, FFMA)
+        float r2 = fmaf(z, z, fmaf(x, x, y * y));     // registration.cu:37-39 (SASS: FMUL y,y; FFMA x,x; FFMA z,z)
         hd[i] = make_float4(x, y, z, r2);
     }
     float4* d_P = nullptr;

@@ -8,13 +8,18 @@ import numpy as np
 
 
 def bumpy_surface(n, rng):
-    """n points on r(theta, phi) = 0.6 + 0.15 sin(3 theta) cos(2 phi) + 0.1 cos(5 phi), directions
-    uniform on the sphere, scaled so that max |coordinate| = 0.9 (asymmetric -> unique optimum)."""
+    """n points on r(theta, phi) = 0.6 + 0.15 sin(3 theta) cos(2 phi) + 0.1 cos(5 phi) + 0.08 sin(theta) sin(phi),
+    directions uniform on the sphere, scaled so that max |coordinate| = 0.9.
+
+    The first three terms are SURVEY.md section 8d's formula; on its own it is invariant under a half-turn
+    about the x axis (theta -> pi - theta, phi -> -phi), i.e. it has TWO globally optimal registrations 180
+    degrees apart.  The last term breaks that symmetry so that the optimum is unique and pose recovery
+    can be asserted."""
     v = rng.normal(size=(n, 3))
     v /= np.linalg.norm(v, axis=1, keepdims=True)
     theta = np.arccos(np.clip(v[:, 2], -1.0, 1.0))
     phi = np.arctan2(v[:, 1], v[:, 0])
-    r = 0.6 + 0.15 * np.sin(3 * theta) * np.cos(2 * phi) + 0.1 * np.cos(5 * phi)
+    r = 0.6 + 0.15 * np.sin(3 * theta) * np.cos(2 * phi) + 0.1 * np.cos(5 * phi) + 0.08 * np.sin(theta) * np.sin(phi)
     p = v * r[:, None]
     return (p * (0.9 / np.abs(p).max())).astype(np.float32)
 
@@ -74,19 +79,16 @@ def translation_cube_list(T=32, level=4, seed=11):
 
 
 def bound_microbench(n_rot=4096, T=32, seed=7):
-    """The pure-throughput bound workload: n_rot rotation cubes x T translation cubes each, no pruning
-    (SURVEY.md section 8d, W5).  Each rotation cube gets its own translation list (mixed depths 2..4)."""
+    """The pure-throughput bound workload: n_rot leaf rotation cubes x T leaf translation cubes each, no
+    pruning.  Translation cubes are the leaf cubes (half-span 0.0625) whose centres
+    lie in [-0.3125, 0.3125]^3 -- where a real search spends its deep levels, and where nearly every
+    transformed point falls INSIDE the model's bounding box, so every evaluation is a genuine scattered
+    gather (nothing is served by the clamped border cells)."""
     rot = rotation_cube_list(n_rot, seed)
     rng = np.random.default_rng(seed + 1)
+    span = 0.0625
+    idx = rng.integers(5, 11, size=(n_rot, T, 3))                 # of 16 leaf cells per axis
     tc = np.empty((n_rot, T, 4), np.float32)
-    for level, frac in ((4, 1.0),):
-        span = 2.0 ** -level
-        idx = rng.integers(0, 2 ** level, size=(n_rot, T, 3))
-        tc[..., :3] = -1.0 + (2 * idx + 1) * span
-        tc[..., 3] = span
-        del frac
-    # translations near the origin matter most in a real search: pull half of them into [-0.5, 0.5]^3
-    half = rng.random((n_rot, T)) < 0.5
-    tc[half, :3] *= 0.5
-    tc[half, :3] = (np.round((tc[half, :3] + 1.0) / (2 * 0.0625) - 0.5) + 0.5) * (2 * 0.0625) - 1.0
+    tc[..., :3] = -1.0 + (2 * idx + 1) * span
+    tc[..., 3] = span
     return rot, tc

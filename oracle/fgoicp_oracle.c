@@ -89,18 +89,21 @@ ORC_API void orc_set_num_threads(int n)
 /* Canonical device arithmetic (association read from the reference's sm_100 SASS)            */
 /* ------------------------------------------------------------------------------------------ */
 
-/* dx*dx + dy*dy + dz*dz  ->  FMUL, FFMA, FFMA   (registration.cu:154-160, 248-254) */
+/* dx*dx + dy*dy + dz*dz  (registration.cu:154-160, 248-254; glm::dot in icp3d.cu:20).
+ * SASS of every reference kernel: FMUL dy,dy ; FFMA dx,dx,. ; FFMA dz,dz,.  -- nvcc keeps the SECOND
+ * product as the plain multiply and fuses the first and third. */
 static inline float orc_sq3(float dx, float dy, float dz)
 {
-    return fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+    return fmaf(dz, dz, fmaf(dx, dx, dy * dy));
 }
 
-/* glm mat3 * vec3 + t in device code -> FMUL, FFMA, FFMA, FADD  (registration.cu:20, 34) */
+/* glm mat3 * vec3 + t in device code (registration.cu:20, 34; icp3d.cu:35).
+ * SASS: FMUL m1r,p.y ; FFMA m0r,p.x,. ; FFMA m2r,p.z,. ; FADD t  (same association as orc_sq3). */
 static inline void orc_xform(const float* R, const float* t, const float* p, float* q)
 {
     int r;
     for (r = 0; r < 3; ++r)
-        q[r] = fmaf(R[6 + r], p[2], fmaf(R[3 + r], p[1], R[r] * p[0])) + t[r];
+        q[r] = fmaf(R[6 + r], p[2], fmaf(R[r], p[0], R[3 + r] * p[1])) + t[r];
 }
 
 /* ------------------------------------------------------------------------------------------ */

@@ -21,7 +21,9 @@ def main(out_path, nt=100_000, ns=10_000, res=0.005, n_rot=2048, T=32, steps=5):
     dev = torch.device("cuda", 0)
     d_rot, d_tc = torch.from_numpy(rot).to(dev), torch.from_numpy(tc).to(dev)
     d_lb, d_ub = torch.empty(n_rot, T, device=dev), torch.empty(n_rot, T, device=dev)
-    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)
     out = {"dims": list(info.dims), "grid_MB": info.grid_bytes / 1e6, "packed_MB": info.packed_bytes / 1e6,
            "build_ms": info.build_ms, "n_rot": n_rot, "T": T, "ns": ns, "results": []}
     ref = None

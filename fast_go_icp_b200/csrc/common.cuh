@@ -49,6 +49,16 @@ struct LutDev
     float ox, oy, oz;         // -bbox_min
 };
 
+// Uniform cell grid over the model cloud in LUT space; cells along x are consecutive in the CSR order,
+// so a run of cells of one (y, z) row is one contiguous range of points.
+struct CellGrid
+{
+    const int* start;      // [ncell + 1] CSR offsets into the sorted points
+    const float4* pts;     // sorted points (LUT-space copy or original-coordinate copy)
+    int nx, ny, nz;
+    float h, inv_h;        // cell size
+};
+
 struct fgoicp_ctx
 {
     int device = 0;
@@ -75,6 +85,14 @@ struct fgoicp_ctx
     size_t scratch_bytes = 0;
     void* h_pinned = nullptr;
     size_t pinned_bytes = 0;
+
+    // uniform cell grid over the model cloud (CSR): built once, used by the grid build and by NN search
+    int* d_cell_start = nullptr;              // [ncell + 1]
+    float4* d_cell_P = nullptr;               // points in LUT space (model - bbox_min), sorted by cell
+    float4* d_cell_M = nullptr;               // same order, original coordinates, w = original index
+    int cnx = 0, cny = 0, cnz = 0;
+    float cell_h = 0.f, cell_inv_h = 0.f;
+    int nn_mode = 0;                          // 0: cell-grid search, 1: tiled brute force (test hook)
 
     // ICP state
     float4* d_work = nullptr;                 // working copy W  [ns]
@@ -162,10 +180,13 @@ __device__ __forceinline__ void fg_tex_axis(float u, int dim, int& i, float& alp
 {
     u = fmaxf(u, -2.0f);                       // also maps NaN to -2
     u = fminf(u, (float)dim + 2.0f);
+    // Measured on B200 (scripts/tex_conformance.py, 65,536-step sweep across a texel): the texture unit
+    // keeps the weight in 1.8 fixed point with ROUND-HALF-UP: alpha*256 = floor(uB*256 + 0.5).
+    // u*256 is exact (power-of-two scale) and so is the +0.5 for |u*256| < 2^23.
 #if FG_WEIGHT_TRUNC
     int xf = __float2int_rd(__fmul_rn(u, 256.0f)) - 128;
 #else
-    int xf = __float2int_rn(__fmul_rn(u, 256.0f)) - 128;
+    int xf = __float2int_rd(__fadd_rn(__fmul_rn(u, 256.0f), 0.5f)) - 128;
 #endif
     i = xf >> 8;
     alpha = __fmul_rn((float)(xf & 255), 1.0f / 256.0f);

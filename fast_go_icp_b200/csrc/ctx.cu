@@ -111,13 +111,6 @@ k_lut_brute(float* __restrict__ out, int dx, int dy, int dz, float res,
 // grid; the brick gathers candidates cell by cell and takes the exact minimum with the same
 // per-pair arithmetic as the brute-force kernel -- the result is bit-identical to it.
 
-struct CellGrid
-{
-    const int* start;      // [ncell + 1] CSR offsets into sorted points
-    const float4* pts;     // model points in LUT space, sorted by cell
-    int nx, ny, nz;
-    float h, inv_h;        // cell size
-};
 
 __global__ void k_cell_index(const float4* __restrict__ P, int nt, CellGrid g, int* __restrict__ cell_of, int* __restrict__ counts)
 {
@@ -166,14 +159,16 @@ __global__ void __launch_bounds__(1024) k_scan_counts(const int* __restrict__ co
     if (threadIdx.x == 0) start[n] = carry;
 }
 
-__global__ void k_cell_scatter(const float4* __restrict__ P, int nt, const int* __restrict__ cell_of,
-                               const int* __restrict__ start, int* __restrict__ fill, float4* __restrict__ sorted)
+__global__ void k_cell_scatter(const float4* __restrict__ P, const float4* __restrict__ M, int nt,
+                               const int* __restrict__ cell_of, const int* __restrict__ start,
+                               int* __restrict__ fill, float4* __restrict__ sortedP, float4* __restrict__ sortedM)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nt) return;
     int c = cell_of[i];
     int slot = start[c] + atomicAdd(&fill[c], 1);
-    sorted[slot] = P[i];
+    sortedP[slot] = P[i];
+    sortedM[slot] = M[i];
 }
 
 #define BRICK 8
@@ -380,35 +375,52 @@ static int build_grid_brute(fgoicp_ctx* c, const float4* d_P)
 
 struct Level { int dx, dy, dz; float ox, oy, oz, s; float* d; };
 
+// Bins the model cloud (LUT-space copy d_P, original copy c->d_model) into the uniform cell grid kept in
+// the context.  Cell size: about four points per occupied cell for a surface-like cloud, at least two grid
+// nodes wide, at most 256 cells per axis.
+static int build_cell_grid(fgoicp_ctx* c, const float4* d_P)
+{
+    const LutDev& L = c->lut;
+    cudaStream_t st = c->stream;
+    int nt = (int)c->nt;
+    float ext[3] = { L.dx * c->res, L.dy * c->res, L.dz * c->res };
+    float max_ext = std::max(ext[0], std::max(ext[1], ext[2]));
+    float area = ext[0] * ext[1] + ext[1] * ext[2] + ext[0] * ext[2];     // half the bounding-box surface
+    float h = std::sqrt(4.0f * area / (float)nt);
+    h = std::max(h, std::max(max_ext / 256.0f, 2.0f * c->res));
+    c->cell_h = h; c->cell_inv_h = 1.0f / h;
+    c->cnx = std::max(1, (int)std::ceil(ext[0] / h)); c->cny = std::max(1, (int)std::ceil(ext[1] / h)); c->cnz = std::max(1, (int)std::ceil(ext[2] / h));
+    int ncell = c->cnx * c->cny * c->cnz;
+    int *d_cell_of = nullptr, *d_counts = nullptr, *d_fill = nullptr;
+    FG_CUDA(cudaMalloc(&d_cell_of, sizeof(int) * nt));
+    FG_CUDA(cudaMalloc(&d_counts, sizeof(int) * ncell));
+    FG_CUDA(cudaMalloc(&d_fill, sizeof(int) * ncell));
+    FG_CUDA(cudaMalloc(&c->d_cell_start, sizeof(int) * (ncell + 1)));
+    FG_CUDA(cudaMalloc(&c->d_cell_P, sizeof(float4) * nt));
+    FG_CUDA(cudaMalloc(&c->d_cell_M, sizeof(float4) * nt));
+    FG_CUDA(cudaMemsetAsync(d_counts, 0, sizeof(int) * ncell, st));
+    FG_CUDA(cudaMemsetAsync(d_fill, 0, sizeof(int) * ncell, st));
+    CellGrid g;
+    g.start = c->d_cell_start; g.pts = c->d_cell_P;
+    g.nx = c->cnx; g.ny = c->cny; g.nz = c->cnz; g.h = h; g.inv_h = c->cell_inv_h;
+    k_cell_index<<<(nt + 255) / 256, 256, 0, st>>>(d_P, nt, g, d_cell_of, d_counts);
+    k_scan_counts<<<1, 1024, 0, st>>>(d_counts, ncell, c->d_cell_start);
+    k_cell_scatter<<<(nt + 255) / 256, 256, 0, st>>>(d_P, c->d_model, nt, d_cell_of, c->d_cell_start, d_fill, c->d_cell_P, c->d_cell_M);
+    FG_CUDA(cudaGetLastError());
+    FG_CUDA(cudaStreamSynchronize(st));
+    cudaFree(d_cell_of); cudaFree(d_counts); cudaFree(d_fill);
+    return FGOICP_OK;
+}
+
 static int build_grid_hier(fgoicp_ctx* c, const float4* d_P)
 {
     const LutDev& L = c->lut;
     cudaStream_t st = c->stream;
     int nt = (int)c->nt;
 
-    // ---- uniform cell grid over the lattice extent (points outside are clamped into edge cells)
-    float ext[3] = { L.dx * c->res, L.dy * c->res, L.dz * c->res };
-    float max_ext = std::max(ext[0], std::max(ext[1], ext[2]));
-    // aim for a few points per occupied cell on a surface-like cloud, but at most 128 cells/axis
-    float h = std::max(max_ext / 128.0f, 4.0f * c->res);
     CellGrid g;
-    g.h = h; g.inv_h = 1.0f / h;
-    g.nx = std::max(1, (int)std::ceil(ext[0] / h)); g.ny = std::max(1, (int)std::ceil(ext[1] / h)); g.nz = std::max(1, (int)std::ceil(ext[2] / h));
-    int ncell = g.nx * g.ny * g.nz;
-    int *d_cell_of = nullptr, *d_counts = nullptr, *d_start = nullptr, *d_fill = nullptr;
-    float4* d_sorted = nullptr;
-    FG_CUDA(cudaMalloc(&d_cell_of, sizeof(int) * nt));
-    FG_CUDA(cudaMalloc(&d_counts, sizeof(int) * ncell));
-    FG_CUDA(cudaMalloc(&d_fill, sizeof(int) * ncell));
-    FG_CUDA(cudaMalloc(&d_start, sizeof(int) * (ncell + 1)));
-    FG_CUDA(cudaMalloc(&d_sorted, sizeof(float4) * nt));
-    FG_CUDA(cudaMemsetAsync(d_counts, 0, sizeof(int) * ncell, st));
-    FG_CUDA(cudaMemsetAsync(d_fill, 0, sizeof(int) * ncell, st));
-    g.start = d_start; g.pts = d_sorted;
-    k_cell_index<<<(nt + 255) / 256, 256, 0, st>>>(d_P, nt, g, d_cell_of, d_counts);
-    k_scan_counts<<<1, 1024, 0, st>>>(d_counts, ncell, d_start);
-    k_cell_scatter<<<(nt + 255) / 256, 256, 0, st>>>(d_P, nt, d_cell_of, d_start, d_fill, d_sorted);
-    FG_CUDA(cudaGetLastError());
+    g.start = c->d_cell_start; g.pts = c->d_cell_P;
+    g.nx = c->cnx; g.ny = c->cny; g.nz = c->cnz; g.h = c->cell_h; g.inv_h = c->cell_inv_h;
 
     // ---- lattice pyramid: level 0 = the LUT itself; level l+1 = brick centres of level l
     std::vector<Level> lv;
@@ -449,7 +461,6 @@ static int build_grid_hier(fgoicp_ctx* c, const float4* d_P)
     }
     FG_CUDA(cudaStreamSynchronize(st));
     for (size_t l = 1; l < lv.size(); ++l) cudaFree(lv[l].d);
-    cudaFree(d_cell_of); cudaFree(d_counts); cudaFree(d_fill); cudaFree(d_start); cudaFree(d_sorted);
     return FGOICP_OK;
 }
 
@@ -561,6 +572,8 @@ extern "C" int fgoicp_ctx_create(const float* model_xyz, size_t nt, const float*
     FG_TRY(cudaMalloc(&c->d_icp, sizeof(double) * 256));
 
     FG_TRY(cudaEventRecord(c->ev0, c->stream));
+    rc = build_cell_grid(c, d_P);
+    if (rc) return fail(rc);
     if (flags & FGOICP_BUILD_BRUTE_LUT) rc = build_grid_brute(c, d_P);
     else rc = build_grid_hier(c, d_P);
     if (rc) return fail(rc);
@@ -597,6 +610,7 @@ extern "C" int fgoicp_ctx_destroy(fgoicp_ctx* c)
     if (c->arr) cudaFreeArray(c->arr);
     cudaFree(c->d_model); cudaFree(c->d_data); cudaFree(c->d_grid); cudaFree(c->d_packed);
     cudaFree(c->d_scratch); cudaFree(c->d_work); cudaFree(c->d_nnkey); cudaFree(c->d_icp);
+    cudaFree(c->d_cell_start); cudaFree(c->d_cell_P); cudaFree(c->d_cell_M);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -627,6 +641,14 @@ extern "C" int fgoicp_set_sampler(fgoicp_ctx* c, int sampler)
     if (sampler == FGOICP_SAMPLER_PACKED && !c->d_packed) { fg::set_error("packed grid was not built"); return FGOICP_ERR_STATE; }
     if (sampler == FGOICP_SAMPLER_TEX && !c->lut.tex) { fg::set_error("texture was not built"); return FGOICP_ERR_STATE; }
     c->sampler = sampler;
+    return FGOICP_OK;
+}
+
+extern "C" int fgoicp_set_nn_mode(fgoicp_ctx* c, int mode)
+{
+    FG_ARG(c, "NULL context");
+    FG_ARG(mode == 0 || mode == 1, "nn mode must be 0 (cell grid) or 1 (brute force)");
+    c->nn_mode = mode;
     return FGOICP_OK;
 }
 

@@ -137,6 +137,118 @@ k_nn_brute(const float4* __restrict__ model, int nt, int chunk,
     }
 }
 
+// largest float x with sqrtf(x) == s
+__device__ __forceinline__ float fg_sqrt_preimage_hi(float s)
+{
+    float x = __fmul_rn(s, s);
+    for (int it = 0; it < 4; ++it)
+    {
+        float xp = __uint_as_float(__float_as_uint(x) + 1u);
+        if (__fsqrt_rn(xp) == s) x = xp; else break;
+    }
+    for (int it = 0; it < 4; ++it)
+    {
+        if (__fsqrt_rn(x) > s && x > 0.0f) x = __uint_as_float(__float_as_uint(x) - 1u); else break;
+    }
+    return x;
+}
+
+// Exact NN through the uniform cell grid (one thread per query).
+//   1. The dense distance grid gives a tight search radius for free: the grid node n nearest to q has a
+//      model point within sqrt(T[n]), so the NN of q lies within U = sqrt(T[n]) + |q - x_n|.
+//   2. Only the (y, z) rows of cells cutting the ball B(q, U) are visited; inside a row the chord of the
+//      ball selects a run of cells, which is ONE contiguous range of the cell-sorted point array.
+//   3. Candidates are compared as a lexicographic (value, original index) minimum, value = d2 (K5 rule)
+//      or sqrtf(d2) (K7 rule), so the visiting order does not matter and ties resolve to the lowest index
+//      exactly as the reference's ascending scan does.  U shrinks as candidates are found.
+// All pruning tests carry a relative slack of 1e-5: they may visit too much, never too little.
+template <int ROOTED>
+__global__ void __launch_bounds__(128)
+k_nn_grid(CellGrid g, LutDev L, float res, const float4* __restrict__ src, int ns, const float* __restrict__ pose,
+          unsigned long long* __restrict__ keys, const int* __restrict__ done_flag)
+{
+    if (done_flag && *done_flag) return;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ns) return;
+    float4 p = src[i];
+    float qx = p.x, qy = p.y, qz = p.z;
+    if (pose)
+    {
+        float R[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) R[k] = pose[k];
+        float3 rp = fg_rotate(R, p.x, p.y, p.z);
+        qx = __fadd_rn(rp.x, pose[9]); qy = __fadd_rn(rp.y, pose[10]); qz = __fadd_rn(rp.z, pose[11]);
+    }
+    // LUT-space position (binning frame) and the nearest grid node
+    float lx = qx + L.ox, ly = qy + L.oy, lz = qz + L.oz;
+    int nx = min(max(__float2int_rn(lx * L.scale), 0), L.dx - 1);
+    int ny = min(max(__float2int_rn(ly * L.scale), 0), L.dy - 1);
+    int nz = min(max(__float2int_rn(lz * L.scale), 0), L.dz - 1);
+    float Tn = __ldg(L.grid + ((size_t)nz * L.dy + ny) * L.dx + nx);
+    float ex = lx - (float)nx * res, ey = ly - (float)ny * res, ez = lz - (float)nz * res;
+    float U = (sqrtf(Tn) + sqrtf(ex * ex + ey * ey + ez * ez)) * 1.0001f + 1e-6f;
+    float U2 = U * U;
+
+    float best = FG_INF, thr_lo = ROOTED ? fg_sqrt_preimage_lo(FG_INF) : FG_INF, thr_hi = thr_lo;
+    int best_idx = 0x7fffffff;
+
+    const float h = g.h, inv_h = g.inv_h;
+    int cz0 = min(max((int)floorf((lz - U) * inv_h), 0), g.nz - 1);
+    int cz1 = min(max((int)floorf((lz + U) * inv_h), 0), g.nz - 1);
+    for (int cz = cz0; cz <= cz1; ++cz)
+    {
+        // edge cells also hold points clamped into them: their slab extends to infinity
+        float zlo = cz == 0 ? -FG_INF : (float)cz * h, zhi = cz == g.nz - 1 ? FG_INF : (float)(cz + 1) * h;
+        float dz = fmaxf(fmaxf(zlo - lz, lz - zhi), 0.0f);
+        float dz2 = dz * dz;
+        if (dz2 > U2) continue;
+        float wy = sqrtf(U2 - dz2) * 1.00001f + 1e-6f;
+        int cy0 = min(max((int)floorf((ly - wy) * inv_h), 0), g.ny - 1);
+        int cy1 = min(max((int)floorf((ly + wy) * inv_h), 0), g.ny - 1);
+        for (int cy = cy0; cy <= cy1; ++cy)
+        {
+            float ylo = cy == 0 ? -FG_INF : (float)cy * h, yhi = cy == g.ny - 1 ? FG_INF : (float)(cy + 1) * h;
+            float dy = fmaxf(fmaxf(ylo - ly, ly - yhi), 0.0f);
+            float dyz2 = dz2 + dy * dy;
+            if (dyz2 > U2) continue;
+            float wx = sqrtf(U2 - dyz2) * 1.00001f + 1e-6f;
+            int cx0 = min(max((int)floorf((lx - wx) * inv_h), 0), g.nx - 1);
+            int cx1 = min(max((int)floorf((lx + wx) * inv_h), 0), g.nx - 1);
+            int c0 = (cz * g.ny + cy) * g.nx;
+            int b = __ldg(g.start + c0 + cx0), e = __ldg(g.start + c0 + cx1 + 1);
+            for (int k = b; k < e; ++k)
+            {
+                float4 m = __ldg(g.pts + k);
+                float d = fg_sq3(__fsub_rn(qx, m.x), __fsub_rn(qy, m.y), __fsub_rn(qz, m.z));
+                int idx = __float_as_int(m.w);
+                if (ROOTED)
+                {
+                    if (d < thr_lo)
+                    {
+                        float s = __fsqrt_rn(d);
+                        best = s; best_idx = idx;
+                        thr_lo = fg_sqrt_preimage_lo(s); thr_hi = fg_sqrt_preimage_hi(s);
+                        U2 = fminf(U2, thr_hi * 1.00002f + 1e-12f);
+                    }
+                    else if (d <= thr_hi && idx < best_idx) best_idx = idx;
+                }
+                else
+                {
+                    if (d < best || (d == best && idx < best_idx))
+                    {
+                        best = d; best_idx = idx;
+                        U2 = fminf(U2, d * 1.00002f + 1e-12f);
+                    }
+                }
+            }
+        }
+    }
+    unsigned long long key = 0xffffffffffffffffull;
+    if (best_idx != 0x7fffffff) key = ((unsigned long long)__float_as_uint(best) << 32) | (unsigned int)best_idx;
+    keys[i] = key;
+}
+
 // keys -> (idx, d2 of the winner recomputed with the canonical formula)
 __global__ void k_nn_finish(const unsigned long long* __restrict__ keys, const float4* __restrict__ model,
                             const float4* __restrict__ src, int ns, const float* __restrict__ pose,
@@ -338,6 +450,19 @@ static void nn_geometry(const fgoicp_ctx* c, dim3& grid, int& chunk)
 // enqueue: keys := NN of (pose ? pose*src : src)
 static int enqueue_nn(fgoicp_ctx* c, const float4* d_src, const float* d_pose, int rooted, const int* d_done)
 {
+    if (c->nn_mode == 0)
+    {
+        CellGrid g;
+        g.start = c->d_cell_start; g.pts = c->d_cell_M;
+        g.nx = c->cnx; g.ny = c->cny; g.nz = c->cnz; g.h = c->cell_h; g.inv_h = c->cell_inv_h;
+        unsigned blocks = (unsigned)((c->ns + 127) / 128);
+        if (rooted)
+            k_nn_grid<1><<<blocks, 128, 0, c->stream>>>(g, c->lut, c->res, d_src, (int)c->ns, d_pose, c->d_nnkey, d_done);
+        else
+            k_nn_grid<0><<<blocks, 128, 0, c->stream>>>(g, c->lut, c->res, d_src, (int)c->ns, d_pose, c->d_nnkey, d_done);
+        FG_CUDA(cudaGetLastError());
+        return FGOICP_OK;
+    }
     dim3 grid; int chunk;
     nn_geometry(c, grid, chunk);
     FG_CUDA(cudaMemsetAsync(c->d_nnkey, 0xff, sizeof(unsigned long long) * c->ns, c->stream));

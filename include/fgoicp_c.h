@@ -84,10 +84,16 @@ int fgoicp_set_sampler(fgoicp_ctx* ctx, int sampler);
 int fgoicp_set_stream(fgoicp_ctx* ctx, void* cuda_stream);
 
 /* Test hooks ------------------------------------------------------------------------------- */
+/* Nearest-neighbour engine behind fgoicp_sse / fgoicp_nn / fgoicp_icp: 0 = uniform cell grid in HBM
+ * (default), 1 = tiled brute force.  Both are exact and return identical indices. */
+int fgoicp_set_nn_mode(fgoicp_ctx* ctx, int mode);
 /* Dense grid download, x fastest: out[(z*dims[1]+y)*dims[0]+x]  (registration.cu:276-277). */
 int fgoicp_lut_download(fgoicp_ctx* ctx, float* out, size_t out_floats);
 /* NearestNeighborLUT::search for n query points with a chosen sampler (registration.cu:320-328). */
 int fgoicp_lut_sample(fgoicp_ctx* ctx, const float* q_xyz, size_t n, int sampler, float* out_d2);
+/* Measurement hook: useful GB/s of independent random gathers of width_bytes (16/32/64/128) over a
+ * buffer of `bytes` bytes -- the gather roofline the bound kernels are compared with. */
+int fgoicp_gather_probe(fgoicp_ctx* ctx, size_t bytes, int width_bytes, int blocks_per_sm, float* out_gbps);
 /* sinf(span * sqrt3 * pi / 2) exactly as the device evaluates it in the bound kernels
  * (registration.cu:41-42). */
 int fgoicp_rot_sin(fgoicp_ctx* ctx, const float* spans, int n, float* out);

@@ -43,7 +43,7 @@
 /* ------------------------------------------------------------------------------------------ */
 /* Tunables pinned empirically against tex3D on a B200 (tests/test_gpu_texture_conformance.py) */
 /* ------------------------------------------------------------------------------------------ */
-static int g_weight_mode = 0;   /* 0: round-to-nearest 1.8 fixed point, 1: truncate            */
+static int g_weight_mode = 0;   /* 0: round-half-up 1.8 fixed point (B200 hardware), 1: truncate, 2: half-even */
 static int g_interp_mode = 0;   /* 0: nested lerps x,y,z with fmaf, 1: 8-term weighted sum      */
 static int g_sin_mode = 0;      /* 0: host sinf(), 1: table lookup of device values (see below) */
 static int g_sin_n = 0;
@@ -282,7 +282,9 @@ static inline void orc_tex_axis(float u, int dim, int* i0, int* i1, float* alpha
     if (!(u > -2.0f)) u = -2.0f;
     if (u > (float)dim + 2.0f) u = (float)dim + 2.0f;
     if (g_weight_mode == 0)
-        xf = (int)rintf(u * 256.0f) - 128;          /* round to nearest 1/256 */
+        xf = (int)floorf(u * 256.0f + 0.5f) - 128;  /* round HALF UP to 1/256: pinned on B200, see DESIGN.md */
+    else if (g_weight_mode == 2)
+        xf = (int)rintf(u * 256.0f) - 128;          /* round half to even (probe only) */
     else
         xf = (int)floorf(u * 256.0f) - 128;         /* truncate to 1/256      */
     i = xf >> 8;                                    /* arithmetic shift = floor */

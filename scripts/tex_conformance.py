@@ -29,19 +29,34 @@ def main(out_path):
     tex = ctx.lut_sample(q, capi.SAMPLER_TEX)
     man = ctx.lut_sample(q, capi.SAMPLER_GRID)
     report = {"n": len(q), "dims": [int(d) for d in dims], "candidates": {}}
-    for wm in (0, 1):
+    for wm in (0, 1, 2):
         for im in (0, 1):
             O.set_modes(wm, im)
             o = O.lut_sample(lut, dims, pp["bbox_min"], res, q)
             u = ulps(o, tex)
             rel = np.abs(o - tex) / np.maximum(np.abs(tex), 1e-12)
-            report["candidates"]["weights=%s,interp=%s" % ("nearest" if wm == 0 else "trunc", "lerp" if im == 0 else "wsum")] = {
+            report["candidates"]["weights=%s,interp=%s" % (("half_up", "trunc", "half_even")[wm], "lerp" if im == 0 else "wsum")] = {
                 "bit_exact_frac": float(np.mean(u == 0)), "within_1ulp_frac": float(np.mean(u <= 1)),
                 "within_4ulp_frac": float(np.mean(u <= 4)), "max_rel": float(rel.max()), "p999_rel": float(np.quantile(rel, 0.999)),
                 "median_rel": float(np.median(rel))}
     O.set_modes(0, 0)
     o = O.lut_sample(lut, dims, pp["bbox_min"], res, q)
     report["manual_kernel_equals_oracle_default"] = bool(np.array_equal(o, man))
+    # the worst disagreements, with everything needed to re-derive the hardware's weights offline
+    rel = np.abs(o - tex) / np.maximum(np.abs(tex), 1e-12)
+    worst = np.argsort(-rel)[:40]
+    Tg = lut.reshape(dims[2], dims[1], dims[0])
+    uu = (q[worst] + (-pp["bbox_min"]).astype(np.float32)) * np.float32(1.0 / np.float32(res))
+    dump = []
+    for n, wi in enumerate(worst):
+        xf = np.floor(uu[n].astype(np.float64) * 256 + 0.5).astype(np.int64) - 128
+        ii = xf >> 8
+        c = [int(np.clip(ii[a] + d, 0, dims[a] - 1)) for a in range(3) for d in (0, 1)]
+        tex8 = [float(Tg[c[4 + dz], c[2 + dy], c[dx]]) for dz in (0, 1) for dy in (0, 1) for dx in (0, 1)]
+        dump.append({"q": [float(x) for x in q[wi]], "u": [float(x) for x in uu[n]], "tex": float(tex[wi]),
+                     "manual": float(o[wi]), "rel": float(rel[wi]), "texels_zyx": tex8,
+                     "alpha256": [int(x & 255) for x in xf], "i": [int(x) for x in ii]})
+    report["worst"] = dump
     # 1-D probe of the weight rule: y, z on texel centres (beta = gamma = 0), x swept across cells in steps
     # of 1/2048 texel; alpha_hw = (tex - T0) / (T1 - T0)
     T = lut.reshape(dims[2], dims[1], dims[0])

@@ -106,8 +106,10 @@ def test_bounds_multi_dev_and_best_ub(small_problem, gpu_ctx):
     assert float(d_best.item()) == float(ub.min())
 
 
-def test_nn_indices_bit_exact(small_problem, gpu_ctx):
+@pytest.mark.parametrize("nn_mode", [0, 1])
+def test_nn_indices_bit_exact(small_problem, gpu_ctx, nn_mode):
     pp = small_problem
+    gpu_ctx.set_nn_mode(nn_mode)
     for rot, t in [((0.2, 0.1, -0.1), (0.05, -0.02, 0.01)), ((0, 0, 0), (0, 0, 0)), ((-0.4, 0.3, 0.2), (0.4, 0.3, -0.5))]:
         R, _ = O.rotation(*np.float32(rot))
         t = np.float32(t)
@@ -118,6 +120,7 @@ def test_nn_indices_bit_exact(small_problem, gpu_ctx):
             assert np.array_equal(d2, wd2)
         sse = gpu_ctx.sse(R, t)
         assert sse == O.sse(pp["model"], pp["data"], R, t)
+    gpu_ctx.set_nn_mode(0)
 
 
 def test_nn_duplicate_points_lowest_index_wins():
@@ -127,10 +130,13 @@ def test_nn_duplicate_points_lowest_index_wins():
     data = base[:257] + np.float32(1e-3)
     ctx = capi.Context(model, data, model.min(0), model.max(0), 0.1, flags=0)
     I = np.eye(3, dtype=np.float32).ravel()
-    for rooted in (False, True):
-        idx, _ = ctx.nn(I, np.zeros(3, np.float32), rooted)
-        widx, _ = O.nn(model, data, I, np.zeros(3, np.float32), rooted)
-        assert np.array_equal(idx, widx) and np.all(idx < 700)
+    for nn_mode in (0, 1):
+        ctx.set_nn_mode(nn_mode)
+        for rooted in (False, True):
+            for t in (np.zeros(3, np.float32), np.float32([0.7, -0.4, 1.3])):      # near and far queries
+                idx, _ = ctx.nn(I, t, rooted)
+                widx, _ = O.nn(model, data, I, t, rooted)
+                assert np.array_equal(idx, widx) and np.all(idx < 700)
     ctx.close()
 
 

@@ -58,7 +58,7 @@ def _numpy_trilinear(lut, dims, bbox_min, res, q):
     """float64 restatement of unnormalised linear texture filtering with clamp, 8-bit weights."""
     T = lut.reshape(dims[2], dims[1], dims[0]).astype(np.float64)
     u = (q.astype(np.float32) + (-bbox_min).astype(np.float32)) * np.float32(1.0 / np.float32(res))
-    xf = np.rint(u.astype(np.float64) * 256.0).astype(np.int64) - 128
+    xf = np.floor(u.astype(np.float64) * 256.0 + 0.5).astype(np.int64) - 128     # round half up (B200 texture unit)
     i = xf >> 8
     a = (xf & 255) / 256.0
     out = np.zeros(len(q))

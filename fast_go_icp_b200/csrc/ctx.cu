@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -510,6 +511,16 @@ extern "C" int fgoicp_ctx_create(const float* model_xyz, size_t nt, const float*
     }
     FG_ARG(device >= 0 && device < ndev, "device index out of range");
     FG_CUDA(cudaSetDevice(device));
+
+    // The bound kernels gather one random 32-byte sector per evaluation from a grid far larger than L2.
+    // With the default L2 fetch granularity every such miss pulls ~3 sectors from HBM (measured with ncu:
+    // 95 B of DRAM traffic per 32 B requested), i.e. two thirds of the HBM bandwidth is wasted.  Ask for
+    // sector-granular fills.  (A hint; FGOICP_L2_FETCH=64|128 restores coarser fills for experiments.)
+    {
+        size_t gran = 32;
+        if (const char* e = getenv("FGOICP_L2_FETCH")) gran = (size_t)atoi(e);
+        if (gran == 32 || gran == 64 || gran == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
+    }
 
     fgoicp_ctx* c = new fgoicp_ctx();
     c->device = device;

@@ -153,22 +153,27 @@ __device__ __forceinline__ float fg_sqrt_preimage_hi(float s)
     return x;
 }
 
-// Exact NN through the uniform cell grid (one thread per query).
+// Exact NN through the uniform cell grid, one WARP per query.
 //   1. The dense distance grid gives a tight search radius for free: the grid node n nearest to q has a
 //      model point within sqrt(T[n]), so the NN of q lies within U = sqrt(T[n]) + |q - x_n|.
-//   2. Only the (y, z) rows of cells cutting the ball B(q, U) are visited; inside a row the chord of the
-//      ball selects a run of cells, which is ONE contiguous range of the cell-sorted point array.
+//   2. Only the (y, z) rows of cells cutting the ball B(q, U) are visited, 32 rows at a time (one per lane);
+//      inside a row the chord of the ball selects a run of cells, which is ONE contiguous range of the
+//      cell-sorted point array.  A query next to the surface needs 9-16 rows (one pass); a far query has
+//      its hundreds of rows spread over the lanes instead of walked serially.
 //   3. Candidates are compared as a lexicographic (value, original index) minimum, value = d2 (K5 rule)
 //      or sqrtf(d2) (K7 rule), so the visiting order does not matter and ties resolve to the lowest index
-//      exactly as the reference's ascending scan does.  U shrinks as candidates are found.
-// All pruning tests carry a relative slack of 1e-5: they may visit too much, never too little.
+//      exactly as the reference's ascending scan does.  Lanes share the shrinking radius after every pass
+//      and merge their winners with a shuffle reduction on the packed 64-bit key.
+// All pruning tests carry a relative slack: they may visit too much, never too little.
+#define NNG_WARPS 4
 template <int ROOTED>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(NNG_WARPS * 32)
 k_nn_grid(CellGrid g, LutDev L, float res, const float4* __restrict__ src, int ns, const float* __restrict__ pose,
           unsigned long long* __restrict__ keys, const int* __restrict__ done_flag)
 {
     if (done_flag && *done_flag) return;
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * NNG_WARPS + (threadIdx.x >> 5);
     if (i >= ns) return;
     float4 p = src[i];
     float qx = p.x, qy = p.y, qz = p.z;
@@ -194,59 +199,71 @@ k_nn_grid(CellGrid g, LutDev L, float res, const float4* __restrict__ src, int n
     int best_idx = 0x7fffffff;
 
     const float h = g.h, inv_h = g.inv_h;
-    int cz0 = min(max((int)floorf((lz - U) * inv_h), 0), g.nz - 1);
-    int cz1 = min(max((int)floorf((lz + U) * inv_h), 0), g.nz - 1);
-    for (int cz = cz0; cz <= cz1; ++cz)
+    const int cz0 = min(max((int)floorf((lz - U) * inv_h), 0), g.nz - 1);
+    const int cz1 = min(max((int)floorf((lz + U) * inv_h), 0), g.nz - 1);
+    const int cy0 = min(max((int)floorf((ly - U) * inv_h), 0), g.ny - 1);
+    const int cy1 = min(max((int)floorf((ly + U) * inv_h), 0), g.ny - 1);
+    const int ny_rows = cy1 - cy0 + 1;
+    const int n_rows = ny_rows * (cz1 - cz0 + 1);
+    for (int row0 = 0; row0 < n_rows; row0 += 32)
     {
-        // edge cells also hold points clamped into them: their slab extends to infinity
-        float zlo = cz == 0 ? -FG_INF : (float)cz * h, zhi = cz == g.nz - 1 ? FG_INF : (float)(cz + 1) * h;
-        float dz = fmaxf(fmaxf(zlo - lz, lz - zhi), 0.0f);
-        float dz2 = dz * dz;
-        if (dz2 > U2) continue;
-        float wy = sqrtf(U2 - dz2) * 1.00001f + 1e-6f;
-        int cy0 = min(max((int)floorf((ly - wy) * inv_h), 0), g.ny - 1);
-        int cy1 = min(max((int)floorf((ly + wy) * inv_h), 0), g.ny - 1);
-        for (int cy = cy0; cy <= cy1; ++cy)
+        int row = row0 + lane;
+        if (row < n_rows)
         {
+            int cz = cz0 + row / ny_rows, cy = cy0 + row % ny_rows;
+            // edge cells also hold points clamped into them: their slab extends to infinity
+            float zlo = cz == 0 ? -FG_INF : (float)cz * h, zhi = cz == g.nz - 1 ? FG_INF : (float)(cz + 1) * h;
             float ylo = cy == 0 ? -FG_INF : (float)cy * h, yhi = cy == g.ny - 1 ? FG_INF : (float)(cy + 1) * h;
+            float dz = fmaxf(fmaxf(zlo - lz, lz - zhi), 0.0f);
             float dy = fmaxf(fmaxf(ylo - ly, ly - yhi), 0.0f);
-            float dyz2 = dz2 + dy * dy;
-            if (dyz2 > U2) continue;
-            float wx = sqrtf(U2 - dyz2) * 1.00001f + 1e-6f;
-            int cx0 = min(max((int)floorf((lx - wx) * inv_h), 0), g.nx - 1);
-            int cx1 = min(max((int)floorf((lx + wx) * inv_h), 0), g.nx - 1);
-            int c0 = (cz * g.ny + cy) * g.nx;
-            int b = __ldg(g.start + c0 + cx0), e = __ldg(g.start + c0 + cx1 + 1);
-            for (int k = b; k < e; ++k)
+            float dyz2 = dz * dz + dy * dy;
+            if (dyz2 <= U2)
             {
-                float4 m = __ldg(g.pts + k);
-                float d = fg_sq3(__fsub_rn(qx, m.x), __fsub_rn(qy, m.y), __fsub_rn(qz, m.z));
-                int idx = __float_as_int(m.w);
-                if (ROOTED)
+                float wx = sqrtf(U2 - dyz2) * 1.00001f + 1e-6f;
+                int cx0 = min(max((int)floorf((lx - wx) * inv_h), 0), g.nx - 1);
+                int cx1 = min(max((int)floorf((lx + wx) * inv_h), 0), g.nx - 1);
+                int c0 = (cz * g.ny + cy) * g.nx;
+                int b = __ldg(g.start + c0 + cx0), e = __ldg(g.start + c0 + cx1 + 1);
+                for (int k = b; k < e; ++k)
                 {
-                    if (d < thr_lo)
+                    float4 m = __ldg(g.pts + k);
+                    float d = fg_sq3(__fsub_rn(qx, m.x), __fsub_rn(qy, m.y), __fsub_rn(qz, m.z));
+                    int idx = __float_as_int(m.w);
+                    if (ROOTED)
                     {
-                        float s = __fsqrt_rn(d);
-                        best = s; best_idx = idx;
-                        thr_lo = fg_sqrt_preimage_lo(s); thr_hi = fg_sqrt_preimage_hi(s);
-                        U2 = fminf(U2, thr_hi * 1.00002f + 1e-12f);
+                        if (d < thr_lo)
+                        {
+                            float s = __fsqrt_rn(d);
+                            best = s; best_idx = idx;
+                            thr_lo = fg_sqrt_preimage_lo(s); thr_hi = fg_sqrt_preimage_hi(s);
+                            U2 = fminf(U2, thr_hi * 1.00002f + 1e-12f);
+                        }
+                        else if (d <= thr_hi && idx < best_idx) best_idx = idx;
                     }
-                    else if (d <= thr_hi && idx < best_idx) best_idx = idx;
-                }
-                else
-                {
-                    if (d < best || (d == best && idx < best_idx))
+                    else
                     {
-                        best = d; best_idx = idx;
-                        U2 = fminf(U2, d * 1.00002f + 1e-12f);
+                        if (d < best || (d == best && idx < best_idx))
+                        {
+                            best = d; best_idx = idx;
+                            U2 = fminf(U2, d * 1.00002f + 1e-12f);
+                        }
                     }
                 }
             }
         }
+        // share the tightest radius before the next pass
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) U2 = fminf(U2, __shfl_xor_sync(0xffffffffu, U2, o));
     }
     unsigned long long key = 0xffffffffffffffffull;
     if (best_idx != 0x7fffffff) key = ((unsigned long long)__float_as_uint(best) << 32) | (unsigned int)best_idx;
-    keys[i] = key;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+    {
+        unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+        key = other < key ? other : key;
+    }
+    if (lane == 0) keys[i] = key;
 }
 
 // keys -> (idx, d2 of the winner recomputed with the canonical formula)
@@ -455,11 +472,11 @@ static int enqueue_nn(fgoicp_ctx* c, const float4* d_src, const float* d_pose, i
         CellGrid g;
         g.start = c->d_cell_start; g.pts = c->d_cell_M;
         g.nx = c->cnx; g.ny = c->cny; g.nz = c->cnz; g.h = c->cell_h; g.inv_h = c->cell_inv_h;
-        unsigned blocks = (unsigned)((c->ns + 127) / 128);
+        unsigned blocks = (unsigned)((c->ns + NNG_WARPS - 1) / NNG_WARPS);
         if (rooted)
-            k_nn_grid<1><<<blocks, 128, 0, c->stream>>>(g, c->lut, c->res, d_src, (int)c->ns, d_pose, c->d_nnkey, d_done);
+            k_nn_grid<1><<<blocks, NNG_WARPS * 32, 0, c->stream>>>(g, c->lut, c->res, d_src, (int)c->ns, d_pose, c->d_nnkey, d_done);
         else
-            k_nn_grid<0><<<blocks, 128, 0, c->stream>>>(g, c->lut, c->res, d_src, (int)c->ns, d_pose, c->d_nnkey, d_done);
+            k_nn_grid<0><<<blocks, NNG_WARPS * 32, 0, c->stream>>>(g, c->lut, c->res, d_src, (int)c->ns, d_pose, c->d_nnkey, d_done);
         FG_CUDA(cudaGetLastError());
         return FGOICP_OK;
     }

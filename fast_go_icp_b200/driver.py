@@ -143,14 +143,16 @@ class FastGoICP:
     """Python mirror of icp::FastGoICP (reference fgoicp/fgoicp.hpp:10-108)."""
 
     def __init__(self, target, source, lut_resolution, mse_threshold, device=0, sampler=None,
-                 flags=capi.BUILD_PACKED, group=None):
+                 flags=capi.BUILD_PACKED, group=None, ctx_factory=None):
         t0 = time.perf_counter()
         self.pp = preprocess(target, source)
         self.ns, self.nt = len(self.pp["data"]), len(self.pp["model"])
         self.mse_threshold = F(mse_threshold)
         self.sse_threshold = F(F(self.ns) * self.mse_threshold)            # fgoicp.hpp:23
-        self.ctx = capi.Context(self.pp["model"], self.pp["data"], self.pp["bbox_min"], self.pp["bbox_max"],
-                                lut_resolution, device=device, flags=flags)
+        # ctx_factory: tests inject a stand-in for the CUDA context to exercise the sharding logic on CPU
+        make = ctx_factory if ctx_factory is not None else capi.Context
+        self.ctx = make(self.pp["model"], self.pp["data"], self.pp["bbox_min"], self.pp["bbox_max"],
+                        lut_resolution, device=device, flags=flags)
         if sampler is not None:
             self.ctx.set_sampler(sampler)
         self.comm = _Comm(group)

@@ -12,16 +12,27 @@
 //   - every iteration: bitonic sort + compaction of the pool, the reference's stop test, pop of
 //     <= 32 cubes, bound evaluation with the same fused evaluator as bounds.cu, update of
 //     best_ub / best_error / best_t, pruning, and spawning of 8 children per surviving cube;
-//   - nothing returns to the host until the search is over; many rotation cubes run concurrently
-//     (one block each), which is where the parallelism of a whole outer level comes from.
+//   - nothing returns to the host until the search is over; many rotation cubes run concurrently,
+//     which is where the parallelism of a whole outer level comes from;
+//   - a rotation cube is owned by a THREAD-BLOCK CLUSTER of 1..8 blocks: every block keeps its own copy of
+//     the (tiny) search state and executes the same control flow, but evaluates only its slice of the data
+//     points; the per-cube fp64 partial sums are exchanged through distributed shared memory (one
+//     cluster.sync per iteration) and folded in rank order, so all blocks see identical bounds.  Few cubes
+//     (outer levels 1-2: 8 and <= 64 cubes) get big clusters so the GPU is not idle; many cubes get small
+//     clusters, which also evens out the tail (searches differ 100x in length).
 // Cube centres are dyadic ( -1 + (2i+1) 2^-level ), so integer coordinates reproduce the reference's
 // float arithmetic (t - span/2 + bit*span, fgoicp.cpp:159-163) exactly.
 #include "common.cuh"
 #include "bounds_eval.cuh"
 
+#include <cooperative_groups.h>
+
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
+
+namespace cg = cooperative_groups;
 
 #define BNB_POOL       8192            // >= 1 + 8 + 64 + 512 + 4096 = 4681 nodes ever pushed
 #define BNB_BATCH_MAX  32              // fgoicp.cpp:122
@@ -54,6 +65,7 @@ k_bnb_r3(LutDev L, const float4* __restrict__ data, int ns, const float4* __rest
     __shared__ float4 s_tc[BNB_BATCH_MAX];
     __shared__ unsigned long long s_bkey[BNB_BATCH_MAX];
     __shared__ double s_part[NWARPS][BD_CPW][2];
+    __shared__ double s_cpart[2][BNB_BATCH_MAX][2];        // this block's partial sums, double-buffered for DSMEM readers
     __shared__ float s_lb[BNB_BATCH_MAX], s_ub[BNB_BATCH_MAX];
     __shared__ int s_n, s_m, s_nb, s_stop;
     __shared__ float s_best_error, s_best_ub, s_best_t[3];
@@ -62,7 +74,14 @@ k_bnb_r3(LutDev L, const float4* __restrict__ data, int ns, const float4* __rest
 
     const int NT = NWARPS * 32;
     const int tid = threadIdx.x;
-    const int r = blockIdx.x;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int csize = (int)cluster.num_blocks();
+    const int crank = (int)cluster.block_rank();
+    const int r = blockIdx.x / csize;
+    // this block's slice of the data points
+    const int per = (ns + csize - 1) / csize;
+    const int p0 = min(ns, crank * per), p1 = min(ns, p0 + per);
+    int parity = 0;
 
     if (tid == 0)
     {
@@ -147,14 +166,26 @@ k_bnb_r3(LutDev L, const float4* __restrict__ data, int ns, const float4* __rest
         __syncthreads();
 
         // ---- (e) bounds of the batch (registration.cu:88-152 fused)
-        fg_eval_chunk<SAMPLER, NWARPS>(L, data, 0, ns, sR, s_sin, fix_rot != 0, s_tc, nb, s_part);
+        fg_eval_chunk<SAMPLER, NWARPS>(L, data, p0, p1, sR, s_sin, fix_rot != 0, s_tc, nb, s_part);
         __syncthreads();
         if (tid < nb)
         {
             double su, sl;
             fg_eval_gather<NWARPS>(s_part, nb, tid, su, sl);
+            s_cpart[parity][tid][0] = su; s_cpart[parity][tid][1] = sl;
+        }
+        cluster.sync();                                   // every block's partials are visible cluster-wide
+        if (tid < nb)
+        {
+            double su = 0.0, sl = 0.0;
+            for (int k = 0; k < csize; ++k)               // rank order: identical totals in every block
+            {
+                const double* rp = cluster.map_shared_rank(&s_cpart[parity][tid][0], k);
+                su += rp[0]; sl += rp[1];
+            }
             s_ub[tid] = (float)su; s_lb[tid] = (float)sl;
         }
+        parity ^= 1;
         __syncthreads();
 
         // ---- (f) best of the batch (fgoicp.cpp:139-145): first minimum in pop order
@@ -215,7 +246,8 @@ k_bnb_r3(LutDev L, const float4* __restrict__ data, int ns, const float4* __rest
         __syncthreads();
     }
 
-    if (tid == 0)
+    cluster.sync();                                       // nobody exits while a peer may still read its partials
+    if (tid == 0 && crank == 0)
     {
         BnbOut o;
         o.best_ub = s_best_ub;
@@ -228,32 +260,47 @@ k_bnb_r3(LutDev L, const float4* __restrict__ data, int ns, const float4* __rest
 // ---------------------------------------------------------------------------------------------
 
 template <int SAMPLER, int NWARPS>
-static int launch_bnb_t(fgoicp_ctx* c, const float4* d_rot, int Rn, int fix_rot, float best_sse, float thr, BnbOut* d_out)
+static int launch_bnb_t(fgoicp_ctx* c, const float4* d_rot, int Rn, int csize, int fix_rot, float best_sse, float thr, BnbOut* d_out)
 {
     size_t smem = sizeof(unsigned long long) * BNB_POOL;
     FG_CUDA(cudaFuncSetAttribute(k_bnb_r3<SAMPLER, NWARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_bnb_r3<SAMPLER, NWARPS><<<Rn, NWARPS * 32, smem, c->stream>>>(c->lut, c->d_data, (int)c->ns, d_rot, fix_rot,
-                                                                 best_sse, thr, BNB_BATCH_MAX, d_out);
-    FG_CUDA(cudaGetLastError());
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(Rn * csize));
+    cfg.blockDim = dim3(NWARPS * 32);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = c->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    int ns = (int)c->ns, bm = BNB_BATCH_MAX;
+    FG_CUDA(cudaLaunchKernelEx(&cfg, k_bnb_r3<SAMPLER, NWARPS>, c->lut, (const float4*)c->d_data, ns, d_rot, fix_rot,
+                               best_sse, thr, bm, d_out));
     return FGOICP_OK;
 }
 
 template <int NWARPS>
-static int launch_bnb_w(fgoicp_ctx* c, const float4* d_rot, int Rn, int fix_rot, float best_sse, float thr, BnbOut* d_out)
+static int launch_bnb_w(fgoicp_ctx* c, const float4* d_rot, int Rn, int csize, int fix_rot, float best_sse, float thr, BnbOut* d_out)
 {
     switch (c->sampler)
     {
-    case FGOICP_SAMPLER_PACKED: return launch_bnb_t<FGOICP_SAMPLER_PACKED, NWARPS>(c, d_rot, Rn, fix_rot, best_sse, thr, d_out);
-    case FGOICP_SAMPLER_TEX:    return launch_bnb_t<FGOICP_SAMPLER_TEX, NWARPS>(c, d_rot, Rn, fix_rot, best_sse, thr, d_out);
-    default:                    return launch_bnb_t<FGOICP_SAMPLER_GRID, NWARPS>(c, d_rot, Rn, fix_rot, best_sse, thr, d_out);
+    case FGOICP_SAMPLER_PACKED: return launch_bnb_t<FGOICP_SAMPLER_PACKED, NWARPS>(c, d_rot, Rn, csize, fix_rot, best_sse, thr, d_out);
+    case FGOICP_SAMPLER_TEX:    return launch_bnb_t<FGOICP_SAMPLER_TEX, NWARPS>(c, d_rot, Rn, csize, fix_rot, best_sse, thr, d_out);
+    default:                    return launch_bnb_t<FGOICP_SAMPLER_GRID, NWARPS>(c, d_rot, Rn, csize, fix_rot, best_sse, thr, d_out);
     }
 }
 
-// Few rotation cubes: big blocks (latency).  Many: smaller blocks, several per SM (throughput).
+// Cluster size: enough blocks for ~8 resident waves' worth of granularity, at most 8 (portable limit),
+// at least 1; never so large that a block gets fewer than 256 points.  FGOICP_BNB_CLUSTER overrides.
 static int launch_bnb(fgoicp_ctx* c, const float4* d_rot, int Rn, int fix_rot, float best_sse, float thr, BnbOut* d_out)
 {
-    if (Rn >= 3 * c->sm_count) return launch_bnb_w<8>(c, d_rot, Rn, fix_rot, best_sse, thr, d_out);
-    return launch_bnb_w<16>(c, d_rot, Rn, fix_rot, best_sse, thr, d_out);
+    int slots = 3 * c->sm_count;                       // 8-warp blocks resident at once (register-limited)
+    int want = (8 * slots + Rn - 1) / Rn;
+    int csize = 1;
+    while (csize < 8 && csize < want) csize <<= 1;
+    while (csize > 1 && (int)c->ns / csize < 256) csize >>= 1;
+    if (const char* e = getenv("FGOICP_BNB_CLUSTER")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) csize = v; }
+    return launch_bnb_w<8>(c, d_rot, Rn, csize, fix_rot, best_sse, thr, d_out);
 }
 
 static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -309,8 +356,8 @@ extern "C" int fgoicp_bnb_r3(fgoicp_ctx* c, const float rot_xyz_span[4], int fix
     return fgoicp_bnb_r3_batch(c, rot_xyz_span, 1, fix_rot, best_sse, sse_threshold, best_ub, best_t, evals);
 }
 
-int fg_icp_run(fgoicp_ctx* c, const float R0[9], const float t0[3], int max_iter, float thr,
-               float* sse, float R[9], float t[3], int* iters);
+int fg_icp_run_batch(fgoicp_ctx* c, const float* R0s, const float* t0s, int n, int max_iter, float thr,
+                     float* sse, float* R, float* t, int* iters);
 
 // Rotation(x, y, z) on the host: same unfused fp32 arithmetic as the reference (common.hpp:37-57)
 static void host_rotation(float x, float y, float z, float* R)
@@ -354,21 +401,33 @@ extern "C" int fgoicp_so3_level_ub(fgoicp_ctx* c, const float* cubes, int n,
     int best_idx = -1;
     cudaEvent_t e0 = c->ev0, e1 = c->ev1;
     FG_CUDA(cudaEventRecord(e0, c->stream));
+    std::vector<int> who;
     for (int i = 0; i < n; ++i)
+        if ((double)ub[i] < (double)best_sse * 1.8) who.push_back(i);
+    if (!who.empty())
     {
-        if (!((double)ub[i] < (double)best_sse * 1.8)) continue;
-        float R0[9], e, R[9], t[3];
-        int it = 0;
-        host_rotation(cubes[4 * i], cubes[4 * i + 1], cubes[4 * i + 2], R0);
-        rc = fg_icp_run(c, R0, bt + 3 * i, 100, (float)0.005, &e, R, t, &it);         // fgoicp.cpp:76
-        if (rc) return rc;
-        ++n_icp; icp_iters += (uint32_t)it;
-        if (e < *io_best_sse)                                                          // fgoicp.cpp:79-84
+        const int m = (int)who.size();
+        std::vector<float> R0(9 * (size_t)m), t0(3 * (size_t)m), e(m), R(9 * (size_t)m), t(3 * (size_t)m);
+        std::vector<int> it(m);
+        for (int k = 0; k < m; ++k)
         {
-            *io_best_sse = e;
-            best_idx = i;
-            memcpy(io_best_R, R, sizeof(float) * 9);
-            memcpy(io_best_t, t, sizeof(float) * 3);
+            int i = who[k];
+            host_rotation(cubes[4 * i], cubes[4 * i + 1], cubes[4 * i + 2], &R0[9 * k]);
+            memcpy(&t0[3 * k], bt + 3 * i, 3 * sizeof(float));
+        }
+        // all promising cubes refine concurrently (independent of one another)          fgoicp.cpp:76
+        rc = fg_icp_run_batch(c, R0.data(), t0.data(), m, 100, (float)0.005, e.data(), R.data(), t.data(), it.data());
+        if (rc) return rc;
+        for (int k = 0; k < m; ++k)
+        {
+            ++n_icp; icp_iters += (uint32_t)it[k];
+            if (e[k] < *io_best_sse)                                                      // fgoicp.cpp:79-84, ascending cube order
+            {
+                *io_best_sse = e[k];
+                best_idx = who[k];
+                memcpy(io_best_R, &R[9 * k], sizeof(float) * 9);
+                memcpy(io_best_t, &t[3 * k], sizeof(float) * 3);
+            }
         }
     }
     FG_CUDA(cudaEventRecord(e1, c->stream));

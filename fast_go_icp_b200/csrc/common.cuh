@@ -97,7 +97,8 @@ struct fgoicp_ctx
     // ICP state
     float4* d_work = nullptr;                 // working copy W  [ns]
     unsigned long long* d_nnkey = nullptr;    // packed (value bits << 32 | index) [ns]
-    double* d_icp = nullptr;                  // small state block, see nn_icp.cu
+    void* d_icp = nullptr;                    // per-instance ICP state blocks, see nn_icp.cu
+    int icp_capacity = 0;                     // concurrent ICP instances the three buffers are sized for
 };
 
 namespace fg

@@ -578,9 +578,6 @@ extern "C" int fgoicp_ctx_create(const float* model_xyz, size_t nt, const float*
     size_t cells = (size_t)L.dx * L.dy * L.dz;
     FG_TRY(cudaMalloc(&c->d_grid, sizeof(float) * cells));
     L.grid = c->d_grid;
-    FG_TRY(cudaMalloc(&c->d_work, sizeof(float4) * ns));
-    FG_TRY(cudaMalloc(&c->d_nnkey, sizeof(unsigned long long) * ns));
-    FG_TRY(cudaMalloc(&c->d_icp, sizeof(double) * 256));
 
     FG_TRY(cudaEventRecord(c->ev0, c->stream));
     rc = build_cell_grid(c, d_P);

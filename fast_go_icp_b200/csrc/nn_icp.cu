@@ -39,6 +39,25 @@ struct IcpState
     double sums[16];
 };
 
+// One 512-byte block per concurrent ICP instance (the ICPs of all promising cubes of a level run together).
+struct IcpInst
+{
+    IcpState st;
+    float pose0[12];             // seed pose (R0 column-major, t0)
+};
+#define ICP_INST_BYTES 512
+static_assert(sizeof(IcpInst) <= ICP_INST_BYTES, "IcpInst must fit its slot");
+#define ICP_MAX_BATCH 64
+
+enum { SRC_DATA = 0, SRC_WORK = 1 };                               // query cloud: shared data cloud / instance working copy
+enum { POSE_NONE = 0, POSE_SEED = 1, POSE_CUR = 2, POSE_INC = 3 }; // transform applied to the source points first
+
+__device__ __forceinline__ IcpInst* fg_inst(char* base, int k) { return (IcpInst*)(base + (size_t)k * ICP_INST_BYTES); }
+__device__ __forceinline__ const float* fg_pose(IcpInst* in, int sel)
+{
+    return sel == POSE_SEED ? in->pose0 : (sel == POSE_CUR ? in->st.R : (sel == POSE_INC ? in->st.Rd : nullptr));
+}
+
 // smallest float x with sqrtf(x) == s  (so that  sqrtf(d) < s  <=>  d < lo(s))
 __device__ __forceinline__ float fg_sqrt_preimage_lo(float s)
 {
@@ -60,11 +79,15 @@ __device__ __forceinline__ float fg_sqrt_preimage_lo(float s)
 template <int ROOTED>
 __global__ void __launch_bounds__(NN_THREADS)
 k_nn_brute(const float4* __restrict__ model, int nt, int chunk,
-           const float4* __restrict__ src, int ns, const float* __restrict__ pose,
-           unsigned long long* __restrict__ keys, const int* __restrict__ done_flag)
+           const float4* __restrict__ data, const float4* __restrict__ work_base, int ns, char* inst_base,
+           int src_sel, int pose_sel, unsigned long long* __restrict__ keys_base, int check_done)
 {
     __shared__ float4 tile[NN_TILE];
-    if (done_flag && *done_flag) return;
+    IcpInst* inst = fg_inst(inst_base, blockIdx.z);
+    if (check_done && inst->st.done) return;
+    const float4* src = src_sel == SRC_DATA ? data : work_base + (size_t)blockIdx.z * ns;
+    const float* pose = fg_pose(inst, pose_sel);
+    unsigned long long* keys = keys_base + (size_t)blockIdx.z * ns;
 
     float qx[NN_QPT], qy[NN_QPT], qz[NN_QPT];
     float best[NN_QPT], thr[NN_QPT];
@@ -168,10 +191,14 @@ __device__ __forceinline__ float fg_sqrt_preimage_hi(float s)
 #define NNG_WARPS 4
 template <int ROOTED>
 __global__ void __launch_bounds__(NNG_WARPS * 32)
-k_nn_grid(CellGrid g, LutDev L, float res, const float4* __restrict__ src, int ns, const float* __restrict__ pose,
-          unsigned long long* __restrict__ keys, const int* __restrict__ done_flag)
+k_nn_grid(CellGrid g, LutDev L, float res, const float4* __restrict__ data, const float4* __restrict__ work_base,
+          int ns, char* inst_base, int src_sel, int pose_sel, unsigned long long* __restrict__ keys_base, int check_done)
 {
-    if (done_flag && *done_flag) return;
+    IcpInst* inst = fg_inst(inst_base, blockIdx.y);
+    if (check_done && inst->st.done) return;
+    const float4* src = src_sel == SRC_DATA ? data : work_base + (size_t)blockIdx.y * ns;
+    const float* pose = fg_pose(inst, pose_sel);
+    unsigned long long* keys = keys_base + (size_t)blockIdx.y * ns;
     const int lane = threadIdx.x & 31;
     const int i = blockIdx.x * NNG_WARPS + (threadIdx.x >> 5);
     if (i >= ns) return;
@@ -316,9 +343,11 @@ __device__ __forceinline__ void fg_block_sum(double (&v)[N], double* out /* shar
 
 // SSE = sum of the winning squared distances (keys carry d2 bits in the high word), fp64 -> float
 __global__ void __launch_bounds__(1024)
-k_sse_reduce(const unsigned long long* __restrict__ keys, int ns, IcpState* st, float* out)
+k_sse_reduce(const unsigned long long* __restrict__ keys_base, int ns, char* inst_base, int check_done, float* out)
 {
-    if (st && st->done) return;
+    IcpInst* inst = fg_inst(inst_base, blockIdx.x);
+    if (check_done && inst->st.done) return;
+    const unsigned long long* keys = keys_base + (size_t)blockIdx.x * ns;
     __shared__ double s_out[1];
     double v[1] = { 0.0 };
     for (int i = threadIdx.x; i < ns; i += blockDim.x)
@@ -327,40 +356,46 @@ k_sse_reduce(const unsigned long long* __restrict__ keys, int ns, IcpState* st, 
     if (threadIdx.x == 0)
     {
         float sse = (float)s_out[0];
-        if (st) st->sse = sse;
-        if (out) *out = sse;
+        inst->st.sse = sse;
+        if (out) out[blockIdx.x] = sse;
     }
 }
 
 // ---- ICP -----------------------------------------------------------------------------------
 
-__global__ void k_icp_init(IcpState* st, const float* __restrict__ pose0, int max_iter, float thr)
+__global__ void k_icp_init(char* inst_base, int max_iter, float thr)
 {
-    for (int k = 0; k < 9; ++k) { st->R[k] = pose0[k]; st->lastR[k] = pose0[k]; }
-    for (int k = 0; k < 3; ++k) { st->t[k] = pose0[9 + k]; st->lastT[k] = pose0[9 + k]; }
+    IcpInst* in = fg_inst(inst_base, blockIdx.x);
+    IcpState* st = &in->st;
+    for (int k = 0; k < 9; ++k) { st->R[k] = in->pose0[k]; st->lastR[k] = in->pose0[k]; }
+    for (int k = 0; k < 3; ++k) { st->t[k] = in->pose0[9 + k]; st->lastT[k] = in->pose0[9 + k]; }
     st->sse = FG_INF; st->last_sse = __fmul_rn(2.0f, FG_INF);      // icp3d.cu:89-90
     st->thr = thr; st->iter = 0; st->max_iter = max_iter; st->done = 0;
     st->out_iters = 0;
 }
 
-// W_i = R * p_i + t  (icp3d.cu:85 with the seed pose; :100 with the increment)
-__global__ void k_icp_transform(const float4* src, float4* dst, int ns,   /* may alias: in-place update */
-                                const float* __restrict__ pose, const int* __restrict__ done_flag)
+// W_i = R * p_i + t  (icp3d.cu:85 with the seed pose; :100 with the increment, in place)
+__global__ void k_icp_transform(const float4* __restrict__ data, float4* work_base, int ns, char* inst_base,
+                                int src_sel, int pose_sel, int check_done)
 {
-    if (done_flag && *done_flag) return;
+    IcpInst* inst = fg_inst(inst_base, blockIdx.y);
+    if (check_done && inst->st.done) return;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= ns) return;
+    float4* work = work_base + (size_t)blockIdx.y * ns;
+    const float* pose = fg_pose(inst, pose_sel);
     float R[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) R[k] = pose[k];
-    float4 p = src[i];
+    float4 p = src_sel == SRC_DATA ? data[i] : work[i];
     float3 rp = fg_rotate(R, p.x, p.y, p.z);
-    dst[i] = make_float4(__fadd_rn(rp.x, pose[9]), __fadd_rn(rp.y, pose[10]), __fadd_rn(rp.z, pose[11]), p.w);
+    work[i] = make_float4(__fadd_rn(rp.x, pose[9]), __fadd_rn(rp.y, pose[10]), __fadd_rn(rp.z, pose[11]), p.w);
 }
 
 // loop head: while (iter++ < max_iter && (last_sse - sse) > thr * last_sse)   (icp3d.cu:94-98)
-__global__ void k_icp_begin(IcpState* st)
+__global__ void k_icp_begin(char* inst_base)
 {
+    IcpState* st = &fg_inst(inst_base, blockIdx.x)->st;
     if (st->done) return;
     bool go = (st->iter++ < st->max_iter) &&
               (__fsub_rn(st->last_sse, st->sse) > __fmul_rn(st->thr, st->last_sse));
@@ -382,10 +417,13 @@ __global__ void k_icp_begin(IcpState* st)
 
 // centroids of the working cloud and of its correspondences (icp3d.cu:150-156)
 __global__ void __launch_bounds__(1024)
-k_icp_centroids(const float4* __restrict__ W, const unsigned long long* __restrict__ keys,
-                const float4* __restrict__ model, int ns, IcpState* st)
+k_icp_centroids(const float4* __restrict__ work_base, const unsigned long long* __restrict__ keys_base,
+                const float4* __restrict__ model, int ns, char* inst_base)
 {
+    IcpState* st = &fg_inst(inst_base, blockIdx.x)->st;
     if (st->done) return;
+    const float4* W = work_base + (size_t)blockIdx.x * ns;
+    const unsigned long long* keys = keys_base + (size_t)blockIdx.x * ns;
     __shared__ double s_out[6];
     double v[6] = { 0, 0, 0, 0, 0, 0 };
     for (int i = threadIdx.x; i < ns; i += blockDim.x)
@@ -405,10 +443,13 @@ k_icp_centroids(const float4* __restrict__ W, const unsigned long long* __restri
 
 // cross-covariance of the centred clouds, closest rotation, pose update (icp3d.cu:158-172, 101-102)
 __global__ void __launch_bounds__(1024)
-k_icp_procrustes(const float4* __restrict__ W, const unsigned long long* __restrict__ keys,
-                 const float4* __restrict__ model, int ns, IcpState* st)
+k_icp_procrustes(const float4* __restrict__ work_base, const unsigned long long* __restrict__ keys_base,
+                 const float4* __restrict__ model, int ns, char* inst_base)
 {
+    IcpState* st = &fg_inst(inst_base, blockIdx.x)->st;
     if (st->done) return;
+    const float4* W = work_base + (size_t)blockIdx.x * ns;
+    const unsigned long long* keys = keys_base + (size_t)blockIdx.x * ns;
     __shared__ double s_out[9];
     float ab[3] = { st->abar[0], st->abar[1], st->abar[2] };
     float bb[3] = { st->bbar[0], st->bbar[1], st->bbar[2] };
@@ -454,70 +495,86 @@ k_icp_procrustes(const float4* __restrict__ W, const unsigned long long* __restr
 
 // ---------------------------------------------------------------------------------------------
 
-static void nn_geometry(const fgoicp_ctx* c, dim3& grid, int& chunk)
+// per-context ICP buffers sized for `n` concurrent instances
+static int ensure_icp_capacity(fgoicp_ctx* c, int n)
+{
+    if (n <= c->icp_capacity) return FGOICP_OK;
+    FG_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(c->d_work); cudaFree(c->d_nnkey); cudaFree(c->d_icp);
+    c->d_work = nullptr; c->d_nnkey = nullptr; c->d_icp = nullptr; c->icp_capacity = 0;
+    FG_CUDA(cudaMalloc(&c->d_work, sizeof(float4) * c->ns * n));
+    FG_CUDA(cudaMalloc(&c->d_nnkey, sizeof(unsigned long long) * c->ns * n));
+    FG_CUDA(cudaMalloc(&c->d_icp, (size_t)ICP_INST_BYTES * n + 256));
+    c->icp_capacity = n;
+    return FGOICP_OK;
+}
+
+static void nn_geometry(const fgoicp_ctx* c, dim3& grid, int& chunk, int n_inst)
 {
     int qtiles = (int)((c->ns + NN_THREADS * NN_QPT - 1) / (NN_THREADS * NN_QPT));
-    int want_chunks = std::max(1, (4 * c->sm_count + qtiles - 1) / qtiles);
+    int want_chunks = std::max(1, (4 * c->sm_count + qtiles * n_inst - 1) / (qtiles * n_inst));
     chunk = (int)((c->nt + want_chunks - 1) / want_chunks);
     chunk = ((chunk + NN_TILE - 1) / NN_TILE) * NN_TILE;
     int nchunks = (int)((c->nt + chunk - 1) / chunk);
-    grid = dim3(qtiles, nchunks);
+    grid = dim3(qtiles, nchunks, n_inst);
 }
 
-// enqueue: keys := NN of (pose ? pose*src : src)
-static int enqueue_nn(fgoicp_ctx* c, const float4* d_src, const float* d_pose, int rooted, const int* d_done)
+// enqueue for instances [0, n_inst): keys := NN of pose(src)
+static int enqueue_nn(fgoicp_ctx* c, int n_inst, int src_sel, int pose_sel, int rooted, int check_done)
 {
+    char* inst = (char*)c->d_icp;
     if (c->nn_mode == 0)
     {
         CellGrid g;
         g.start = c->d_cell_start; g.pts = c->d_cell_M;
         g.nx = c->cnx; g.ny = c->cny; g.nz = c->cnz; g.h = c->cell_h; g.inv_h = c->cell_inv_h;
-        unsigned blocks = (unsigned)((c->ns + NNG_WARPS - 1) / NNG_WARPS);
+        dim3 grid((unsigned)((c->ns + NNG_WARPS - 1) / NNG_WARPS), (unsigned)n_inst);
         if (rooted)
-            k_nn_grid<1><<<blocks, NNG_WARPS * 32, 0, c->stream>>>(g, c->lut, c->res, d_src, (int)c->ns, d_pose, c->d_nnkey, d_done);
+            k_nn_grid<1><<<grid, NNG_WARPS * 32, 0, c->stream>>>(g, c->lut, c->res, c->d_data, c->d_work, (int)c->ns, inst, src_sel, pose_sel, c->d_nnkey, check_done);
         else
-            k_nn_grid<0><<<blocks, NNG_WARPS * 32, 0, c->stream>>>(g, c->lut, c->res, d_src, (int)c->ns, d_pose, c->d_nnkey, d_done);
+            k_nn_grid<0><<<grid, NNG_WARPS * 32, 0, c->stream>>>(g, c->lut, c->res, c->d_data, c->d_work, (int)c->ns, inst, src_sel, pose_sel, c->d_nnkey, check_done);
         FG_CUDA(cudaGetLastError());
         return FGOICP_OK;
     }
     dim3 grid; int chunk;
-    nn_geometry(c, grid, chunk);
-    FG_CUDA(cudaMemsetAsync(c->d_nnkey, 0xff, sizeof(unsigned long long) * c->ns, c->stream));
+    nn_geometry(c, grid, chunk, n_inst);
+    FG_CUDA(cudaMemsetAsync(c->d_nnkey, 0xff, sizeof(unsigned long long) * c->ns * n_inst, c->stream));
     if (rooted)
-        k_nn_brute<1><<<grid, NN_THREADS, 0, c->stream>>>(c->d_model, (int)c->nt, chunk, d_src, (int)c->ns, d_pose, c->d_nnkey, d_done);
+        k_nn_brute<1><<<grid, NN_THREADS, 0, c->stream>>>(c->d_model, (int)c->nt, chunk, c->d_data, c->d_work, (int)c->ns, inst, src_sel, pose_sel, c->d_nnkey, check_done);
     else
-        k_nn_brute<0><<<grid, NN_THREADS, 0, c->stream>>>(c->d_model, (int)c->nt, chunk, d_src, (int)c->ns, d_pose, c->d_nnkey, d_done);
+        k_nn_brute<0><<<grid, NN_THREADS, 0, c->stream>>>(c->d_model, (int)c->nt, chunk, c->d_data, c->d_work, (int)c->ns, inst, src_sel, pose_sel, c->d_nnkey, check_done);
     FG_CUDA(cudaGetLastError());
     return FGOICP_OK;
 }
 
-static int upload_pose(fgoicp_ctx* c, const float R[9], const float t[3], float** d_pose_out)
+// seed poses of n instances -> pose0 slots (through pinned staging)
+static int upload_seeds(fgoicp_ctx* c, const float* R0s, const float* t0s, int n)
 {
-    int rc = fg::ensure_pinned(c, 256);
+    int rc = ensure_icp_capacity(c, n);
+    if (rc) return rc;
+    rc = fg::ensure_pinned(c, (size_t)n * (sizeof(IcpInst) + 64) + 4096);
     if (rc) return rc;
     float* hp = (float*)c->h_pinned;
-    memcpy(hp, R, 9 * sizeof(float));
-    memcpy(hp + 9, t, 3 * sizeof(float));
-    // pose staging area: the tail of the ICP state block (beyond IcpState)
-    float* d_pose = (float*)((char*)c->d_icp + 1024);
-    FG_CUDA(cudaMemcpyAsync(d_pose, hp, 12 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-    *d_pose_out = d_pose;
+    for (int k = 0; k < n; ++k)
+    {
+        memcpy(hp + 12 * k, R0s + 9 * k, 9 * sizeof(float));
+        memcpy(hp + 12 * k + 9, t0s + 3 * k, 3 * sizeof(float));
+    }
+    FG_CUDA(cudaMemcpy2DAsync((char*)c->d_icp + offsetof(IcpInst, pose0), ICP_INST_BYTES, hp, 12 * sizeof(float),
+                              12 * sizeof(float), n, cudaMemcpyHostToDevice, c->stream));
     return FGOICP_OK;
 }
-
-static_assert(sizeof(IcpState) <= 1024, "IcpState must fit the first KiB of the state block");
 
 extern "C" int fgoicp_sse(fgoicp_ctx* c, const float R[9], const float t[3], float* sse)
 {
     FG_ARG(c && R && t && sse, "NULL pointer");
     FG_CUDA(cudaSetDevice(c->device));
-    float* d_pose = nullptr;
-    int rc = upload_pose(c, R, t, &d_pose);
+    int rc = upload_seeds(c, R, t, 1);
     if (rc) return rc;
-    rc = enqueue_nn(c, c->d_data, d_pose, 0, nullptr);
+    rc = enqueue_nn(c, 1, SRC_DATA, POSE_SEED, 0, 0);
     if (rc) return rc;
-    float* d_out = d_pose + 16;
-    k_sse_reduce<<<1, 1024, 0, c->stream>>>(c->d_nnkey, (int)c->ns, nullptr, d_out);
+    float* d_out = (float*)((char*)c->d_icp + (size_t)ICP_INST_BYTES * c->icp_capacity);
+    k_sse_reduce<<<1, 1024, 0, c->stream>>>(c->d_nnkey, (int)c->ns, (char*)c->d_icp, 0, d_out);
     FG_CUDA(cudaGetLastError());
     float* hp = (float*)c->h_pinned;
     FG_CUDA(cudaMemcpyAsync(hp + 32, d_out, sizeof(float), cudaMemcpyDeviceToHost, c->stream));
@@ -530,16 +587,16 @@ extern "C" int fgoicp_nn(fgoicp_ctx* c, const float R[9], const float t[3], int 
 {
     FG_ARG(c && R && t, "NULL pointer");
     FG_CUDA(cudaSetDevice(c->device));
-    float* d_pose = nullptr;
-    int rc = upload_pose(c, R, t, &d_pose);
+    int rc = upload_seeds(c, R, t, 1);
     if (rc) return rc;
-    rc = enqueue_nn(c, c->d_data, d_pose, rooted, nullptr);
+    rc = enqueue_nn(c, 1, SRC_DATA, POSE_SEED, rooted, 0);
     if (rc) return rc;
     size_t ns = c->ns;
     rc = fg::ensure_scratch(c, ns * 8);
     if (rc) return rc;
     int* d_idx = (int*)c->d_scratch;
     float* d_d2 = (float*)c->d_scratch + ns;
+    const float* d_pose = (const float*)((char*)c->d_icp + offsetof(IcpInst, pose0));
     k_nn_finish<<<(unsigned)((ns + 255) / 256), 256, 0, c->stream>>>(c->d_nnkey, c->d_model, c->d_data, (int)ns, d_pose, d_idx, d_d2);
     FG_CUDA(cudaGetLastError());
     if (idx) FG_CUDA(cudaMemcpyAsync(idx, d_idx, ns * 4, cudaMemcpyDeviceToHost, c->stream));
@@ -548,58 +605,64 @@ extern "C" int fgoicp_nn(fgoicp_ctx* c, const float R[9], const float t[3], int 
     return FGOICP_OK;
 }
 
-// Runs one ICP to completion on the context stream; results stay in the device state block and
-// are copied to the pinned area.  Used by fgoicp_icp and by the level driver in bnb.cu.
+// Runs n independent ICPs to completion, concurrently (instance = blockIdx.y / blockIdx.x of every kernel).
+// R0s[n][9], t0s[n][3] -> sse[n], R[n][9], t[n][3], iters[n].  Used by fgoicp_icp and by the level driver.
+int fg_icp_run_batch(fgoicp_ctx* c, const float* R0s, const float* t0s, int n, int max_iter, float thr,
+                     float* sse, float* R, float* t, int* iters)
+{
+    for (int base = 0; base < n; base += ICP_MAX_BATCH)
+    {
+        int m = std::min(ICP_MAX_BATCH, n - base);
+        int rc = upload_seeds(c, R0s + 9 * base, t0s + 3 * base, m);
+        if (rc) return rc;
+        char* inst = (char*)c->d_icp;
+        int ns = (int)c->ns;
+        dim3 pgrid((unsigned)((ns + 255) / 256), (unsigned)m);
+        k_icp_init<<<m, 1, 0, c->stream>>>(inst, max_iter, thr);
+        k_icp_transform<<<pgrid, 256, 0, c->stream>>>(c->d_data, c->d_work, ns, inst, SRC_DATA, POSE_SEED, 0);   // icp3d.cu:85
+        k_icp_begin<<<m, 1, 0, c->stream>>>(inst);           // loop head of iteration 1
+        FG_CUDA(cudaGetLastError());
+        char* hinst = (char*)c->h_pinned + 4096;
+        const int burst = 4;     // iterations enqueued between polls of the done flags
+        bool all_done = false;
+        for (int guard = 0; guard <= max_iter + burst && !all_done; guard += burst)
+        {
+            for (int b = 0; b < burst; ++b)
+            {
+                // one loop body per instance still running; every kernel returns at once for finished ones
+                rc = enqueue_nn(c, m, SRC_WORK, POSE_NONE, 1, 1);                                        // icp3d.cu:146
+                if (rc) return rc;
+                k_icp_centroids<<<m, 1024, 0, c->stream>>>(c->d_work, c->d_nnkey, c->d_model, ns, inst);
+                k_icp_procrustes<<<m, 1024, 0, c->stream>>>(c->d_work, c->d_nnkey, c->d_model, ns, inst);
+                k_icp_transform<<<pgrid, 256, 0, c->stream>>>(c->d_data, c->d_work, ns, inst, SRC_WORK, POSE_INC, 1);  // icp3d.cu:100
+                rc = enqueue_nn(c, m, SRC_DATA, POSE_CUR, 0, 1);                                         // icp3d.cu:103
+                if (rc) return rc;
+                k_sse_reduce<<<m, 1024, 0, c->stream>>>(c->d_nnkey, ns, inst, 1, nullptr);
+                k_icp_begin<<<m, 1, 0, c->stream>>>(inst);   // loop head of the next iteration (or publish the result)
+                FG_CUDA(cudaGetLastError());
+            }
+            FG_CUDA(cudaMemcpyAsync(hinst, inst, (size_t)ICP_INST_BYTES * m, cudaMemcpyDeviceToHost, c->stream));
+            FG_CUDA(cudaStreamSynchronize(c->stream));
+            all_done = true;
+            for (int k = 0; k < m; ++k) all_done = all_done && ((IcpInst*)(hinst + (size_t)k * ICP_INST_BYTES))->st.done;
+        }
+        if (!all_done) { fg::set_error("ICP loop did not terminate"); return FGOICP_ERR_STATE; }
+        for (int k = 0; k < m; ++k)
+        {
+            const IcpState& st = ((IcpInst*)(hinst + (size_t)k * ICP_INST_BYTES))->st;
+            if (sse) sse[base + k] = st.out_sse;
+            if (R) memcpy(R + 9 * (base + k), st.outR, 9 * sizeof(float));
+            if (t) memcpy(t + 3 * (base + k), st.outT, 3 * sizeof(float));
+            if (iters) iters[base + k] = st.out_iters;
+        }
+    }
+    return FGOICP_OK;
+}
+
 int fg_icp_run(fgoicp_ctx* c, const float R0[9], const float t0[3], int max_iter, float thr,
                float* sse, float R[9], float t[3], int* iters)
 {
-    float* d_pose0 = nullptr;
-    int rc = upload_pose(c, R0, t0, &d_pose0);
-    if (rc) return rc;
-    IcpState* st = (IcpState*)c->d_icp;
-    int ns = (int)c->ns;
-    unsigned pb = (unsigned)((ns + 255) / 256);
-    k_icp_init<<<1, 1, 0, c->stream>>>(st, d_pose0, max_iter, thr);
-    k_icp_transform<<<pb, 256, 0, c->stream>>>(c->d_data, c->d_work, ns, d_pose0, nullptr);      // icp3d.cu:85
-    FG_CUDA(cudaGetLastError());
-    IcpState* hst = (IcpState*)((char*)c->h_pinned + 512);
-    rc = fg::ensure_pinned(c, 512 + sizeof(IcpState));
-    if (rc) return rc;
-    hst = (IcpState*)((char*)c->h_pinned + 512);
-    const int* d_done = &st->done;
-    const int burst = 4;     // iterations enqueued between polls of the done flag
-    for (int guard = 0; guard <= max_iter + burst; guard += burst)
-    {
-        for (int b = 0; b < burst; ++b)
-        {
-            k_icp_begin<<<1, 1, 0, c->stream>>>(st);
-            rc = enqueue_nn(c, c->d_work, nullptr, 1, d_done);                                   // icp3d.cu:146
-            if (rc) return rc;
-            k_icp_centroids<<<1, 1024, 0, c->stream>>>(c->d_work, c->d_nnkey, c->d_model, ns, st);
-            k_icp_procrustes<<<1, 1024, 0, c->stream>>>(c->d_work, c->d_nnkey, c->d_model, ns, st);
-            k_icp_transform<<<pb, 256, 0, c->stream>>>(c->d_work, c->d_work, ns, st->Rd, d_done);  // icp3d.cu:100
-            rc = enqueue_nn(c, c->d_data, st->R, 0, d_done);                                     // icp3d.cu:103
-            if (rc) return rc;
-            k_sse_reduce<<<1, 1024, 0, c->stream>>>(c->d_nnkey, ns, st, nullptr);
-            FG_CUDA(cudaGetLastError());
-        }
-        FG_CUDA(cudaMemcpyAsync(hst, st, sizeof(IcpState), cudaMemcpyDeviceToHost, c->stream));
-        FG_CUDA(cudaStreamSynchronize(c->stream));
-        if (hst->done) break;
-    }
-    if (!hst->done)
-    {
-        // the loop above always reaches the head once more after max_iter iterations
-        k_icp_begin<<<1, 1, 0, c->stream>>>(st);
-        FG_CUDA(cudaMemcpyAsync(hst, st, sizeof(IcpState), cudaMemcpyDeviceToHost, c->stream));
-        FG_CUDA(cudaStreamSynchronize(c->stream));
-    }
-    if (!hst->done) { fg::set_error("ICP loop did not terminate"); return FGOICP_ERR_STATE; }
-    if (sse) *sse = hst->out_sse;
-    if (R) memcpy(R, hst->outR, 9 * sizeof(float));
-    if (t) memcpy(t, hst->outT, 3 * sizeof(float));
-    if (iters) *iters = hst->out_iters;
-    return FGOICP_OK;
+    return fg_icp_run_batch(c, R0, t0, 1, max_iter, thr, sse, R, t, iters);
 }
 
 extern "C" int fgoicp_icp(fgoicp_ctx* c, const float R0[9], const float t0[3], int max_iter, float thr,
@@ -608,5 +671,5 @@ extern "C" int fgoicp_icp(fgoicp_ctx* c, const float R0[9], const float t0[3], i
     FG_ARG(c && R0 && t0, "NULL pointer");
     FG_ARG(max_iter >= 0, "max_iter must be non-negative");
     FG_CUDA(cudaSetDevice(c->device));
-    return fg_icp_run(c, R0, t0, max_iter, thr, sse, R, t, iters);
+    return fg_icp_run_batch(c, R0, t0, 1, max_iter, thr, sse, R, t, iters);
 }

@@ -41,21 +41,25 @@ __device__ __forceinline__ void fg_eval_chunk(const LutDev& L, const float4* __r
 #pragma unroll
         for (int k = 0; k < BD_CPW; ++k) { acc_ub[k] = 0.0; acc_lb[k] = 0.0; }
 
-        for (int i = p0 + ps * 32 + lane; i < p1; i += Wp * 32)
+        const int i0 = p0 + ps * 32 + lane, stride = Wp * 32;
+        float4 p_next = i0 < p1 ? __ldg(&data[i0]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = i0; i < p1; i += stride)
         {
-            float4 p = __ldg(&data[i]);
+            float4 p = p_next;
+            if (i + stride < p1) p_next = __ldg(&data[i + stride]);     // prefetch: hides the point load behind the gathers
             float3 rp = fg_rotate(R, p.x, p.y, p.z);
             // rot_uncertain_radius = 2 * |p|^2 * sin(half_angle)  (SASS: FADD r,r ; FMUL)
             float rot_r = __fmul_rn(__fadd_rn(p.w, p.w), sin_half);
-            float d2[BD_CPW];
+            // issue all BD_CPW gathers before blending any of them: one DRAM round trip instead of four
+            SampleReq req[BD_CPW];
 #pragma unroll
             for (int k = 0; k < BD_CPW; ++k)
-                d2[k] = fg_sample<SAMPLER>(L, __fadd_rn(rp.x, tx[k]), __fadd_rn(rp.y, ty[k]), __fadd_rn(rp.z, tz[k]));
+                fg_sample_issue<SAMPLER>(L, __fadd_rn(rp.x, tx[k]), __fadd_rn(rp.y, ty[k]), __fadd_rn(rp.z, tz[k]), req[k]);
 #pragma unroll
             for (int k = 0; k < BD_CPW; ++k)
             {
                 float u, l;
-                fg_bound_terms(d2[k], rot_r, fix_rot, tsp[k], u, l);
+                fg_bound_terms(fg_sample_finish<SAMPLER>(req[k]), rot_r, fix_rot, tsp[k], u, l);
                 acc_ub[k] += (double)u;
                 acc_lb[k] += (double)l;
             }

@@ -222,7 +222,9 @@ __device__ __forceinline__ float fg_trilerp(float a, float b, float c,
 // one 256-bit read-only load (sm_100+): the whole corner-packed cell in a single request
 __device__ __forceinline__ void fg_ld256(const float* p, float (&v)[8])
 {
-    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+    // not volatile: a read-only load with no side effects -- the scheduler is free to hoist it and to keep
+    // several of them in flight (the bound kernels issue 4 per lane before consuming any)
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]),
                    "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
                  : "l"(p));
@@ -268,6 +270,59 @@ __device__ __forceinline__ float fg_sample(const LutDev& L, float qx, float qy, 
         float t011 = __ldg(g + x0 + y1 * sy + z1 * sz), t111 = __ldg(g + x1 + y1 * sy + z1 * sz);
         return fg_trilerp(a, b, c, t000, t100, t010, t110, t001, t101, t011, t111);
     }
+}
+
+// Split form of fg_sample for kernels that want several gathers in flight per lane: *_issue computes the
+// filter weights and ISSUES the loads into the request's registers, *_finish blends them.  Issuing all
+// requests of a lane before finishing any turns N serial DRAM round trips into one.
+struct SampleReq
+{
+    float a, b, c;      // filter weights
+    float v[8];         // the 8 corner texels (TEX sampler: v[0] holds the filtered value)
+};
+
+template <int SAMPLER>
+__device__ __forceinline__ void fg_sample_issue(const LutDev& L, float qx, float qy, float qz, SampleReq& r)
+{
+    float ux = __fmul_rn(__fadd_rn(qx, L.ox), L.scale);
+    float uy = __fmul_rn(__fadd_rn(qy, L.oy), L.scale);
+    float uz = __fmul_rn(__fadd_rn(qz, L.oz), L.scale);
+    if (SAMPLER == FGOICP_SAMPLER_TEX)
+    {
+        r.v[0] = tex3D<float>(L.tex, ux, uy, uz);
+        return;
+    }
+    int ix, iy, iz;
+    fg_tex_axis(ux, L.dx, ix, r.a);
+    fg_tex_axis(uy, L.dy, iy, r.b);
+    fg_tex_axis(uz, L.dz, iz, r.c);
+    if (SAMPLER == FGOICP_SAMPLER_PACKED)
+    {
+        int cx = min(max(ix, -1), L.dx - 1) + 1;
+        int cy = min(max(iy, -1), L.dy - 1) + 1;
+        int cz = min(max(iz, -1), L.dz - 1) + 1;
+        size_t cell = ((size_t)cz * (size_t)(L.dy + 1) + (size_t)cy) * (size_t)(L.dx + 1) + (size_t)cx;
+        fg_ld256(L.packed + cell * 8, r.v);
+    }
+    else
+    {
+        int x0 = min(max(ix, 0), L.dx - 1), x1 = min(max(ix + 1, 0), L.dx - 1);
+        int y0 = min(max(iy, 0), L.dy - 1), y1 = min(max(iy + 1, 0), L.dy - 1);
+        int z0 = min(max(iz, 0), L.dz - 1), z1 = min(max(iz + 1, 0), L.dz - 1);
+        size_t sy = (size_t)L.dx, sz = (size_t)L.dx * (size_t)L.dy;
+        const float* g = L.grid;
+        r.v[0] = __ldg(g + x0 + y0 * sy + z0 * sz); r.v[1] = __ldg(g + x1 + y0 * sy + z0 * sz);
+        r.v[2] = __ldg(g + x0 + y1 * sy + z0 * sz); r.v[3] = __ldg(g + x1 + y1 * sy + z0 * sz);
+        r.v[4] = __ldg(g + x0 + y0 * sy + z1 * sz); r.v[5] = __ldg(g + x1 + y0 * sy + z1 * sz);
+        r.v[6] = __ldg(g + x0 + y1 * sy + z1 * sz); r.v[7] = __ldg(g + x1 + y1 * sy + z1 * sz);
+    }
+}
+
+template <int SAMPLER>
+__device__ __forceinline__ float fg_sample_finish(const SampleReq& r)
+{
+    if (SAMPLER == FGOICP_SAMPLER_TEX) return r.v[0];
+    return fg_trilerp(r.a, r.b, r.c, r.v[0], r.v[1], r.v[2], r.v[3], r.v[4], r.v[5], r.v[6], r.v[7]);
 }
 
 // Per-point body of kernComputeBounds (reference registration.cu:27-60) after the sample:

@@ -205,17 +205,22 @@ class FastGoICP:
             span = F(pspan / F(2.0))
             if span < F(0.05):                                             # fgoicp.cpp:53
                 break
-            nxt, ev = [], []
-            for n in frontier:
-                for j in range(8):
-                    cx = F(F(n[0] - span) + F(F(j >> 0 & 1) * pspan))
-                    cy = F(F(n[1] - span) + F(F(j >> 1 & 1) * pspan))
-                    cz = F(F(n[2] - span) + F(F(j >> 2 & 1) * pspan))
-                    if not overlaps_so3(cx, cy, cz, span):                 # fgoicp.cpp:61
-                        continue
-                    row = [cx, cy, cz, span, n[4], n[5]]
-                    (ev if in_so3(cx, cy, cz) else nxt).append(row)        # fgoicp.cpp:62-66
-            ev = np.array(ev, F).reshape(-1, 6)
+            # children of every open node, (node, octant) order, in fp32 array arithmetic (same operations and
+            # order as the scalar code of the reference: x - span + bit * parent_span, fgoicp.cpp:55-59)
+            bits = np.array([[(j >> a) & 1 for a in range(3)] for j in range(8)], F)          # (8, 3)
+            ctr = (frontier[:, None, :3] - span) + bits[None, :, :] * pspan                     # (n, 8, 3) fp32
+            cx, cy, cz = ctr[..., 0].ravel(), ctr[..., 1].ravel(), ctr[..., 2].ravel()
+            rr = (cx * cx + cy * cy) + cz * cz
+            rq = np.where(rr > F(1.0), rr, np.sqrt(rr)).astype(F)                               # Rotation::r (Q3)
+            a = (np.abs(cx) + np.abs(cy)) + np.abs(cz)
+            overl = ((rq - (F(2.0) * span) * a) + (F(3.0) * span) * span) <= F(1.0)             # fgoicp.cpp:61
+            inside = rq <= F(1.0)                                                               # fgoicp.cpp:62
+            rows = np.empty((len(cx), 6), F)
+            rows[:, 0], rows[:, 1], rows[:, 2], rows[:, 3] = cx, cy, cz, span
+            rows[:, 4] = np.repeat(frontier[:, 4], 8)
+            rows[:, 5] = np.repeat(frontier[:, 5], 8)
+            nxt = rows[overl & ~inside]
+            ev = rows[overl & inside]
             n_ev = len(ev)
             mine = ev[comm.rank::comm.world, :4]
 
@@ -241,7 +246,7 @@ class FastGoICP:
             kept = ev[surv].copy()
             kept[:, 4] = lb[surv]
             kept[:, 5] = ubt[surv, 0]
-            frontier = np.concatenate([np.array(nxt, F).reshape(-1, 6), kept], axis=0)
+            frontier = np.concatenate([nxt, kept], axis=0)
 
             s = self.stats
             s["levels"] += 1

@@ -79,3 +79,25 @@ def test_driver_preprocess_is_bit_identical_to_oracle():
     t = np.array([0.1, -0.2, 0.05], np.float32)
     assert np.array_equal(driver.restore_translation(R, t, a["scale"], a["offset_pcs"], a["offset_pct"]),
                           O.restore_translation(R, t, b["scale"], b["offset_pcs"], b["offset_pct"]))
+
+
+def test_vectorised_child_enumeration_matches_scalar_rules():
+    """The driver's array form of the octant split / overlaps_SO3 / in_SO3 tests equals the scalar rules."""
+    F = np.float32
+    rng = np.random.default_rng(9)
+    for pspan in (1.0, 0.5, 0.25, 0.125):
+        pspan = F(pspan)
+        span = F(pspan / F(2))
+        k = int(round(1 / pspan))
+        parents = ((2 * rng.integers(-k, k, size=(40, 3)) + 1) * pspan).astype(F) if pspan < 1 else np.zeros((1, 3), F)
+        bits = np.array([[(j >> a) & 1 for a in range(3)] for j in range(8)], F)
+        ctr = (parents[:, None, :] - span) + bits[None, :, :] * pspan
+        cx, cy, cz = ctr[..., 0].ravel(), ctr[..., 1].ravel(), ctr[..., 2].ravel()
+        rr = (cx * cx + cy * cy) + cz * cz
+        rq = np.where(rr > F(1.0), rr, np.sqrt(rr)).astype(F)
+        a = (np.abs(cx) + np.abs(cy)) + np.abs(cz)
+        overl = ((rq - (F(2.0) * span) * a) + (F(3.0) * span) * span) <= F(1.0)
+        inside = rq <= F(1.0)
+        for i in range(len(cx)):
+            assert bool(overl[i]) == O.overlaps_so3(cx[i], cy[i], cz[i], span)
+            assert bool(inside[i]) == O.in_so3(cx[i], cy[i], cz[i])

@@ -138,8 +138,16 @@ struct BoundsLaunch
     const float4* d_tc; int T; float* d_lb; float* d_ub; float* d_best_ub; double* d_partial; int S;
 };
 
+int fg_bounds_phased(fgoicp_ctx* c, const float4* d_rot, int Rn, int fix_rot, const float4* d_tc, int T,
+                     float* d_lb, float* d_ub, float* d_best_ub);
+
 static int run_bounds(fgoicp_ctx* c, const BoundsLaunch& b)
 {
+    if (c->phased && c->sampler == FGOICP_SAMPLER_PACKED && !b.d_Rmats && (long long)b.Rn * b.T >= 4096)
+    {
+        int rc = fg_bounds_phased(c, b.d_rot, b.Rn, b.fix_rot, b.d_tc, b.T, b.d_lb, b.d_ub, b.d_best_ub);
+        if (rc <= 0) return rc;       // done (0) or error (<0); 1 = not applicable, fall through
+    }
     unsigned int* d_bits = (unsigned int*)b.d_best_ub;
     if (d_bits) k_set_u32<<<1, 1, 0, c->stream>>>(d_bits, 0x7f800000u);
     dim3 grid((unsigned)(b.Rn * b.S));

@@ -94,6 +94,11 @@ struct fgoicp_ctx
     float cell_h = 0.f, cell_inv_h = 0.f;
     int nn_mode = 0;                          // 0: cell-grid search, 1: tiled brute force (test hook)
 
+    // z-phase-ordered bound evaluation (bounds_phased.cu): per-launch index lists
+    void* d_phase = nullptr;
+    size_t phase_bytes = 0;
+    int phased = 0;                           // 1: fgoicp_bounds_multi* use the phase-ordered kernel
+
     // ICP state
     float4* d_work = nullptr;                 // working copy W  [ns]
     unsigned long long* d_nnkey = nullptr;    // packed (value bits << 32 | index) [ns]

@@ -605,6 +605,7 @@ extern "C" int fgoicp_ctx_create(const float* model_xyz, size_t nt, const float*
     d_P = nullptr;
 #undef FG_TRY
     c->sampler = c->d_packed ? FGOICP_SAMPLER_PACKED : FGOICP_SAMPLER_GRID;
+    if (const char* e = getenv("FGOICP_PHASED")) c->phased = atoi(e) != 0;
     *out = c;
     return FGOICP_OK;
 }
@@ -618,7 +619,7 @@ extern "C" int fgoicp_ctx_destroy(fgoicp_ctx* c)
     if (c->arr) cudaFreeArray(c->arr);
     cudaFree(c->d_model); cudaFree(c->d_data); cudaFree(c->d_grid); cudaFree(c->d_packed);
     cudaFree(c->d_scratch); cudaFree(c->d_work); cudaFree(c->d_nnkey); cudaFree(c->d_icp);
-    cudaFree(c->d_cell_start); cudaFree(c->d_cell_P); cudaFree(c->d_cell_M);
+    cudaFree(c->d_cell_start); cudaFree(c->d_cell_P); cudaFree(c->d_cell_M); cudaFree(c->d_phase);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);

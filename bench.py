@@ -145,6 +145,7 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
 
@@ -159,6 +160,8 @@ def run_ours(args):
     if sampler == capi.SAMPLER_TEX:
         raise SystemExit("--sampler tex needs a context built with BUILD_TEX (use scripts/sampler_sweep.py)")
     ctx.set_sampler(sampler)
+    phased = (args.sampler == "packed") and not args.no_phased
+    ctx.set_phased(phased)
     # our kernels and torch's events/collectives must share one stream: a dedicated non-default stream
     # (the legacy default stream has handle 0, which the C ABI reads as "use the context's own stream")
     stream = torch.cuda.Stream(device=dev)
@@ -217,7 +220,9 @@ def run_ours(args):
     peak, peak_src = measured_peak()
     achieved = ALGO_BYTES_PER_EVAL * evals_per_step_rank / (kernel_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": profiled_traffic(), "kernel": "k_bounds_multi<%s>" % args.sampler,
+                "traffic": profiled_traffic(),
+                "kernel": ("k_bounds_phased (+ k_phase_bin/groups/scan prologue, timed together)" if phased
+                           else "k_bounds_multi<%s>" % args.sampler),
                 "kernel_ms": kernel_ms, "algorithmic_bytes_per_eval": ALGO_BYTES_PER_EVAL, "peak_source": peak_src}
 
     # end to end through the C ABI with host buffers (H2D of the cube lists, D2H of lb/ub per step)
@@ -274,12 +279,12 @@ def run_ours(args):
                "config": {"workload": "W5 synthetic: 100k-point model / 10k-point data, lut_resolution 0.005; "
                                       "step = %d rotation cubes x %d translation cubes x %d points per GPU, fix_rot=false, "
                                       "then MIN all-reduce of the best upper bound" % (N_ROT, T_CUBES, NS),
-                          "sampler": args.sampler, "grid_dims": list(info.dims),
+                          "sampler": args.sampler, "evaluation_order": "z-phase-ordered" if phased else "plain", "grid_dims": list(info.dims),
                           "grid_bytes": int(info.packed_bytes if args.sampler == "packed" else info.grid_bytes),
                           "l2": "gathered grid (%.2f GB) is larger than L2 (126 MB); no flush needed" %
                                 ((info.packed_bytes if args.sampler == "packed" else info.grid_bytes) / 1e9),
                           "parallelism": "frontier-sharded x%d" % world},
-               "e2e": e2e, "gpu_launches": 2 * args.steps, "clocks": clk, "roofline": roofline,
+               "e2e": e2e, "gpu_launches": (4 if phased else 2) * args.steps, "clocks": clk, "roofline": roofline,
                "cpu_baseline": cpu, "ctor_ms": ctor_ms, "lut_build_ms": info.build_ms}
         if bnb:
             out["bnb"] = bnb
@@ -361,6 +366,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--sampler", default="packed", choices=["packed", "grid", "tex"])
+    ap.add_argument("--no-phased", action="store_true", help="use the plain bound kernel instead of the z-phase-ordered one")
     ap.add_argument("--no-bnb", action="store_true", help="skip the end-to-end run() measurement")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline sample")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)

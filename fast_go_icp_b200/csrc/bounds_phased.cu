@@ -24,16 +24,21 @@
 #include <algorithm>
 #include <cstdlib>
 
-#define PH_NB      128                 // z' buckets
-#define PH_W       0.03125f            // bucket width; leaf translation cubes sit at odd multiples of 2w
-#define PH_INV_W   32.0f
-#define PH_ZMIN    (-2.0f)             // bucket 0 starts here: |R p| <= sqrt(3) < 2 for data in [-1,1]^3
-#define PH_TZOFF   64                  // phase = bucket + round(t.z / w) + PH_TZOFF  (t.z in [-2, 2))
+// Bucket width w = 1/PH_INV_W (a power of two, so leaf translation cubes -- odd multiples of 1/16 -- shift
+// buckets by whole numbers).  z' in [-2, 2): |R p| <= sqrt(3) < 2 for data in [-1,1]^3.
+#ifndef PH_INV_W_I
+#define PH_INV_W_I 32
+#endif
+#define PH_INV_W   ((float)PH_INV_W_I)
+#define PH_NB      (4 * PH_INV_W_I)    // z' buckets
+#define PH_ZMIN    (-2.0f)
+#define PH_TZOFF   (2 * PH_INV_W_I)    // phase = bucket + round(t.z / w) + PH_TZOFF  (t.z in [-2, 2))
 #define PH_PHASES  (PH_NB + 2 * PH_TZOFF)
+#ifndef PH_EVICT_LAST
+#define PH_EVICT_LAST 0
+#endif
 #define PH_THREADS 256
 #define PH_WARPS   8
-#define PH_MAXPAIR 64                  // pairs per warp (shared-memory accumulators)
-#define PH_ILP     4                   // points per lane per inner iteration
 
 __device__ __forceinline__ int ph_bucket(float z)
 {
@@ -112,6 +117,111 @@ k_phase_bin(const float4* __restrict__ data, int ns, const float4* __restrict__ 
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// z-groups: translation cubes of one rotation cube that share t.z visit the same bucket in the same
+// phase, so the bucket's points are loaded and rotated ONCE for up to PH_G cubes (children of one parent
+// cube come as 2 z-values x 4 cubes).  One warp per rotation cube builds its groups.
+// ---------------------------------------------------------------------------------------------
+#define PH_G 4
+
+struct PhGroup
+{
+    int r;                  // rotation cube
+    short tzb;              // phase offset of the group
+    short cnt;              // cubes in the group (1..PH_G)
+    int pair[PH_G];         // flattened pair indices r*T + c
+};
+
+__global__ void __launch_bounds__(32)
+k_phase_groups(const float4* __restrict__ tcubes, int T, PhGroup* __restrict__ gpad /*[Rn][T]*/, int* __restrict__ gcount /*[Rn]*/)
+{
+    const int r = blockIdx.x, lane = threadIdx.x;
+    __shared__ int s_tzb[32], s_cube[32];
+    int n_groups = 0;
+    // T may exceed 32: process the cube list in chunks of 32 (groups never span chunks)
+    for (int c0 = 0; c0 < T; c0 += 32)
+    {
+        int c = c0 + lane;
+        bool valid = false;
+        int tzb = 0x7fff;   // sentinel > any real phase offset
+        if (c < T)
+        {
+            float4 t = tcubes[(size_t)r * T + c];
+            valid = t.w >= 0.0f;                      // negative span marks an unused slot
+            if (valid) tzb = __float2int_rn(t.z * PH_INV_W) + PH_TZOFF;
+        }
+        // stable rank sort by tzb (invalid slots last)
+        int rank = 0;
+        for (int j = 0; j < 32; ++j)
+        {
+            int tj = __shfl_sync(0xffffffffu, tzb, j);
+            rank += (tj < tzb) || (tj == tzb && j < lane);
+        }
+        s_tzb[rank] = tzb; s_cube[rank] = c;
+        __syncwarp();
+        int my_t = s_tzb[lane];
+        bool my_valid = my_t != 0x7fff;
+        // position inside the run of equal tzb
+        int run_start = lane;
+        while (run_start > 0 && s_tzb[run_start - 1] == my_t) --run_start;
+        bool leader = my_valid && ((lane - run_start) % PH_G == 0);
+        unsigned lead_mask = __ballot_sync(0xffffffffu, leader);
+        if (leader)
+        {
+            int g = n_groups + __popc(lead_mask & ((1u << lane) - 1u));
+            PhGroup grp;
+            grp.r = r; grp.tzb = (short)my_t;
+            int cnt = 0;
+            for (int k = 0; k < PH_G; ++k)
+            {
+                int q = lane + k;
+                bool in = q < 32 && s_tzb[q] == my_t && (q - run_start) / PH_G == (lane - run_start) / PH_G;
+                grp.pair[k] = in ? r * T + s_cube[q] : -1;
+                cnt += in;
+            }
+            grp.cnt = (short)cnt;
+            gpad[(size_t)r * T + g] = grp;
+        }
+        n_groups += __popc(lead_mask);
+        __syncwarp();
+    }
+    if (lane == 0) gcount[r] = n_groups;
+}
+
+// single-block exclusive scan: base[0..n] from count[0..n-1]
+__global__ void __launch_bounds__(1024) k_phase_scan(const int* __restrict__ cnt, int n, int* __restrict__ base)
+{
+    __shared__ int warp_sums[32];
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int b0 = 0; b0 < n; b0 += 1024)
+    {
+        int i = b0 + threadIdx.x;
+        int v = i < n ? cnt[i] : 0;
+        int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        if (lane == 31) warp_sums[w] = incl;
+        __syncthreads();
+        if (w == 0)
+        {
+            int sv = warp_sums[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, sv, o); if (lane >= o) sv += t; }
+            warp_sums[lane] = sv;
+        }
+        __syncthreads();
+        int prefix = carry + (w > 0 ? warp_sums[w - 1] : 0) + incl - v;
+        if (i < n) base[i] = prefix;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = prefix + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) base[n] = carry;
+}
+
 // 256-bit gather with an L2 evict_last hint (the slab in flight should stay resident)
 __device__ __forceinline__ void fg_ld256_keep(const float* p, float (&v)[8])
 {
@@ -133,40 +243,67 @@ __device__ __forceinline__ void ph_issue(const LutDev& L, float qx, float qy, fl
     int cy = min(max(iy, -1), L.dy - 1) + 1;
     int cz = min(max(iz, -1), L.dz - 1) + 1;
     size_t cell = ((size_t)cz * (size_t)(L.dy + 1) + (size_t)cy) * (size_t)(L.dx + 1) + (size_t)cx;
+#if PH_EVICT_LAST
     fg_ld256_keep(L.packed + cell * 8, r.v);
+#else
+    fg_ld256(L.packed + cell * 8, r.v);
+#endif
 }
+
+#define PH_MAXGRP 32                  // groups per warp (shared-memory accumulators)
 
 __global__ void __launch_bounds__(PH_THREADS)
 k_bounds_phased(LutDev L, const float4* __restrict__ data, int ns, int fix_rot,
-                const float4* __restrict__ tcubes, int n_pairs, int T,
+                const float4* __restrict__ tcubes, int Rn, int T,
+                const PhGroup* __restrict__ gpad, const int* __restrict__ gbase,
                 const float* __restrict__ Rmats, const unsigned short* __restrict__ order, const int* __restrict__ off,
-                float* __restrict__ lb, float* __restrict__ ub, unsigned int* __restrict__ best_ub_bits)
+                float* __restrict__ lb, float* __restrict__ ub, unsigned int* __restrict__ best_ub_bits,
+                int* __restrict__ phase_done, int pace_lag)
 {
-    __shared__ double s_acc[PH_WARPS][PH_MAXPAIR][2];
-    __shared__ float4 s_tc[PH_WARPS][PH_MAXPAIR];
-    __shared__ short s_tzb[PH_WARPS][PH_MAXPAIR];
+    __shared__ double s_acc[PH_WARPS][PH_MAXGRP][PH_G][2];
+    __shared__ PhGroup s_grp[PH_WARPS][PH_MAXGRP];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int n_groups = gbase[Rn];
     const long long gw = (long long)blockIdx.x * PH_WARPS + w, nw = (long long)gridDim.x * PH_WARPS;
-    const int pair0 = (int)(gw * n_pairs / nw), pair1 = (int)((gw + 1) * n_pairs / nw);
-    const int np = pair1 - pair0;                              // <= PH_MAXPAIR by launch geometry
-    for (int k = lane; k < np; k += 32)
+    const int gfirst = (int)(gw * n_groups / nw), glast = (int)((gw + 1) * n_groups / nw);
+    // normally one sweep; a warp that owns more than PH_MAXGRP groups sweeps again for the rest (correct,
+    // merely out of phase with the others)
+    for (int g0 = gfirst; g0 < glast; g0 += PH_MAXGRP)
     {
-        float4 t = tcubes[pair0 + k];
-        s_tc[w][k] = t;
-        s_tzb[w][k] = (short)(__float2int_rn(t.z * PH_INV_W) + PH_TZOFF);
-        s_acc[w][k][0] = 0.0; s_acc[w][k][1] = 0.0;
+    const int ng = min(PH_MAXGRP, glast - g0);
+    // locate the rotation cube of each compact group (binary search in gbase)
+    for (int k = lane; k < ng; k += 32)
+    {
+        int g = g0 + k;
+        int lo = 0, hi = Rn;                                    // largest r with gbase[r] <= g
+        while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (gbase[mid] <= g) lo = mid; else hi = mid; }
+        s_grp[w][k] = gpad[(size_t)lo * T + (g - gbase[lo])];
+#pragma unroll
+        for (int j = 0; j < PH_G; ++j) { s_acc[w][k][j][0] = 0.0; s_acc[w][k][j][1] = 0.0; }
     }
     __syncwarp();
 
     int cur_r = -1;
     float R[9], sin_half = 0.f;
+    const bool paced = pace_lag > 0 && g0 == gfirst;           // only the first sweep is in step with the others
     for (int phi = 0; phi < PH_PHASES; ++phi)
     {
-        for (int k = 0; k < np; ++k)
+        // Soft pacing: do not run more than pace_lag phases ahead of the slowest warp, so the slabs in flight
+        // stay within L2.  Never blocks for long: the wait gives up after a bounded number of polls.
+        if (paced && phi >= pace_lag)
         {
-            const int b = phi - (int)s_tzb[w][k];
+            if (lane == 0)
+            {
+                const volatile int* flag = phase_done + (phi - pace_lag);
+                for (int spin = 0; spin < 20000 && *flag < (int)nw; ++spin) __nanosleep(100);
+            }
+            __syncwarp();
+        }
+        for (int k = 0; k < ng; ++k)
+        {
+            const int b = phi - (int)s_grp[w][k].tzb;
             if (b < 0 || b >= PH_NB) continue;
-            const int r = (pair0 + k) / T;
+            const int r = s_grp[w][k].r;
             const int* ro = off + (size_t)r * (PH_NB + 1) + b;
             const int k0 = __ldg(ro), k1 = __ldg(ro + 1);
             if (k0 == k1) continue;
@@ -177,44 +314,64 @@ k_bounds_phased(LutDev L, const float4* __restrict__ data, int ns, int fix_rot,
                 for (int j = 0; j < 9; ++j) R[j] = __ldg(Rmats + 12 * r + j);
                 sin_half = __ldg(Rmats + 12 * r + 9);
             }
-            const float4 t = s_tc[w][k];
-            const unsigned short* ord = order + (size_t)r * ns;
-            double au = 0.0, al = 0.0;
-            for (int j0 = k0 + lane; j0 < k1; j0 += 32 * PH_ILP)
+            const int cnt = s_grp[w][k].cnt;
+            float tx[PH_G], ty[PH_G], tz[PH_G], tsp[PH_G];
+#pragma unroll
+            for (int j = 0; j < PH_G; ++j)
             {
-                SampleReq req[PH_ILP];
-                float rot_r[PH_ILP];
-                bool live[PH_ILP];
-#pragma unroll
-                for (int u = 0; u < PH_ILP; ++u)
-                {
-                    int j = j0 + 32 * u;
-                    live[u] = j < k1;
-                    int idx = live[u] ? (int)__ldcs(ord + j) : 0;          // streamed once per use: evict-first
-                    float4 p = __ldg(&data[idx]);
-                    float3 rp = fg_rotate(R, p.x, p.y, p.z);
-                    rot_r[u] = __fmul_rn(__fadd_rn(p.w, p.w), sin_half);
-                    ph_issue(L, __fadd_rn(rp.x, t.x), __fadd_rn(rp.y, t.y), __fadd_rn(rp.z, t.z), req[u]);
-                }
-#pragma unroll
-                for (int u = 0; u < PH_ILP; ++u)
-                {
-                    float uu, ll;
-                    fg_bound_terms(fg_sample_finish<FGOICP_SAMPLER_PACKED>(req[u]), rot_r[u], fix_rot != 0, t.w, uu, ll);
-                    if (live[u]) { au += (double)uu; al += (double)ll; }
-                }
+                int pr = s_grp[w][k].pair[j < cnt ? j : 0];
+                float4 t = __ldg(&tcubes[pr]);
+                tx[j] = t.x; ty[j] = t.y; tz[j] = t.z; tsp[j] = t.w;
             }
-            au = fg_warp_sum(au); al = fg_warp_sum(al);
-            if (lane == 0) { s_acc[w][k][0] += au; s_acc[w][k][1] += al; }
+            const unsigned short* ord = order + (size_t)r * ns;
+            double au[PH_G], al[PH_G];
+#pragma unroll
+            for (int j = 0; j < PH_G; ++j) { au[j] = 0.0; al[j] = 0.0; }
+            int jn = k0 + lane;
+            float4 p_next = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (jn < k1) p_next = __ldg(&data[(int)__ldcs(ord + jn)]);
+            for (int j0 = k0 + lane; j0 < k1; j0 += 32)
+            {
+                float4 p = p_next;
+                if (j0 + 32 < k1) p_next = __ldg(&data[(int)__ldcs(ord + j0 + 32)]);     // prefetch the next point
+                float3 rp = fg_rotate(R, p.x, p.y, p.z);
+                float rot_r = __fmul_rn(__fadd_rn(p.w, p.w), sin_half);
+                SampleReq req[PH_G];
+#pragma unroll
+                for (int j = 0; j < PH_G; ++j)
+                    if (j < cnt)                                   // warp-uniform: unused slots cost nothing
+                        ph_issue(L, __fadd_rn(rp.x, tx[j]), __fadd_rn(rp.y, ty[j]), __fadd_rn(rp.z, tz[j]), req[j]);
+#pragma unroll
+                for (int j = 0; j < PH_G; ++j)
+                    if (j < cnt)
+                    {
+                        float uu, ll;
+                        fg_bound_terms(fg_sample_finish<FGOICP_SAMPLER_PACKED>(req[j]), rot_r, fix_rot != 0, tsp[j], uu, ll);
+                        au[j] += (double)uu; al[j] += (double)ll;
+                    }
+            }
+#pragma unroll
+            for (int j = 0; j < PH_G; ++j)
+                if (j < cnt)
+                {
+                    double su = fg_warp_sum(au[j]), sl = fg_warp_sum(al[j]);
+                    if (lane == 0) { s_acc[w][k][j][0] += su; s_acc[w][k][j][1] += sl; }
+                }
         }
+        if (paced && lane == 0) atomicAdd(phase_done + phi, 1);
     }
     __syncwarp();
-    for (int k = lane; k < np; k += 32)
+    for (int k = lane; k < ng * PH_G; k += 32)
     {
-        float fu = (float)s_acc[w][k][0], fl = (float)s_acc[w][k][1];
-        ub[pair0 + k] = fu; lb[pair0 + k] = fl;
+        int gi = k / PH_G, j = k % PH_G;
+        if (j >= s_grp[w][gi].cnt) continue;
+        int pr = s_grp[w][gi].pair[j];
+        float fu = (float)s_acc[w][gi][j][0], fl = (float)s_acc[w][gi][j][1];
+        ub[pr] = fu; lb[pr] = fl;
         if (best_ub_bits) atomicMin(best_ub_bits, __float_as_uint(fu));
     }
+    __syncwarp();
+    }   // sweeps
 }
 
 // host: returns FGOICP_OK and runs the phased path, or 1 if the problem does not fit it (caller falls back)
@@ -230,27 +387,40 @@ int fg_bounds_phased(fgoicp_ctx* c, const float4* d_rot, int Rn, int fix_rot, co
     if (per_sm < 1) return 1;
     if (const char* e = getenv("FGOICP_PHASED_BPS")) per_sm = std::max(1, std::min(per_sm, atoi(e)));
     int blocks = per_sm * c->sm_count;
-    if ((n_pairs + (long long)blocks * PH_WARPS - 1) / ((long long)blocks * PH_WARPS) > PH_MAXPAIR) return 1;
-    size_t b_R = ((sizeof(float) * 12 * Rn) + 255) & ~(size_t)255;
-    size_t b_off = ((sizeof(int) * (PH_NB + 1) * (size_t)Rn) + 255) & ~(size_t)255;
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    size_t b_R = al(sizeof(float) * 12 * Rn);
+    size_t b_off = al(sizeof(int) * (PH_NB + 1) * (size_t)Rn);
+    size_t b_grp = al(sizeof(PhGroup) * (size_t)n_pairs);
+    size_t b_cnt = al(sizeof(int) * (size_t)(Rn + 1)) * 2;
+    size_t b_pace = al(sizeof(int) * PH_PHASES);
     size_t b_ord = sizeof(unsigned short) * (size_t)Rn * c->ns;
-    if (b_R + b_off + b_ord > c->phase_bytes)
+    size_t need = b_R + b_off + b_grp + b_cnt + b_pace + b_ord;
+    if (need > c->phase_bytes)
     {
         FG_CUDA(cudaStreamSynchronize(c->stream));
         cudaFree(c->d_phase); c->d_phase = nullptr; c->phase_bytes = 0;
-        FG_CUDA(cudaMalloc(&c->d_phase, b_R + b_off + b_ord));
-        c->phase_bytes = b_R + b_off + b_ord;
+        FG_CUDA(cudaMalloc(&c->d_phase, need));
+        c->phase_bytes = need;
     }
     char* base = (char*)c->d_phase;
     float* d_R = (float*)base;
     int* d_off = (int*)(base + b_R);
-    unsigned short* d_ord = (unsigned short*)(base + b_R + b_off);
+    PhGroup* d_grp = (PhGroup*)(base + b_R + b_off);
+    int* d_gcount = (int*)(base + b_R + b_off + b_grp);
+    int* d_gbase = (int*)(base + b_R + b_off + b_grp + b_cnt / 2);
+    int* d_pace = (int*)(base + b_R + b_off + b_grp + b_cnt);
+    unsigned short* d_ord = (unsigned short*)(base + b_R + b_off + b_grp + b_cnt + b_pace);
     k_phase_bin<<<Rn, PH_THREADS, 0, c->stream>>>(c->d_data, (int)c->ns, d_rot, fix_rot, d_R, d_ord, d_off);
+    k_phase_groups<<<Rn, 32, 0, c->stream>>>(d_tc, T, d_grp, d_gcount);
+    k_phase_scan<<<1, 1024, 0, c->stream>>>(d_gcount, Rn, d_gbase);
     FG_CUDA(cudaGetLastError());
     unsigned int* d_bits = (unsigned int*)d_best_ub;
     if (d_bits) FG_CUDA(cudaMemsetAsync(d_bits, 0x7f, 4, c->stream));   // 0x7f7f7f7f: a huge positive float
-    k_bounds_phased<<<blocks, PH_THREADS, 0, c->stream>>>(c->lut, c->d_data, (int)c->ns, fix_rot, d_tc, (int)n_pairs, T,
-                                                        d_R, d_ord, d_off, d_lb, d_ub, d_bits);
+    int pace = 2;
+    if (const char* e = getenv("FGOICP_PHASED_LAG")) pace = atoi(e);
+    FG_CUDA(cudaMemsetAsync(d_pace, 0, sizeof(int) * PH_PHASES, c->stream));
+    k_bounds_phased<<<blocks, PH_THREADS, 0, c->stream>>>(c->lut, c->d_data, (int)c->ns, fix_rot, d_tc, Rn, T,
+                                                        d_grp, d_gbase, d_R, d_ord, d_off, d_lb, d_ub, d_bits, d_pace, pace);
     FG_CUDA(cudaGetLastError());
     return FGOICP_OK;
 }

@@ -605,6 +605,9 @@ extern "C" int fgoicp_ctx_create(const float* model_xyz, size_t nt, const float*
     d_P = nullptr;
 #undef FG_TRY
     c->sampler = c->d_packed ? FGOICP_SAMPLER_PACKED : FGOICP_SAMPLER_GRID;
+    // phase-ordered evaluation is the default for the flat bound entry points (bit-identical results, ~1.6x);
+    // FGOICP_PHASED=0 selects the plain kernel
+    c->phased = c->d_packed != nullptr;
     if (const char* e = getenv("FGOICP_PHASED")) c->phased = atoi(e) != 0;
     *out = c;
     return FGOICP_OK;
@@ -650,6 +653,13 @@ extern "C" int fgoicp_set_sampler(fgoicp_ctx* c, int sampler)
     if (sampler == FGOICP_SAMPLER_PACKED && !c->d_packed) { fg::set_error("packed grid was not built"); return FGOICP_ERR_STATE; }
     if (sampler == FGOICP_SAMPLER_TEX && !c->lut.tex) { fg::set_error("texture was not built"); return FGOICP_ERR_STATE; }
     c->sampler = sampler;
+    return FGOICP_OK;
+}
+
+extern "C" int fgoicp_set_phased(fgoicp_ctx* c, int on)
+{
+    FG_ARG(c, "NULL context");
+    c->phased = on != 0;
     return FGOICP_OK;
 }
 

@@ -91,6 +91,9 @@ int fgoicp_set_nn_mode(fgoicp_ctx* ctx, int mode);
 int fgoicp_lut_download(fgoicp_ctx* ctx, float* out, size_t out_floats);
 /* NearestNeighborLUT::search for n query points with a chosen sampler (registration.cu:320-328). */
 int fgoicp_lut_sample(fgoicp_ctx* ctx, const float* q_xyz, size_t n, int sampler, float* out_d2);
+/* Evaluation order of fgoicp_bounds_multi / _multi_dev: 1 = z-phase-ordered kernel (default with the packed
+ * sampler; same results, L2-friendly), 0 = plain kernel. */
+int fgoicp_set_phased(fgoicp_ctx* ctx, int on);
 /* Measurement hook: useful GB/s of independent random gathers of width_bytes (16/32/64/128) over a
  * buffer of `bytes` bytes -- the gather roofline the bound kernels are compared with. */
 int fgoicp_gather_probe(fgoicp_ctx* ctx, size_t bytes, int width_bytes, int blocks_per_sm, float* out_gbps);

@@ -87,6 +87,23 @@ def test_bounds_multi_matches_batch_and_is_deterministic(small_problem, gpu_ctx)
             assert np.allclose(l1, lb[r], rtol=ULP) and np.allclose(u1, ub[r], rtol=ULP)
 
 
+def test_phase_ordered_kernel_equals_plain_kernel(small_problem, gpu_ctx):
+    """The z-phase-ordered evaluation reorders the same per-point terms; sums are fp64, so floats are equal."""
+    rng = np.random.default_rng(31)
+    for n_rot, T in ((200, 32), (137, 45), (300, 20)):
+        rot = workloads.rotation_cube_list(n_rot, seed=n_rot)
+        rot[::7, 3] = 0.25
+        tc = np.stack([workloads.translation_cube_list(T, level=2 + (r % 3), seed=r) for r in range(n_rot)])
+        tc[rng.random((n_rot, T)) < 0.2, 3] = 0.0          # zero-span cubes are legal
+        for fix_rot in (True, False):
+            gpu_ctx.set_phased(False)
+            lb0, ub0 = gpu_ctx.bounds_multi(rot, fix_rot, tc)
+            gpu_ctx.set_phased(True)
+            lb1, ub1 = gpu_ctx.bounds_multi(rot, fix_rot, tc)
+            assert np.array_equal(lb0, lb1) and np.array_equal(ub0, ub1)
+    gpu_ctx.set_phased(True)
+
+
 def test_bounds_multi_dev_and_best_ub(small_problem, gpu_ctx):
     import torch
     rot = workloads.rotation_cube_list(300, seed=8)

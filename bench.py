@@ -250,7 +250,14 @@ def run_ours(args):
     # end-to-end Go-ICP search (the second half of the metric): run() wall time, frontier sharded over ranks
     bnb = None
     if not args.no_bnb:
-        g = driver.FastGoICP(w["model"], w["data"], RES, MSE_THR, device=local, flags=capi.BUILD_PACKED)
+        # one small untimed run first: loads every kernel of the search (CUDA loads modules lazily)
+        from fast_go_icp_b200 import workloads
+        ws = workloads.synthetic_pair(nt=3000, ns=400, seed=3)
+        gw = driver.FastGoICP(ws["model"], ws["data"], 0.03, MSE_THR, device=local, flags=capi.BUILD_PACKED)
+        gw.run()
+        gw.close()
+        g = driver.FastGoICP(w["model"], w["data"], RES, MSE_THR, device=local, flags=capi.BUILD_PACKED,
+                             wave1=args.wave1, skip_dead_lb=not args.keep_dead_lb)
         barrier()
         R, t = g.run()
         barrier()
@@ -367,6 +374,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--sampler", default="packed", choices=["packed", "grid", "tex"])
     ap.add_argument("--no-phased", action="store_true", help="use the plain bound kernel instead of the z-phase-ordered one")
+    ap.add_argument("--wave1", type=int, default=32, help="cubes per level searched first in run() (0: no split)")
+    ap.add_argument("--keep-dead-lb", action="store_true", help="also run the leaf level's (output-neutral) lower-bound searches")
     ap.add_argument("--no-bnb", action="store_true", help="skip the end-to-end run() measurement")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline sample")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)

@@ -122,7 +122,9 @@ k_phase_bin(const float4* __restrict__ data, int ns, const float4* __restrict__ 
 // phase, so the bucket's points are loaded and rotated ONCE for up to PH_G cubes (children of one parent
 // cube come as 2 z-values x 4 cubes).  One warp per rotation cube builds its groups.
 // ---------------------------------------------------------------------------------------------
+#ifndef PH_G
 #define PH_G 4
+#endif
 
 struct PhGroup
 {
@@ -252,7 +254,10 @@ __device__ __forceinline__ void ph_issue(const LutDev& L, float qx, float qy, fl
 
 #define PH_MAXGRP 32                  // groups per warp (shared-memory accumulators)
 
-__global__ void __launch_bounds__(PH_THREADS)
+#ifndef PH_MIN_BLOCKS
+#define PH_MIN_BLOCKS 2
+#endif
+__global__ void __launch_bounds__(PH_THREADS, PH_MIN_BLOCKS)
 k_bounds_phased(LutDev L, const float4* __restrict__ data, int ns, int fix_rot,
                 const float4* __restrict__ tcubes, int Rn, int T,
                 const PhGroup* __restrict__ gpad, const int* __restrict__ gbase,

@@ -184,16 +184,18 @@ __device__ __forceinline__ float fg_rot_sin(float span)
 
 __device__ __forceinline__ void fg_tex_axis(float u, int dim, int& i, float& alpha)
 {
-    u = fmaxf(u, -2.0f);                       // also maps NaN to -2
-    u = fminf(u, (float)dim + 2.0f);
     // Measured on B200 (scripts/tex_conformance.py, 65,536-step sweep across a texel): the texture unit
-    // keeps the weight in 1.8 fixed point with ROUND-HALF-UP: alpha*256 = floor(uB*256 + 0.5).
-    // u*256 is exact (power-of-two scale) and so is the +0.5 for |u*256| < 2^23.
+    // keeps the weight in 1.8 fixed point with ROUND-HALF-UP: alpha*256 = floor(uB*256 + 0.5), uB = u - 0.5.
+    // Written as ONE conversion: xf = floor(u*256 - 127.5).  u*256 is exact (power-of-two scale) and so is
+    // the -127.5 while |u*256| < 2^23; beyond that (queries thousands of cells outside the grid) and for
+    // NaN the conversion saturates, and the callers clamp the texel index anyway.
+    (void)dim;
 #if FG_WEIGHT_TRUNC
-    int xf = __float2int_rd(__fmul_rn(u, 256.0f)) - 128;
+    int xf = __float2int_rd(__fadd_rn(__fmul_rn(u, 256.0f), -128.0f));
 #else
-    int xf = __float2int_rd(__fadd_rn(__fmul_rn(u, 256.0f), 0.5f)) - 128;
+    int xf = __float2int_rd(__fadd_rn(__fmul_rn(u, 256.0f), -127.5f));
 #endif
+    xf = max(xf, -(1 << 30));                  // keeps xf >> 8 and the index arithmetic far from overflow
     i = xf >> 8;
     alpha = __fmul_rn((float)(xf & 255), 1.0f / 256.0f);
 }

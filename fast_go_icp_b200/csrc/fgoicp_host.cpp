@@ -73,6 +73,8 @@ namespace icp
         }
         if (const char* s = std::getenv("FGOICP_SAMPLER")) options_.sampler = std::atoi(s);
         if (const char* s = std::getenv("FGOICP_DEVICE")) options_.device = std::atoi(s);
+        if (const char* s = std::getenv("FGOICP_WAVE1")) options_.wave1 = std::atoi(s);
+        if (const char* s = std::getenv("FGOICP_SKIP_DEAD_LB")) options_.skip_dead_lb = std::atoi(s) != 0;
         init(_lut_resolution);
     }
 
@@ -182,23 +184,59 @@ namespace icp
                 cubes[4 * i] = eval[i].q.x; cubes[4 * i + 1] = eval[i].q.y; cubes[4 * i + 2] = eval[i].q.z;
                 cubes[4 * i + 3] = eval[i].span;
             }
-            float bR[9], bT[3] = { best_translation.x, best_translation.y, best_translation.z };
-            to_array(best_rotation, bR);
-            float level_best = best_sse;
-            fgoicp_level_stats st_ub{}, st_lb{};
-            check(fgoicp_so3_level_ub(ctx_, cubes.data(), n, best_sse, sse_threshold, ub.data(), bt.data(),
-                                      &level_best, bR, bT, &st_ub), "fgoicp_so3_level_ub");
-            if (level_best < best_sse)
+            // Fixed-rotation phase in (up to) two waves: the children of the parents with the smallest
+            // fixed-rotation error first, so that what their ICPs find tightens best_sse for the rest.
+            std::vector<int> order(n);
+            for (int i = 0; i < n; ++i) order[i] = i;
+            std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return eval[a].ub < eval[b].ub; });
+            std::vector<std::vector<int>> waves;               // sizes wave1, 4*wave1, 16*wave1, then the rest
+            for (int lo = 0, size = options_.wave1; lo < n; size *= 4)
             {
-                best_sse = level_best;
-                best_rotation = to_mat3(bR);
-                best_translation = glm::vec3(bT[0], bT[1], bT[2]);
-                Logger(LogLevel::Debug) << "New best error: " << best_sse
-                                        << "\n\tRotation:\n" << best_rotation
-                                        << "\n\tTranslation: " << restore_translation(best_rotation, best_translation);
+                int hi = (size <= 0 || waves.size() >= 3) ? n : std::min(n, lo + size);
+                waves.emplace_back(order.begin() + lo, order.begin() + hi);
+                lo = hi;
             }
-            check(fgoicp_so3_level_lb(ctx_, cubes.data(), n, best_sse, sse_threshold, lb.data(), &st_lb),
-                  "fgoicp_so3_level_lb");
+            fgoicp_level_stats st_ub{}, st_lb{};
+            for (auto& wave : waves)
+            {
+                if (wave.empty()) continue;
+                std::sort(wave.begin(), wave.end());
+                const int m = static_cast<int>(wave.size());
+                std::vector<float> wc(4 * static_cast<size_t>(m)), wub(m), wbt(3 * static_cast<size_t>(m));
+                for (int k = 0; k < m; ++k) std::memcpy(&wc[4 * k], &cubes[4 * wave[k]], 4 * sizeof(float));
+                float bR[9], bT[3] = { best_translation.x, best_translation.y, best_translation.z };
+                to_array(best_rotation, bR);
+                float level_best = best_sse;
+                fgoicp_level_stats st{};
+                check(fgoicp_so3_level_ub(ctx_, wc.data(), m, best_sse, sse_threshold, wub.data(), wbt.data(),
+                                          &level_best, bR, bT, &st), "fgoicp_so3_level_ub");
+                for (int k = 0; k < m; ++k)
+                {
+                    ub[wave[k]] = wub[k];
+                    std::memcpy(&bt[3 * wave[k]], &wbt[3 * k], 3 * sizeof(float));
+                }
+                if (level_best < best_sse)
+                {
+                    best_sse = level_best;
+                    best_rotation = to_mat3(bR);
+                    best_translation = glm::vec3(bT[0], bT[1], bT[2]);
+                    Logger(LogLevel::Debug) << "New best error: " << best_sse
+                                            << "\n\tRotation:\n" << best_rotation
+                                            << "\n\tTranslation: " << restore_translation(best_rotation, best_translation);
+                }
+                st_ub.evals += st.evals; st_ub.n_icp += st.n_icp; st_ub.icp_iters += st.icp_iters;
+                st_ub.ms_bnb_ub += st.ms_bnb_ub; st_ub.ms_icp += st.ms_icp;
+            }
+            if (options_.skip_dead_lb && span / 2.0f < 0.05f)
+            {
+                // Leaf level: the children of these cubes are never evaluated (reference fgoicp.cpp:53), so their
+                // lower bounds can only feed the loop's exit test; the reference computes them anyway (:90).
+                // Skipping them changes no output.
+                std::fill(lb.begin(), lb.end(), 0.0f);
+            }
+            else
+                check(fgoicp_so3_level_lb(ctx_, cubes.data(), n, best_sse, sse_threshold, lb.data(), &st_lb),
+                      "fgoicp_so3_level_lb");
             for (int i = 0; i < n; ++i)
             {
                 if (lb[i] >= best_sse) continue;

@@ -143,7 +143,7 @@ class FastGoICP:
     """Python mirror of icp::FastGoICP (reference fgoicp/fgoicp.hpp:10-108)."""
 
     def __init__(self, target, source, lut_resolution, mse_threshold, device=0, sampler=None,
-                 flags=capi.BUILD_PACKED, group=None, ctx_factory=None):
+                 flags=capi.BUILD_PACKED, group=None, ctx_factory=None, wave1=32, skip_dead_lb=True):
         t0 = time.perf_counter()
         self.pp = preprocess(target, source)
         self.ns, self.nt = len(self.pp["data"]), len(self.pp["model"])
@@ -156,6 +156,8 @@ class FastGoICP:
         if sampler is not None:
             self.ctx.set_sampler(sampler)
         self.comm = _Comm(group)
+        self.wave1 = int(wave1)      # size of the first wave of a level (0: whole level at once)
+        self.skip_dead_lb = bool(skip_dead_lb)
         self.best_sse = M_INF
         self.best_R = np.array([1, 0, 0, 0, 1, 0, 0, 0, 1], F)
         self.best_t = np.zeros(3, F)
@@ -222,42 +224,68 @@ class FastGoICP:
             nxt = rows[overl & ~inside]
             ev = rows[overl & inside]
             n_ev = len(ev)
+            # Fixed-rotation phase in (up to) two waves.  The children of the parents with the smallest
+            # fixed-rotation error go first: whatever their ICPs find tightens best_sse -- and with it every
+            # inner search -- for the (much larger) rest of the level.  The split depends only on the level's
+            # global data, so results are still independent of the number of ranks.
+            ub = np.zeros(n_ev, F)
+            bt = np.zeros((n_ev, 3), F)
+            by_parent_ub = np.argsort(ev[:, 5], kind="stable")
+            waves, lo, size = [], 0, self.wave1
+            while lo < n_ev:                                   # wave sizes wave1, 4*wave1, 16*wave1, ... then the rest
+                hi = n_ev if (size <= 0 or len(waves) >= 3) else min(n_ev, lo + size)
+                waves.append(np.sort(by_parent_ub[lo:hi]))
+                lo, size = hi, size * 4
+            tot = dict(evals=0, n_icp=0, icp_iters=0, ms_ub=0.0, ms_icp=0.0, local=0)
+            for widx in waves:
+                if not len(widx):
+                    continue
+                my_idx = widx[comm.rank::comm.world]
+                ub_l, bt_l, e_l, R_l, t_l, st = self.ctx.so3_level_ub(ev[my_idx, :4], self.best_sse, thr,
+                                                                     self.best_R, self.best_t)
+                # global best: MIN over (sse bits, global child index); ties -> lowest child index
+                if st.best_icp_index >= 0 and e_l < self.best_sse:
+                    gidx = int(my_idx[st.best_icp_index])
+                    key = (int(np.array([e_l], F).view(np.uint32)[0]) << 32) | gidx
+                else:
+                    key = (int(np.array([self.best_sse], F).view(np.uint32)[0]) << 32) | 0xffffffff
+                gkey = comm.min_key(key)
+                if (gkey & 0xffffffff) != 0xffffffff:
+                    owner = int(np.nonzero(widx == (gkey & 0xffffffff))[0][0]) % comm.world
+                    pose = comm.bcast_f32(np.concatenate([R_l, t_l]), owner)
+                    self.best_sse = np.array([gkey >> 32], np.uint32).view(F)[0]
+                    self.best_R, self.best_t = pose[:9].copy(), pose[9:].copy()
+                ubt_w = comm.gather_rows(np.concatenate([ub_l[:, None], bt_l], axis=1), len(widx))
+                ub[widx], bt[widx] = ubt_w[:, 0], ubt_w[:, 1:]
+                tot["evals"] += int(st.evals); tot["n_icp"] += int(st.n_icp); tot["icp_iters"] += int(st.icp_iters)
+                tot["ms_ub"] += st.ms_bnb_ub; tot["ms_icp"] += st.ms_icp; tot["local"] += len(my_idx)
+
             mine = ev[comm.rank::comm.world, :4]
-
-            ub_l, bt_l, e_l, R_l, t_l, st = self.ctx.so3_level_ub(mine, self.best_sse, thr, self.best_R, self.best_t)
-            # global best: MIN over (sse bits, global child index); ties -> lowest child index
-            if st.best_icp_index >= 0 and e_l < self.best_sse:
-                gidx = comm.rank + comm.world * st.best_icp_index
-                key = (int(np.array([e_l], F).view(np.uint32)[0]) << 32) | gidx
+            if self.skip_dead_lb and F(span / F(2.0)) < F(0.05):
+                # Leaf level: the children of these cubes are never evaluated (fgoicp.cpp:53), so their lower
+                # bounds can only feed the loop's exit test -- the reference computes them anyway (fgoicp.cpp:90);
+                # skipping them changes no output.
+                lb_l, st2 = np.zeros(len(mine), F), capi.LevelStats()
             else:
-                key = (int(np.array([self.best_sse], F).view(np.uint32)[0]) << 32) | 0xffffffff
-            gkey = comm.min_key(key)
-            if (gkey & 0xffffffff) != 0xffffffff:
-                owner = (gkey & 0xffffffff) % comm.world
-                pose = comm.bcast_f32(np.concatenate([R_l, t_l]), owner)
-                self.best_sse = np.array([gkey >> 32], np.uint32).view(F)[0]
-                self.best_R, self.best_t = pose[:9].copy(), pose[9:].copy()
-            ubt = comm.gather_rows(np.concatenate([ub_l[:, None], bt_l], axis=1), n_ev)
-
-            lb_l, st2 = self.ctx.so3_level_lb(mine, self.best_sse, thr)
+                lb_l, st2 = self.ctx.so3_level_lb(mine, self.best_sse, thr)
             lb = comm.gather_rows(lb_l[:, None], n_ev)[:, 0] if n_ev else np.zeros(0, F)
 
             surv = lb < self.best_sse                                      # fgoicp.cpp:92
             kept = ev[surv].copy()
             kept[:, 4] = lb[surv]
-            kept[:, 5] = ubt[surv, 0]
+            kept[:, 5] = ub[surv]
             frontier = np.concatenate([nxt, kept], axis=0)
 
             s = self.stats
             s["levels"] += 1
             s["rot_cubes"] += len(mine)
-            s["bound_evals"] += int(st.evals) + int(st2.evals)
-            s["icp_runs"] += int(st.n_icp)
-            s["icp_iters"] += int(st.icp_iters)
-            s["ms_bnb_ub"] += st.ms_bnb_ub
-            s["ms_icp"] += st.ms_icp
+            s["bound_evals"] += tot["evals"] + int(st2.evals)
+            s["icp_runs"] += tot["n_icp"]
+            s["icp_iters"] += tot["icp_iters"]
+            s["ms_bnb_ub"] += tot["ms_ub"]
+            s["ms_icp"] += tot["ms_icp"]
             s["ms_bnb_lb"] += st2.ms_bnb_lb
-            s["level_log"].append(dict(span=float(span), cubes=n_ev, local_cubes=len(mine), icps=int(st.n_icp),
-                                       evals=int(st.evals) + int(st2.evals), best_sse=float(self.best_sse),
-                                       survivors=len(frontier), ms_ub=st.ms_bnb_ub, ms_icp=st.ms_icp,
+            s["level_log"].append(dict(span=float(span), cubes=n_ev, local_cubes=len(mine), icps=tot["n_icp"],
+                                       evals=tot["evals"] + int(st2.evals), best_sse=float(self.best_sse),
+                                       survivors=len(frontier), ms_ub=tot["ms_ub"], ms_icp=tot["ms_icp"],
                                        ms_lb=st2.ms_bnb_lb))

@@ -31,6 +31,8 @@ namespace icp
             Schedule schedule = Schedule::Level;
             int device = 0;
             int sampler = -1;        // FGOICP_SAMPLER_*, -1 = library default
+            int wave1 = 32;          // first-wave size of a level (then x4, x16, rest): early ICPs tighten best_sse; 0: no split
+            bool skip_dead_lb = true; // skip the leaf level's rotation-uncertainty searches (they cannot change any output)
             bool verbose_levels = false;
         };
 

@@ -5,8 +5,11 @@
 // although every cell is used dozens of times per launch, two uses are too far apart in time to meet
 // in L2.  This variant reorders the SAME evaluations so that they do meet:
 //
-//   1. k_phase_bin: per rotation cube, the rotated data points are bucketed by z' = (R p).z into
-//      slices of width w = 1/32 (a stable counting sort: point order inside a bucket is ascending index).
+//   1. k_phase_bin: per rotation cube, the rotated data points R p (with their rotation-uncertainty radius
+//      in .w) are bucketed by z' = (R p).z into slices of width w = 1/32 and WRITTEN OUT in bucket order
+//      (a stable counting sort: point order inside a bucket is ascending index).  The main kernel then
+//      streams them sequentially: no index indirection, no rotation, nothing between a bucket's offsets
+//      and its gathers but one coalesced load.
 //   2. k_bounds_phased: persistent blocks; every warp owns a fixed set of (rotation cube, translation
 //      cube) pairs and sweeps a global phase counter phi = 0, 1, 2, ...  At phase phi, pair (r, c)
 //      evaluates the points of bucket  b = phi - round(t_c.z / w):  all their queries have
@@ -49,10 +52,9 @@ __device__ __forceinline__ int ph_bucket(float z)
 // One block per rotation cube: rotation matrix, sin(half-angle), stable z'-bucketing of the data points.
 __global__ void __launch_bounds__(PH_THREADS)
 k_phase_bin(const float4* __restrict__ data, int ns, const float4* __restrict__ rot, int fix_rot,
-            float* __restrict__ Rmats /*[Rn][12]: R(9), sin_half, pad*/,
-            unsigned short* __restrict__ order /*[Rn][ns]*/, int* __restrict__ off /*[Rn][PH_NB+1]*/)
+            float4* __restrict__ P /*[Rn][ns]: (R p, rot_r) in bucket order*/, int* __restrict__ off /*[Rn][PH_NB+1]*/)
 {
-    __shared__ float sR[9];
+    __shared__ float sR[10];
     __shared__ int s_cnt[PH_WARPS][PH_NB];      // per-warp bucket counts -> exclusive bases
     __shared__ int s_off[PH_NB + 1];
     const int r = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -61,14 +63,15 @@ k_phase_bin(const float4* __restrict__ data, int ns, const float4* __restrict__ 
         float4 rc = rot[r];
         float Rm[9];
         fg_rotation_matrix(rc.x, rc.y, rc.z, Rm);
-        for (int k = 0; k < 9; ++k) { sR[k] = Rm[k]; Rmats[12 * r + k] = Rm[k]; }
-        Rmats[12 * r + 9] = fix_rot ? 0.0f : fg_rot_sin(rc.w);
+        for (int k = 0; k < 9; ++k) sR[k] = Rm[k];
+        sR[9] = fix_rot ? 0.0f : fg_rot_sin(rc.w);
     }
     for (int i = threadIdx.x; i < PH_WARPS * PH_NB; i += PH_THREADS) (&s_cnt[0][0])[i] = 0;
     __syncthreads();
     float R[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) R[k] = sR[k];
+    const float sin_half = sR[9];
     // each warp owns a contiguous chunk of points and walks it in index order
     const int per = (ns + PH_WARPS - 1) / PH_WARPS;
     const int c0 = w * per, c1 = min(ns, c0 + per);
@@ -104,12 +107,20 @@ k_phase_bin(const float4* __restrict__ data, int ns, const float4* __restrict__ 
     {
         int i = base + lane;
         int b = -1;
-        if (i < c1) { float4 p = data[i]; b = ph_bucket(fg_rotate(R, p.x, p.y, p.z).z); }
+        float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < c1)
+        {
+            float4 p = data[i];
+            float3 rp = fg_rotate(R, p.x, p.y, p.z);
+            b = ph_bucket(rp.z);
+            // rot_uncertain_radius = 2 * |p|^2 * sin(half_angle)  (SASS: FADD r,r ; FMUL); 0 when fix_rot
+            out = make_float4(rp.x, rp.y, rp.z, __fmul_rn(__fadd_rn(p.w, p.w), sin_half));
+        }
         unsigned peers = __match_any_sync(0xffffffffu, b);
         if (b >= 0)
         {
             int rank = __popc(peers & ((1u << lane) - 1u));
-            order[(size_t)r * ns + s_cnt[w][b] + rank] = (unsigned short)i;
+            P[(size_t)r * ns + s_cnt[w][b] + rank] = out;
         }
         __syncwarp();
         if (b >= 0 && lane == __ffs(peers) - 1) s_cnt[w][b] += __popc(peers);
@@ -234,39 +245,70 @@ __device__ __forceinline__ void fg_ld256_keep(const float* p, float (&v)[8])
 
 __device__ __forceinline__ void ph_issue(const LutDev& L, float qx, float qy, float qz, SampleReq& r)
 {
-    float ux = __fmul_rn(__fadd_rn(qx, L.ox), L.scale);
-    float uy = __fmul_rn(__fadd_rn(qy, L.oy), L.scale);
-    float uz = __fmul_rn(__fadd_rn(qz, L.oz), L.scale);
-    int ix, iy, iz;
-    fg_tex_axis(ux, L.dx, ix, r.a);
-    fg_tex_axis(uy, L.dy, iy, r.b);
-    fg_tex_axis(uz, L.dz, iz, r.c);
-    int cx = min(max(ix, -1), L.dx - 1) + 1;
-    int cy = min(max(iy, -1), L.dy - 1) + 1;
-    int cz = min(max(iz, -1), L.dz - 1) + 1;
-    size_t cell = ((size_t)cz * (size_t)(L.dy + 1) + (size_t)cy) * (size_t)(L.dx + 1) + (size_t)cx;
 #if PH_EVICT_LAST
-    fg_ld256_keep(L.packed + cell * 8, r.v);
+    int ix, iy, iz;
+    fg_axis(qx, L.ox, L.scale256, L.vmx, ix, r.a);
+    fg_axis(qy, L.oy, L.scale256, L.vmy, iy, r.b);
+    fg_axis(qz, L.oz, L.scale256, L.vmz, iz, r.c);
+    fg_ld256_keep(fg_packed_cell(L, ix, iy, iz), r.v);
 #else
-    fg_ld256(L.packed + cell * 8, r.v);
+    fg_sample_issue<FGOICP_SAMPLER_PACKED>(L, qx, qy, qz, r);
 #endif
 }
 
-#define PH_MAXGRP 32                  // groups per warp (shared-memory accumulators)
+#define PH_MAXGRP 32                  // groups per warp and sweep (one per lane; shared-memory accumulators)
+
+// One (group, bucket) pass: CNT translation cubes against the bucket's rotated points Pr[k0 .. k1).
+// p_head is this lane's first point, loaded by the caller while the previous group was being evaluated.
+template <int CNT>
+__device__ __forceinline__ void ph_run(const LutDev& L, const float4* __restrict__ Pr, int k0, int k1, int lane,
+                                       float4 p_head, const float4* tc, double (*acc)[2])
+{
+    float tx[CNT], ty[CNT], tz[CNT], tsp[CNT];
+#pragma unroll
+    for (int j = 0; j < CNT; ++j) { float4 t = tc[j]; tx[j] = t.x; ty[j] = t.y; tz[j] = t.z; tsp[j] = t.w; }
+    double au[CNT], al[CNT];
+#pragma unroll
+    for (int j = 0; j < CNT; ++j) { au[j] = 0.0; al[j] = 0.0; }
+    float4 p_next = p_head;
+    for (int j0 = k0 + lane; j0 < k1; j0 += 32)
+    {
+        float4 p = p_next;
+        if (j0 + 32 < k1) p_next = __ldcs(&Pr[j0 + 32]);                // next point: a plain sequential stream
+        SampleReq req[CNT];
+#pragma unroll
+        for (int j = 0; j < CNT; ++j)
+            ph_issue(L, __fadd_rn(p.x, tx[j]), __fadd_rn(p.y, ty[j]), __fadd_rn(p.z, tz[j]), req[j]);
+#pragma unroll
+        for (int j = 0; j < CNT; ++j)
+        {
+            float uu, ll;
+            fg_bound_terms(fg_sample_finish<FGOICP_SAMPLER_PACKED>(req[j]), p.w, false, tsp[j], uu, ll);
+            au[j] += (double)uu; al[j] += (double)ll;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < CNT; ++j)
+    {
+        double su = fg_warp_sum(au[j]), sl = fg_warp_sum(al[j]);
+        if (lane == 0) { acc[j][0] += su; acc[j][1] += sl; }
+    }
+}
 
 #ifndef PH_MIN_BLOCKS
 #define PH_MIN_BLOCKS 2
 #endif
 __global__ void __launch_bounds__(PH_THREADS, PH_MIN_BLOCKS)
-k_bounds_phased(LutDev L, const float4* __restrict__ data, int ns, int fix_rot,
+k_bounds_phased(LutDev L, int ns,
                 const float4* __restrict__ tcubes, int Rn, int T,
                 const PhGroup* __restrict__ gpad, const int* __restrict__ gbase,
-                const float* __restrict__ Rmats, const unsigned short* __restrict__ order, const int* __restrict__ off,
+                const float4* __restrict__ P, const int* __restrict__ off,
                 float* __restrict__ lb, float* __restrict__ ub, unsigned int* __restrict__ best_ub_bits,
-                int* __restrict__ phase_done, int pace_lag)
+                int* __restrict__ phase_done, int pace_lag, int pf_dist)
 {
     __shared__ double s_acc[PH_WARPS][PH_MAXGRP][PH_G][2];
-    __shared__ PhGroup s_grp[PH_WARPS][PH_MAXGRP];
+    __shared__ float4 s_tc[PH_WARPS][PH_MAXGRP][PH_G];
+    __shared__ int s_pair[PH_WARPS][PH_MAXGRP][PH_G];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int n_groups = gbase[Rn];
     const long long gw = (long long)blockIdx.x * PH_WARPS + w, nw = (long long)gridDim.x * PH_WARPS;
@@ -276,20 +318,26 @@ k_bounds_phased(LutDev L, const float4* __restrict__ data, int ns, int fix_rot,
     for (int g0 = gfirst; g0 < glast; g0 += PH_MAXGRP)
     {
     const int ng = min(PH_MAXGRP, glast - g0);
-    // locate the rotation cube of each compact group (binary search in gbase)
-    for (int k = lane; k < ng; k += 32)
+    // lane k holds group g0 + k: rotation cube (binary search in gbase), phase offset, cube count; the cubes
+    // themselves and the accumulators live in shared memory
+    int my_r = 0, my_tzb = 0, my_cnt = 0;
+    if (lane < ng)
     {
-        int g = g0 + k;
+        int g = g0 + lane;
         int lo = 0, hi = Rn;                                    // largest r with gbase[r] <= g
         while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (gbase[mid] <= g) lo = mid; else hi = mid; }
-        s_grp[w][k] = gpad[(size_t)lo * T + (g - gbase[lo])];
+        PhGroup grp = gpad[(size_t)lo * T + (g - gbase[lo])];
+        my_r = grp.r; my_tzb = grp.tzb; my_cnt = grp.cnt;
 #pragma unroll
-        for (int j = 0; j < PH_G; ++j) { s_acc[w][k][j][0] = 0.0; s_acc[w][k][j][1] = 0.0; }
+        for (int j = 0; j < PH_G; ++j)
+        {
+            s_pair[w][lane][j] = grp.pair[j];
+            s_tc[w][lane][j] = __ldg(&tcubes[grp.pair[j < my_cnt ? j : 0]]);
+            s_acc[w][lane][j][0] = 0.0; s_acc[w][lane][j][1] = 0.0;
+        }
     }
     __syncwarp();
 
-    int cur_r = -1;
-    float R[9], sin_half = 0.f;
     const bool paced = pace_lag > 0 && g0 == gfirst;           // only the first sweep is in step with the others
     for (int phi = 0; phi < PH_PHASES; ++phi)
     {
@@ -300,68 +348,78 @@ k_bounds_phased(LutDev L, const float4* __restrict__ data, int ns, int fix_rot,
             if (lane == 0)
             {
                 const volatile int* flag = phase_done + (phi - pace_lag);
+#pragma unroll 1
                 for (int spin = 0; spin < 20000 && *flag < (int)nw; ++spin) __nanosleep(100);
             }
             __syncwarp();
         }
-        for (int k = 0; k < ng; ++k)
+        // Optional slab prefetch (off by default: measured neutral): every warp pulls its share of the
+        // packed-grid layers that phase phi + pf_dist adds into L2 with bulk prefetches.
+        if (pf_dist > 0 && g0 == gfirst)
         {
-            const int b = phi - (int)s_grp[w][k].tzb;
-            if (b < 0 || b >= PH_NB) continue;
-            const int r = s_grp[w][k].r;
-            const int* ro = off + (size_t)r * (PH_NB + 1) + b;
-            const int k0 = __ldg(ro), k1 = __ldg(ro + 1);
-            if (k0 == k1) continue;
-            if (r != cur_r)
+            const int psi = phi + pf_dist;
+            auto cz_hi = [&](int ps) {
+                float zq = PH_ZMIN + ((float)(ps - PH_TZOFF) + 1.5f) * (1.0f / PH_INV_W);
+                int c = (int)floorf((zq + L.oz) * L.scale - 0.5f) + 3;           // +1 cell offset, +2 margin
+                return min(max(c, 0), L.dz + 1);
+            };
+            const int c0 = phi == 0 ? 0 : cz_hi(psi - 1), c1 = cz_hi(psi);
+            if (c1 > c0)
             {
-                cur_r = r;
-#pragma unroll
-                for (int j = 0; j < 9; ++j) R[j] = __ldg(Rmats + 12 * r + j);
-                sin_half = __ldg(Rmats + 12 * r + 9);
-            }
-            const int cnt = s_grp[w][k].cnt;
-            float tx[PH_G], ty[PH_G], tz[PH_G], tsp[PH_G];
-#pragma unroll
-            for (int j = 0; j < PH_G; ++j)
-            {
-                int pr = s_grp[w][k].pair[j < cnt ? j : 0];
-                float4 t = __ldg(&tcubes[pr]);
-                tx[j] = t.x; ty[j] = t.y; tz[j] = t.z; tsp[j] = t.w;
-            }
-            const unsigned short* ord = order + (size_t)r * ns;
-            double au[PH_G], al[PH_G];
-#pragma unroll
-            for (int j = 0; j < PH_G; ++j) { au[j] = 0.0; al[j] = 0.0; }
-            int jn = k0 + lane;
-            float4 p_next = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (jn < k1) p_next = __ldg(&data[(int)__ldcs(ord + jn)]);
-            for (int j0 = k0 + lane; j0 < k1; j0 += 32)
-            {
-                float4 p = p_next;
-                if (j0 + 32 < k1) p_next = __ldg(&data[(int)__ldcs(ord + j0 + 32)]);     // prefetch the next point
-                float3 rp = fg_rotate(R, p.x, p.y, p.z);
-                float rot_r = __fmul_rn(__fadd_rn(p.w, p.w), sin_half);
-                SampleReq req[PH_G];
-#pragma unroll
-                for (int j = 0; j < PH_G; ++j)
-                    if (j < cnt)                                   // warp-uniform: unused slots cost nothing
-                        ph_issue(L, __fadd_rn(rp.x, tx[j]), __fadd_rn(rp.y, ty[j]), __fadd_rn(rp.z, tz[j]), req[j]);
-#pragma unroll
-                for (int j = 0; j < PH_G; ++j)
-                    if (j < cnt)
-                    {
-                        float uu, ll;
-                        fg_bound_terms(fg_sample_finish<FGOICP_SAMPLER_PACKED>(req[j]), rot_r, fix_rot != 0, tsp[j], uu, ll);
-                        au[j] += (double)uu; al[j] += (double)ll;
-                    }
-            }
-#pragma unroll
-            for (int j = 0; j < PH_G; ++j)
-                if (j < cnt)
+                const size_t layer = (size_t)L.dx1 * (size_t)L.dy1 * 32;
+                const size_t total = (size_t)(c1 - c0) * layer;
+                size_t piece = (total / (size_t)(nw * 32) + 127) & ~(size_t)127;
+                size_t o = ((size_t)gw * 32 + lane) * piece;
+                if (o < total)
                 {
-                    double su = fg_warp_sum(au[j]), sl = fg_warp_sum(al[j]);
-                    if (lane == 0) { s_acc[w][k][j][0] += su; s_acc[w][k][j][1] += sl; }
+                    size_t n = min(piece, total - o);                             // layer is a multiple of 32 B
+                    const char* src = (const char*)L.packed + (size_t)c0 * layer + o;
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(src), "r"((unsigned)n) : "memory");
                 }
+            }
+        }
+        // all groups of the warp look up their bucket of this phase at once (one memory round trip, not ng)
+        int k0 = 0, k1 = 0;
+        {
+            const int b = phi - my_tzb;
+            if (lane < ng && b >= 0 && b < PH_NB)
+            {
+                const int* ro = off + (size_t)my_r * (PH_NB + 1) + b;
+                k0 = __ldg(ro); k1 = __ldg(ro + 1);
+            }
+        }
+        unsigned act = __ballot_sync(0xffffffffu, k1 > k0);
+        if (act)
+        {
+            int k = __ffs(act) - 1; act &= act - 1;
+            int ck0 = __shfl_sync(0xffffffffu, k0, k), ck1 = __shfl_sync(0xffffffffu, k1, k);
+            const float4* Pr = P + (size_t)__shfl_sync(0xffffffffu, my_r, k) * ns;
+            float4 p_head = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ck0 + lane < ck1) p_head = __ldcs(&Pr[ck0 + lane]);
+            while (true)
+            {
+                // first points of the NEXT active group: in flight while this one is evaluated
+                int kn = -1, nk0 = 0, nk1 = 0;
+                const float4* Pn = Pr;
+                float4 p_head_n = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (act)
+                {
+                    kn = __ffs(act) - 1; act &= act - 1;
+                    nk0 = __shfl_sync(0xffffffffu, k0, kn); nk1 = __shfl_sync(0xffffffffu, k1, kn);
+                    Pn = P + (size_t)__shfl_sync(0xffffffffu, my_r, kn) * ns;
+                    if (nk0 + lane < nk1) p_head_n = __ldcs(&Pn[nk0 + lane]);
+                }
+                const int cnt = __shfl_sync(0xffffffffu, my_cnt, k);
+                switch (cnt)                                    // warp-uniform
+                {
+                case 1: ph_run<1>(L, Pr, ck0, ck1, lane, p_head, s_tc[w][k], s_acc[w][k]); break;
+                case 2: ph_run<2>(L, Pr, ck0, ck1, lane, p_head, s_tc[w][k], s_acc[w][k]); break;
+                case 3: ph_run<3>(L, Pr, ck0, ck1, lane, p_head, s_tc[w][k], s_acc[w][k]); break;
+                default: ph_run<PH_G>(L, Pr, ck0, ck1, lane, p_head, s_tc[w][k], s_acc[w][k]); break;
+                }
+                if (kn < 0) break;
+                k = kn; ck0 = nk0; ck1 = nk1; Pr = Pn; p_head = p_head_n;
+            }
         }
         if (paced && lane == 0) atomicAdd(phase_done + phi, 1);
     }
@@ -369,8 +427,8 @@ k_bounds_phased(LutDev L, const float4* __restrict__ data, int ns, int fix_rot,
     for (int k = lane; k < ng * PH_G; k += 32)
     {
         int gi = k / PH_G, j = k % PH_G;
-        if (j >= s_grp[w][gi].cnt) continue;
-        int pr = s_grp[w][gi].pair[j];
+        int pr = s_pair[w][gi][j];
+        if (pr < 0) continue;
         float fu = (float)s_acc[w][gi][j][0], fl = (float)s_acc[w][gi][j][1];
         ub[pr] = fu; lb[pr] = fl;
         if (best_ub_bits) atomicMin(best_ub_bits, __float_as_uint(fu));
@@ -383,23 +441,26 @@ k_bounds_phased(LutDev L, const float4* __restrict__ data, int ns, int fix_rot,
 int fg_bounds_phased(fgoicp_ctx* c, const float4* d_rot, int Rn, int fix_rot, const float4* d_tc, int T,
                      float* d_lb, float* d_ub, float* d_best_ub)
 {
-    if (!c->d_packed || c->ns > 65535) return 1;
-    long long n_pairs = (long long)Rn * T;
-    if (n_pairs > (1LL << 30)) return 1;
+    if (!c->d_packed) return 1;
     // persistent blocks, all co-resident (a second wave would start its sweep out of phase)
     int per_sm = 0;
     FG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bounds_phased, PH_THREADS, 0));
     if (per_sm < 1) return 1;
     if (const char* e = getenv("FGOICP_PHASED_BPS")) per_sm = std::max(1, std::min(per_sm, atoi(e)));
     int blocks = per_sm * c->sm_count;
+    // the bucket-ordered rotated points take 16 B per (rotation cube, point): cap the scratch and, if need be,
+    // sweep the rotation cubes in several launches
+    size_t cap = (size_t)2 << 30;
+    if (const char* e = getenv("FGOICP_PHASED_SCRATCH_MB")) cap = (size_t)atoll(e) << 20;
+    int Rc = (int)std::min<size_t>((size_t)Rn, std::max<size_t>(1, cap / (sizeof(float4) * c->ns)));
+    if ((long long)Rc * T > (1LL << 30)) return 1;
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
-    size_t b_R = al(sizeof(float) * 12 * Rn);
-    size_t b_off = al(sizeof(int) * (PH_NB + 1) * (size_t)Rn);
-    size_t b_grp = al(sizeof(PhGroup) * (size_t)n_pairs);
-    size_t b_cnt = al(sizeof(int) * (size_t)(Rn + 1)) * 2;
+    size_t b_off = al(sizeof(int) * (PH_NB + 1) * (size_t)Rc);
+    size_t b_grp = al(sizeof(PhGroup) * (size_t)Rc * T);
+    size_t b_cnt = al(sizeof(int) * (size_t)(Rc + 1)) * 2;
     size_t b_pace = al(sizeof(int) * PH_PHASES);
-    size_t b_ord = sizeof(unsigned short) * (size_t)Rn * c->ns;
-    size_t need = b_R + b_off + b_grp + b_cnt + b_pace + b_ord;
+    size_t b_P = sizeof(float4) * (size_t)Rc * c->ns;
+    size_t need = b_off + b_grp + b_cnt + b_pace + b_P;
     if (need > c->phase_bytes)
     {
         FG_CUDA(cudaStreamSynchronize(c->stream));
@@ -408,24 +469,29 @@ int fg_bounds_phased(fgoicp_ctx* c, const float4* d_rot, int Rn, int fix_rot, co
         c->phase_bytes = need;
     }
     char* base = (char*)c->d_phase;
-    float* d_R = (float*)base;
-    int* d_off = (int*)(base + b_R);
-    PhGroup* d_grp = (PhGroup*)(base + b_R + b_off);
-    int* d_gcount = (int*)(base + b_R + b_off + b_grp);
-    int* d_gbase = (int*)(base + b_R + b_off + b_grp + b_cnt / 2);
-    int* d_pace = (int*)(base + b_R + b_off + b_grp + b_cnt);
-    unsigned short* d_ord = (unsigned short*)(base + b_R + b_off + b_grp + b_cnt + b_pace);
-    k_phase_bin<<<Rn, PH_THREADS, 0, c->stream>>>(c->d_data, (int)c->ns, d_rot, fix_rot, d_R, d_ord, d_off);
-    k_phase_groups<<<Rn, 32, 0, c->stream>>>(d_tc, T, d_grp, d_gcount);
-    k_phase_scan<<<1, 1024, 0, c->stream>>>(d_gcount, Rn, d_gbase);
-    FG_CUDA(cudaGetLastError());
+    int* d_off = (int*)base;
+    PhGroup* d_grp = (PhGroup*)(base + b_off);
+    int* d_gcount = (int*)(base + b_off + b_grp);
+    int* d_gbase = (int*)(base + b_off + b_grp + b_cnt / 2);
+    int* d_pace = (int*)(base + b_off + b_grp + b_cnt);
+    float4* d_P = (float4*)(base + b_off + b_grp + b_cnt + b_pace);
     unsigned int* d_bits = (unsigned int*)d_best_ub;
     if (d_bits) FG_CUDA(cudaMemsetAsync(d_bits, 0x7f, 4, c->stream));   // 0x7f7f7f7f: a huge positive float
-    int pace = 2;
+    int pace = 2, pf = 0;
     if (const char* e = getenv("FGOICP_PHASED_LAG")) pace = atoi(e);
-    FG_CUDA(cudaMemsetAsync(d_pace, 0, sizeof(int) * PH_PHASES, c->stream));
-    k_bounds_phased<<<blocks, PH_THREADS, 0, c->stream>>>(c->lut, c->d_data, (int)c->ns, fix_rot, d_tc, Rn, T,
-                                                        d_grp, d_gbase, d_R, d_ord, d_off, d_lb, d_ub, d_bits, d_pace, pace);
-    FG_CUDA(cudaGetLastError());
+    if (const char* e = getenv("FGOICP_PHASED_PF")) pf = atoi(e);
+    for (int r0 = 0; r0 < Rn; r0 += Rc)
+    {
+        const int rn = std::min(Rc, Rn - r0);
+        const float4* tc = d_tc + (size_t)r0 * T;
+        k_phase_bin<<<rn, PH_THREADS, 0, c->stream>>>(c->d_data, (int)c->ns, d_rot + r0, fix_rot, d_P, d_off);
+        k_phase_groups<<<rn, 32, 0, c->stream>>>(tc, T, d_grp, d_gcount);
+        k_phase_scan<<<1, 1024, 0, c->stream>>>(d_gcount, rn, d_gbase);
+        FG_CUDA(cudaMemsetAsync(d_pace, 0, sizeof(int) * PH_PHASES, c->stream));
+        k_bounds_phased<<<blocks, PH_THREADS, 0, c->stream>>>(c->lut, (int)c->ns, tc, rn, T, d_grp, d_gbase, d_P, d_off,
+                                                            d_lb + (size_t)r0 * T, d_ub + (size_t)r0 * T, d_bits, d_pace,
+                                                            pace, (long long)rn * T < 4096 ? 0 : pf);
+        FG_CUDA(cudaGetLastError());
+    }
     return FGOICP_OK;
 }

@@ -47,7 +47,20 @@ struct LutDev
     int dx, dy, dz;
     float scale;              // 1 / resolution
     float ox, oy, oz;         // -bbox_min
+    // derived, for the manual samplers (filled by fg_lut_finalise):
+    float scale256;           // scale * 256 (exact: power-of-two factor)
+    float vmx, vmy, vmz;      // 256 * dim - 1: upper clamp of the 24.8 fixed-point texel coordinate
+    int dx1, dy1;             // dx + 1, dy + 1: row / slice pitch of the corner-packed grid in cells
+    const float* packed0;     // packed + 8 * ((dy1 + 1) * dx1 + 1): cell (ix, iy, iz) = texel index, no +1 needed
 };
+
+inline void fg_lut_finalise(LutDev& L)
+{
+    L.scale256 = L.scale * 256.0f;
+    L.vmx = 256.0f * (float)L.dx - 1.0f; L.vmy = 256.0f * (float)L.dy - 1.0f; L.vmz = 256.0f * (float)L.dz - 1.0f;
+    L.dx1 = L.dx + 1; L.dy1 = L.dy + 1;
+    L.packed0 = L.packed ? L.packed + 8 * ((size_t)(L.dy1 + 1) * (size_t)L.dx1 + 1) : nullptr;
+}
 
 // Uniform cell grid over the model cloud in LUT space; cells along x are consecutive in the CSR order,
 // so a run of cells of one (y, z) row is one contiguous range of points.
@@ -182,22 +195,36 @@ __device__ __forceinline__ float fg_rot_sin(float span)
 #define FG_INTERP_WSUM 0
 #endif
 
-__device__ __forceinline__ void fg_tex_axis(float u, int dim, int& i, float& alpha)
-{
-    // Measured on B200 (scripts/tex_conformance.py, 65,536-step sweep across a texel): the texture unit
-    // keeps the weight in 1.8 fixed point with ROUND-HALF-UP: alpha*256 = floor(uB*256 + 0.5), uB = u - 0.5.
-    // Written as ONE conversion: xf = floor(u*256 - 127.5).  u*256 is exact (power-of-two scale) and so is
-    // the -127.5 while |u*256| < 2^23; beyond that (queries thousands of cells outside the grid) and for
-    // NaN the conversion saturates, and the callers clamp the texel index anyway.
-    (void)dim;
 #if FG_WEIGHT_TRUNC
-    int xf = __float2int_rd(__fadd_rn(__fmul_rn(u, 256.0f), -128.0f));
+#define FG_WEIGHT_BIAS (-128.0f)
 #else
-    int xf = __float2int_rd(__fadd_rn(__fmul_rn(u, 256.0f), -127.5f));
+#define FG_WEIGHT_BIAS (-127.5f)
 #endif
-    xf = max(xf, -(1 << 30));                  // keeps xf >> 8 and the index arithmetic far from overflow
+
+// One axis of the filter footprint: texel index i in [-1, dim-1] and weight alpha.
+// Measured on B200 (scripts/tex_conformance.py, 65,536-step sweep across a texel): the texture unit
+// keeps the weight in 1.8 fixed point with ROUND-HALF-UP: alpha*256 = floor(uB*256 + 0.5), uB = u - 0.5,
+// u = (q + offset) * scale (reference registration.cu:323-325: FADD then FMUL).
+//   * u * 256 is an exact power-of-two scaling, so it is folded into the multiplier (scale256): one FMUL
+//     gives fl(u) * 256 bit for bit; the bias -127.5 is then ONE rounded add, as before;
+//   * the clamp to the grid happens on that float (2 FMNMX) instead of on three integers: v in
+//     [-256, 256*dim-1] <=> i in [-1, dim-1].  Wherever the clamp acts both corners of the axis are the
+//     same texel (clamp-to-edge), so the weight there is irrelevant: fma(a, t-t, t) = t.  NaN -> -256.
+__device__ __forceinline__ void fg_axis(float q, float o, float scale256, float vmax, int& i, float& alpha)
+{
+    float v = __fadd_rn(__fmul_rn(__fadd_rn(q, o), scale256), FG_WEIGHT_BIAS);
+    v = fminf(fmaxf(v, -256.0f), vmax);
+    int xf = __float2int_rd(v);
     i = xf >> 8;
     alpha = __fmul_rn((float)(xf & 255), 1.0f / 256.0f);
+}
+
+// address of the corner-packed cell of texel index (ix, iy, iz), each in [-1, dim-1]: 32-bit cell arithmetic
+// (the +1 per axis lives in packed0), one widening multiply-add for the byte address
+__device__ __forceinline__ const float* fg_packed_cell(const LutDev& L, int ix, int iy, int iz)
+{
+    int cell = (iz * L.dy1 + iy) * L.dx1 + ix;
+    return L.packed0 + (long long)cell * 8;
 }
 
 __device__ __forceinline__ float fg_trilerp(float a, float b, float c,
@@ -240,35 +267,31 @@ __device__ __forceinline__ void fg_ld256(const float* p, float (&v)[8])
 template <int SAMPLER>
 __device__ __forceinline__ float fg_sample(const LutDev& L, float qx, float qy, float qz)
 {
-    // NearestNeighborLUT::search: (query + offset) * scale   (FADD then FMUL in the SASS)
-    float ux = __fmul_rn(__fadd_rn(qx, L.ox), L.scale);
-    float uy = __fmul_rn(__fadd_rn(qy, L.oy), L.scale);
-    float uz = __fmul_rn(__fadd_rn(qz, L.oz), L.scale);
     if (SAMPLER == FGOICP_SAMPLER_TEX)
     {
+        // NearestNeighborLUT::search: (query + offset) * scale   (FADD then FMUL in the SASS)
+        float ux = __fmul_rn(__fadd_rn(qx, L.ox), L.scale);
+        float uy = __fmul_rn(__fadd_rn(qy, L.oy), L.scale);
+        float uz = __fmul_rn(__fadd_rn(qz, L.oz), L.scale);
         return tex3D<float>(L.tex, ux, uy, uz);
     }
     int ix, iy, iz;
     float a, b, c;
-    fg_tex_axis(ux, L.dx, ix, a);
-    fg_tex_axis(uy, L.dy, iy, b);
-    fg_tex_axis(uz, L.dz, iz, c);
+    fg_axis(qx, L.ox, L.scale256, L.vmx, ix, a);
+    fg_axis(qy, L.oy, L.scale256, L.vmy, iy, b);
+    fg_axis(qz, L.oz, L.scale256, L.vmz, iz, c);
     if (SAMPLER == FGOICP_SAMPLER_PACKED)
     {
-        // cell c = clamp(i, -1, dim-1) + 1 holds the 8 clamped corner texels of texel index i
-        int cx = min(max(ix, -1), L.dx - 1) + 1;
-        int cy = min(max(iy, -1), L.dy - 1) + 1;
-        int cz = min(max(iz, -1), L.dz - 1) + 1;
-        size_t cell = ((size_t)cz * (size_t)(L.dy + 1) + (size_t)cy) * (size_t)(L.dx + 1) + (size_t)cx;
+        // the cell of texel index i holds the 8 clamped corner texels i, i+1 per axis
         float v[8];
-        fg_ld256(L.packed + cell * 8, v);
+        fg_ld256(fg_packed_cell(L, ix, iy, iz), v);
         return fg_trilerp(a, b, c, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
     }
     else
     {
-        int x0 = min(max(ix, 0), L.dx - 1), x1 = min(max(ix + 1, 0), L.dx - 1);
-        int y0 = min(max(iy, 0), L.dy - 1), y1 = min(max(iy + 1, 0), L.dy - 1);
-        int z0 = min(max(iz, 0), L.dz - 1), z1 = min(max(iz + 1, 0), L.dz - 1);
+        int x0 = max(ix, 0), x1 = min(ix + 1, L.dx - 1);
+        int y0 = max(iy, 0), y1 = min(iy + 1, L.dy - 1);
+        int z0 = max(iz, 0), z1 = min(iz + 1, L.dz - 1);
         size_t sy = (size_t)L.dx, sz = (size_t)L.dx * (size_t)L.dy;
         const float* g = L.grid;
         float t000 = __ldg(g + x0 + y0 * sy + z0 * sz), t100 = __ldg(g + x1 + y0 * sy + z0 * sz);
@@ -291,31 +314,27 @@ struct SampleReq
 template <int SAMPLER>
 __device__ __forceinline__ void fg_sample_issue(const LutDev& L, float qx, float qy, float qz, SampleReq& r)
 {
-    float ux = __fmul_rn(__fadd_rn(qx, L.ox), L.scale);
-    float uy = __fmul_rn(__fadd_rn(qy, L.oy), L.scale);
-    float uz = __fmul_rn(__fadd_rn(qz, L.oz), L.scale);
     if (SAMPLER == FGOICP_SAMPLER_TEX)
     {
+        float ux = __fmul_rn(__fadd_rn(qx, L.ox), L.scale);
+        float uy = __fmul_rn(__fadd_rn(qy, L.oy), L.scale);
+        float uz = __fmul_rn(__fadd_rn(qz, L.oz), L.scale);
         r.v[0] = tex3D<float>(L.tex, ux, uy, uz);
         return;
     }
     int ix, iy, iz;
-    fg_tex_axis(ux, L.dx, ix, r.a);
-    fg_tex_axis(uy, L.dy, iy, r.b);
-    fg_tex_axis(uz, L.dz, iz, r.c);
+    fg_axis(qx, L.ox, L.scale256, L.vmx, ix, r.a);
+    fg_axis(qy, L.oy, L.scale256, L.vmy, iy, r.b);
+    fg_axis(qz, L.oz, L.scale256, L.vmz, iz, r.c);
     if (SAMPLER == FGOICP_SAMPLER_PACKED)
     {
-        int cx = min(max(ix, -1), L.dx - 1) + 1;
-        int cy = min(max(iy, -1), L.dy - 1) + 1;
-        int cz = min(max(iz, -1), L.dz - 1) + 1;
-        size_t cell = ((size_t)cz * (size_t)(L.dy + 1) + (size_t)cy) * (size_t)(L.dx + 1) + (size_t)cx;
-        fg_ld256(L.packed + cell * 8, r.v);
+        fg_ld256(fg_packed_cell(L, ix, iy, iz), r.v);
     }
     else
     {
-        int x0 = min(max(ix, 0), L.dx - 1), x1 = min(max(ix + 1, 0), L.dx - 1);
-        int y0 = min(max(iy, 0), L.dy - 1), y1 = min(max(iy + 1, 0), L.dy - 1);
-        int z0 = min(max(iz, 0), L.dz - 1), z1 = min(max(iz + 1, 0), L.dz - 1);
+        int x0 = max(ix, 0), x1 = min(ix + 1, L.dx - 1);
+        int y0 = max(iy, 0), y1 = min(iy + 1, L.dy - 1);
+        int z0 = max(iz, 0), z1 = min(iz + 1, L.dz - 1);
         size_t sy = (size_t)L.dx, sz = (size_t)L.dx * (size_t)L.dy;
         const float* g = L.grid;
         r.v[0] = __ldg(g + x0 + y0 * sy + z0 * sz); r.v[1] = __ldg(g + x1 + y0 * sy + z0 * sz);
@@ -338,11 +357,12 @@ __device__ __forceinline__ float fg_sample_finish(const SampleReq& r)
 __device__ __forceinline__ void fg_bound_terms(float d2, float rot_r, bool fix_rot, float span_t,
                                                float& ub, float& lb)
 {
-    float d = __fsqrt_rn(d2);
-    if (!fix_rot) d = __fsub_rn(d, rot_r);
-    ub = d > 0.0f ? __fmul_rn(d, d) : 0.0f;
-    float e = __fmaf_rn(span_t, -FG_SQRT3, d);
-    lb = e > 0.0f ? __fmul_rn(e, e) : 0.0f;
+    // branch-free: d - 0 == d bit for bit (d = sqrt >= +0), and x > 0 ? x*x : 0 == sq(max(x, 0)) (NaN -> 0 both ways)
+    float d = __fsub_rn(__fsqrt_rn(d2), fix_rot ? 0.0f : rot_r);
+    float du = fmaxf(d, 0.0f);
+    ub = __fmul_rn(du, du);
+    float e = fmaxf(__fmaf_rn(span_t, -FG_SQRT3, d), 0.0f);
+    lb = __fmul_rn(e, e);
 }
 
 __device__ __forceinline__ double fg_warp_sum(double v)

@@ -598,6 +598,7 @@ extern "C" int fgoicp_ctx_create(const float* model_xyz, size_t nt, const float*
         rc = build_texture(c);
         if (rc) return fail(rc);
     }
+    fg_lut_finalise(L);
     FG_TRY(cudaEventRecord(c->ev1, c->stream));
     FG_TRY(cudaStreamSynchronize(c->stream));
     FG_TRY(cudaEventElapsedTime(&c->build_ms, c->ev0, c->ev1));

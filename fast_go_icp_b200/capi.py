@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libfgoicp_b200.so")
+# FGOICP_LIB selects an experimental build of the same library (scripts/build_variant.py)
+LIB_PATH = os.environ.get("FGOICP_LIB") or os.path.join(HERE, "libfgoicp_b200.so")
 
 SAMPLER_GRID, SAMPLER_PACKED, SAMPLER_TEX = 0, 1, 2
 BUILD_PACKED, BUILD_TEX, BUILD_BRUTE_LUT = 1, 2, 4

@@ -6,7 +6,7 @@
 // in L2.  This variant reorders the SAME evaluations so that they do meet:
 //
 //   1. k_phase_bin: per rotation cube, the rotated data points R p (with their rotation-uncertainty radius
-//      in .w) are bucketed by z' = (R p).z into slices of width w = 1/32 and WRITTEN OUT in bucket order
+//      in .w) are bucketed by z' = (R p).z into slices of width w = 1/16 and WRITTEN OUT in bucket order
 //      (a stable counting sort: point order inside a bucket is ascending index).  The main kernel then
 //      streams them sequentially: no index indirection, no rotation, nothing between a bucket's offsets
 //      and its gathers but one coalesced load.
@@ -30,7 +30,7 @@
 // Bucket width w = 1/PH_INV_W (a power of two, so leaf translation cubes -- odd multiples of 1/16 -- shift
 // buckets by whole numbers).  z' in [-2, 2): |R p| <= sqrt(3) < 2 for data in [-1,1]^3.
 #ifndef PH_INV_W_I
-#define PH_INV_W_I 32
+#define PH_INV_W_I 16
 #endif
 #define PH_INV_W   ((float)PH_INV_W_I)
 #define PH_NB      (4 * PH_INV_W_I)    // z' buckets

@@ -157,6 +157,45 @@ def test_nn_duplicate_points_lowest_index_wins():
     ctx.close()
 
 
+def test_nn_rooted_rule_near_ties():
+    """Distinct squared distances that round to the SAME square root: the rooted rule (icp3d.cu:17-26) keeps the
+    first such index, the squared rule (registration.cu:160-172) the strictly smaller d2.  The CUDA search finds
+    the squared winner first and must fall back to the exact rooted scan exactly in this window."""
+    rng = np.random.default_rng(21)
+    filler = rng.uniform(-0.9, 0.9, (500, 3)).astype(np.float32)
+    filler = filler[np.linalg.norm(filler, axis=1) > 0.6]        # keep the neighbourhood of the probes empty
+    data = np.zeros((64, 3), np.float32)
+    model = [np.float32([-0.95, -0.95, -0.95]), np.float32([0.95, 0.95, 0.95])]
+    # probe k: query q_k = (0.01 k, 0, 0); model gets p_a = q + (r, 0, dz) then p_b = q + (r, 0, 0) with
+    # d2(p_a) one or two ulps above d2(p_b) = r*r
+    for k in range(64):
+        q = np.float32([0.004 * k - 0.128, 0.0, 0.0])
+        data[k] = q
+    # the probes sit on a ring of radius 0.25 around their query, far from each other's queries
+    want_cases = 0
+    for k in range(64):
+        q = data[k]
+        r = np.float32(0.25)
+        dz = np.float32(r * np.sqrt(np.float32(2.0 ** -23)) * (1.0 + 0.1 * (k % 5)))
+        model.append((q + np.float32([0, r, dz])).astype(np.float32))     # earlier index, slightly farther
+        model.append((q + np.float32([0, r, 0])).astype(np.float32))      # later index, nearest in d2
+    model = np.concatenate([np.array(model, np.float32), filler]).astype(np.float32)
+    ctx = capi.Context(model, data, model.min(0), model.max(0), 0.05, flags=0)
+    I = np.eye(3, dtype=np.float32).ravel()
+    z = np.zeros(3, np.float32)
+    for nn_mode in (0, 1):
+        ctx.set_nn_mode(nn_mode)
+        idx_r, d_r = ctx.nn(I, z, True)
+        idx_s, d_s = ctx.nn(I, z, False)
+        w_r, wd_r = O.nn(model, data, I, z, True)
+        w_s, wd_s = O.nn(model, data, I, z, False)
+        assert np.array_equal(idx_r, w_r) and np.array_equal(idx_s, w_s)
+        assert np.array_equal(d_r, wd_r) and np.array_equal(d_s, wd_s)
+        want_cases = int(np.sum(w_r != w_s))
+    assert want_cases >= 8, "the construction must actually produce rooted/squared disagreements (%d)" % want_cases
+    ctx.close()
+
+
 def test_icp_vs_oracle(small_problem, gpu_ctx):
     pp = small_problem
     I = np.eye(3, dtype=np.float32).ravel()

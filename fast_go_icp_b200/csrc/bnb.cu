@@ -28,6 +28,7 @@
 #include <cooperative_groups.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -258,6 +259,215 @@ k_bnb_r3(LutDev L, const float4* __restrict__ data, int ns, const float4* __rest
 }
 
 // ---------------------------------------------------------------------------------------------
+// Round-synchronous form of the same search, for levels with many rotation cubes.
+//
+// k_bnb_r3 above lets every rotation cube run ahead on its own, which makes the cube-bound gathers of
+// the ~450 resident blocks land all over the 1 GB grid (HBM random-access bound, ~6e10 evals/s).  Here all
+// searches of the level advance one iteration per ROUND:
+//   k_bnbr_round  (one block per rotation cube): fold the bounds of the previous batch into the search
+//                 (best update, child spawning, pruning), sort, stop test, pop the next <= 32 cubes;
+//   bounds        of ALL popped cubes of the level in one launch of the z-phase-ordered kernel
+//                 (bounds_phased.cu, 2.4x the throughput of unordered gathers), or of the plain kernel
+//                 when only a few searches are still running.
+// The per-cube search logic, its order of operations and the bound values are exactly those of k_bnb_r3,
+// so every rotation cube takes the same decisions and spends the same number of evaluations (tested).
+// The open lists live in HBM between rounds (<= 4736 keys = 37 KB per rotation cube).
+// ---------------------------------------------------------------------------------------------
+#define BNBR_POOL 4736                  // >= 4681 nodes ever pushed; multiple of 32
+#define BNBR_THREADS 256
+
+struct BnbrMeta
+{
+    int n;                              // live keys stored for the next round
+    unsigned int seq;
+    float best_error, best_ub, best_t[3];
+    int nb;                             // cubes popped this round (bounds pending)
+    int done;
+    unsigned int batches;
+    unsigned long long evals;
+};
+
+__global__ void k_bnbr_init(BnbrMeta* __restrict__ meta, unsigned long long* __restrict__ pools, int Rn, float best_sse,
+                            int* __restrict__ counts, float4* __restrict__ tcubes)
+{
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= Rn) return;
+    BnbrMeta m;
+    m.n = 1; m.seq = 1;
+    m.best_error = best_sse;                                  // fgoicp.cpp:104
+    m.best_ub = FG_INF;                                       // fgoicp.cpp:106
+    m.best_t[0] = m.best_t[1] = m.best_t[2] = 0.0f;           // fgoicp.cpp:105
+    m.nb = 0; m.done = 0; m.batches = 0; m.evals = 0;
+    meta[r] = m;
+    pools[(size_t)r * BNBR_POOL] = bnb_key(0.0f, 0, 0, 0, 0, 0);   // root: t = 0, span = 1, lb = 0 (fgoicp.cpp:113)
+    counts[r] = 0;
+    for (int i = 0; i < BNB_BATCH_MAX; ++i) tcubes[(size_t)r * BNB_BATCH_MAX + i] = make_float4(0.f, 0.f, 0.f, -1.0f);
+}
+
+__device__ __forceinline__ float4 bnb_key_cube(unsigned long long key)
+{
+    unsigned lo = (unsigned)key;
+    unsigned level = (lo >> 25) & 7u, ix = lo & 15u, iy = (lo >> 4) & 15u, iz = (lo >> 8) & 15u;
+    float span = __uint_as_float((127u - level) << 23);                  // 2^-level
+    float4 t;
+    t.x = __fmaf_rn((float)(2 * ix + 1), span, -1.0f);                   // exact: dyadic
+    t.y = __fmaf_rn((float)(2 * iy + 1), span, -1.0f);
+    t.z = __fmaf_rn((float)(2 * iz + 1), span, -1.0f);
+    t.w = span;
+    return t;
+}
+
+__global__ void __launch_bounds__(BNBR_THREADS)
+k_bnbr_round(BnbrMeta* __restrict__ meta, unsigned long long* __restrict__ pools, unsigned long long* __restrict__ bkeys,
+             float4* __restrict__ tcubes, int* __restrict__ counts, const float* __restrict__ lb, const float* __restrict__ ub,
+             float sse_threshold, int ns, unsigned int* __restrict__ ctl /*[2]: active searches, popped cubes*/)
+{
+    extern __shared__ unsigned long long pool[];          // BNB_POOL keys
+    __shared__ BnbrMeta M;
+    __shared__ int s_m, s_stop, s_nb;
+    const int NT = BNBR_THREADS;
+    const int tid = threadIdx.x, r = blockIdx.x;
+    if (tid == 0) M = meta[r];
+    __syncthreads();
+    if (M.done) return;
+    unsigned long long* gpool = pools + (size_t)r * BNBR_POOL;
+    unsigned long long* gkeys = bkeys + (size_t)r * BNB_BATCH_MAX;
+    float4* gtc = tcubes + (size_t)r * BNB_BATCH_MAX;
+    const int n0 = M.n, nb_prev = M.nb;
+    for (int i = tid; i < n0; i += NT) pool[i] = gpool[i];
+    __syncthreads();
+
+    if (nb_prev > 0)
+    {
+        const float* rub = ub + (size_t)r * BNB_BATCH_MAX;
+        const float* rlb = lb + (size_t)r * BNB_BATCH_MAX;
+        // ---- (f) best of the batch (fgoicp.cpp:139-145): first minimum in pop order
+        if (tid == 0)
+        {
+            int idx_min = 0;
+            for (int i = 1; i < nb_prev; ++i) if (rub[i] < rub[idx_min]) idx_min = i;
+            float u = rub[idx_min];
+            M.best_ub = M.best_ub < u ? M.best_ub : u;
+            if (u < M.best_error)
+            {
+                float4 t = bnb_key_cube(gkeys[idx_min]);
+                M.best_error = u;
+                M.best_t[0] = t.x; M.best_t[1] = t.y; M.best_t[2] = t.z;
+            }
+            M.evals += (unsigned long long)nb_prev * (unsigned long long)ns;      // fgoicp.cpp:132 (x ns)
+            M.batches += 1;
+        }
+        __syncthreads();
+        // ---- (g) spawn children of surviving cubes (fgoicp.cpp:148-169), in pop order
+        const float best_error = M.best_error;
+        if (tid < 32)
+        {
+            bool spawn = false;
+            unsigned long long key = 0;
+            float lbv = 0.f;
+            if (tid < nb_prev)
+            {
+                key = gkeys[tid];
+                lbv = rlb[tid];
+                float span = bnb_key_cube(key).w;
+                spawn = !(lbv >= best_error) && !(span < BNB_MIN_TSPAN);
+            }
+            unsigned mask = __ballot_sync(0xffffffffu, spawn);
+            int before = __popc(mask & ((1u << tid) - 1u));
+            int total = __popc(mask);
+            if (spawn)
+            {
+                unsigned lo = (unsigned)key;
+                unsigned level = (lo >> 25) & 7u, ix = lo & 15u, iy = (lo >> 4) & 15u, iz = (lo >> 8) & 15u;
+                unsigned seq0 = M.seq + 8u * before;
+                int base = n0 + 8 * before;
+#pragma unroll
+                for (unsigned k = 0; k < 8; ++k)
+                    pool[base + k] = bnb_key(lbv, level + 1, seq0 + k, 2 * ix + (k & 1u), 2 * iy + ((k >> 1) & 1u), 2 * iz + ((k >> 2) & 1u));
+            }
+            __syncwarp();
+            if (tid == 0) { M.n = n0 + 8 * total; M.seq += 8u * total; }
+        }
+        __syncthreads();
+        // ---- (h) prune everything that can no longer be popped (lb >= best_error, fgoicp.cpp:126)
+        const unsigned be_bits = __float_as_uint(best_error);
+        for (int i = tid; i < M.n; i += NT)
+        {
+            unsigned long long key = pool[i];
+            if (key != BNB_KEY_MAX && (unsigned)(key >> 32) >= be_bits) pool[i] = BNB_KEY_MAX;
+        }
+        __syncthreads();
+    }
+
+    // ---- (a) sort the pool ascending; dead entries (KEY_MAX) sink to the end
+    const int n = M.n;
+    int P = 32; while (P < n) P <<= 1;
+    for (int i = n + tid; i < P; i += NT) pool[i] = BNB_KEY_MAX;
+    __syncthreads();
+    for (int k = 2; k <= P; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1)
+        {
+            for (int i = tid; i < P; i += NT)
+            {
+                int ixj = i ^ j;
+                if (ixj > i)
+                {
+                    unsigned long long a = pool[i], b = pool[ixj];
+                    bool up = ((i & k) == 0);
+                    if ((a > b) == up) { pool[i] = b; pool[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    // ---- (b) live count m = index of the first dead entry
+    if (tid == 0) s_m = (pool[P - 1] != BNB_KEY_MAX) ? P : -1;
+    __syncthreads();
+    for (int i = tid; i < P; i += NT)
+    {
+        bool live = pool[i] != BNB_KEY_MAX;
+        bool prev_live = (i == 0) ? true : (pool[i - 1] != BNB_KEY_MAX);
+        if (!live && prev_live) s_m = i;              // exactly one thread at most
+    }
+    __syncthreads();
+    // ---- (c) stop test and (d) batch pop
+    if (tid == 0)
+    {
+        int m = s_m;
+        int stop = 0, nb = 0;
+        if (m <= 0) stop = 1;
+        else
+        {
+            float top_lb = __uint_as_float((unsigned)(pool[0] >> 32));
+            if (__fsub_rn(M.best_error, top_lb) < sse_threshold) stop = 1;      // fgoicp.cpp:120
+            else nb = min(m, BNB_BATCH_MAX);
+        }
+        s_stop = stop; s_nb = nb;
+    }
+    __syncthreads();
+    const int m = s_m, nb = s_nb;
+    if (tid < BNB_BATCH_MAX)
+    {
+        float4 t = make_float4(0.f, 0.f, 0.f, -1.0f);      // unused slot
+        if (tid < nb)
+        {
+            unsigned long long key = pool[tid];
+            gkeys[tid] = key;
+            t = bnb_key_cube(key);
+        }
+        if (tid < nb || tid < nb_prev) gtc[tid] = t;      // also clears the slots the previous batch used
+    }
+    // keep the survivors [nb, m) for the next round
+    if (!s_stop) for (int i = nb + tid; i < m; i += NT) gpool[i - nb] = pool[i];
+    if (tid == 0)
+    {
+        M.nb = nb; M.n = s_stop ? 0 : m - nb; M.done = s_stop;
+        meta[r] = M;
+        counts[r] = nb;
+        if (!s_stop) { atomicAdd(&ctl[0], 1u); atomicAdd(&ctl[1], (unsigned)nb); }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 
 template <int SAMPLER, int NWARPS>
 static int launch_bnb_t(fgoicp_ctx* c, const float4* d_rot, int Rn, int csize, int fix_rot, float best_sse, float thr, BnbOut* d_out)
@@ -305,6 +515,118 @@ static int launch_bnb(fgoicp_ctx* c, const float4* d_rot, int Rn, int fix_rot, f
 
 static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
+__global__ void k_bnbr_export(const BnbrMeta* __restrict__ meta, int Rn, BnbOut* __restrict__ out)
+{
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= Rn) return;
+    BnbrMeta m = meta[r];
+    BnbOut o;
+    o.best_ub = m.best_ub;
+    o.best_t[0] = m.best_t[0]; o.best_t[1] = m.best_t[1]; o.best_t[2] = m.best_t[2];
+    o.evals = m.evals; o.batches = m.batches; o.pushed = m.seq;
+    out[r] = o;
+}
+
+int fg_phased_prepare(fgoicp_ctx* c, const float4* d_rot, int Rn, int fix_rot, int T);
+int fg_phased_eval(fgoicp_ctx* c, int Rn, const float4* d_tc, int T, float* d_lb, float* d_ub, unsigned int* d_best_bits);
+int fg_phased_max_cubes(const fgoicp_ctx* c);
+int fg_bounds_slices(const fgoicp_ctx* c, int active);
+int fg_bounds_plain_counts(fgoicp_ctx* c, const float4* d_rot, int Rn, int fix_rot, const float4* d_tc, int T,
+                           const int* d_counts, int S, double* d_partial, float* d_lb, float* d_ub);
+
+// All Rn searches of a level, one iteration per round (see k_bnbr_round).  Results land in d_out exactly as
+// launch_bnb leaves them.
+static int bnb_rounds(fgoicp_ctx* c, const float4* d_rot, int Rn, int fix_rot, float best_sse, float thr, BnbOut* d_out)
+{
+    const int T = BNB_BATCH_MAX;
+    const int S_max = std::max(1, std::min(16, (int)(c->ns / 256)));
+    size_t b_meta = align256(sizeof(BnbrMeta) * (size_t)Rn);
+    size_t b_pool = align256(sizeof(unsigned long long) * (size_t)Rn * BNBR_POOL);
+    size_t b_keys = align256(sizeof(unsigned long long) * (size_t)Rn * T);
+    size_t b_tc = align256(sizeof(float4) * (size_t)Rn * T);
+    size_t b_cnt = align256(sizeof(int) * (size_t)Rn);
+    size_t b_out = align256(sizeof(float) * (size_t)Rn * T);
+    size_t b_ctl = 256;
+    size_t b_part = align256(sizeof(double) * 2 * (size_t)Rn * T * S_max);
+    size_t need = b_meta + b_pool + b_keys + b_tc + b_cnt + 2 * b_out + b_ctl + b_part;
+    if (need > c->rounds_bytes)
+    {
+        FG_CUDA(cudaStreamSynchronize(c->stream));
+        cudaFree(c->d_rounds); c->d_rounds = nullptr; c->rounds_bytes = 0;
+        FG_CUDA(cudaMalloc(&c->d_rounds, need));
+        c->rounds_bytes = need;
+    }
+    int rc = fg::ensure_pinned(c, 4096);
+    if (rc) return rc;
+    char* p = (char*)c->d_rounds;
+    BnbrMeta* d_meta = (BnbrMeta*)p; p += b_meta;
+    unsigned long long* d_pool = (unsigned long long*)p; p += b_pool;
+    unsigned long long* d_keys = (unsigned long long*)p; p += b_keys;
+    float4* d_tc = (float4*)p; p += b_tc;
+    int* d_cnt = (int*)p; p += b_cnt;
+    float* d_lb = (float*)p; p += b_out;
+    float* d_ub = (float*)p; p += b_out;
+    unsigned int* d_ctl = (unsigned int*)p; p += b_ctl;
+    double* d_part = (double*)p;
+
+    int min_pairs = 12000;                             // fewer popped cubes than this: plain kernel (the sweep has a ~1 ms floor)
+    if (const char* e = getenv("FGOICP_BNBR_MIN_PAIRS")) min_pairs = atoi(e);
+    bool can_phase = c->phased && c->sampler == FGOICP_SAMPLER_PACKED && Rn <= fg_phased_max_cubes(c);
+    bool prepared = false;
+
+    size_t smem = sizeof(unsigned long long) * BNB_POOL;
+    FG_CUDA(cudaFuncSetAttribute(k_bnbr_round, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_bnbr_init<<<(Rn + 127) / 128, 128, 0, c->stream>>>(d_meta, d_pool, Rn, best_sse, d_cnt, d_tc);
+    FG_CUDA(cudaGetLastError());
+    volatile unsigned int* h_ctl = (volatile unsigned int*)((char*)c->h_pinned + 2048);
+    const bool log_rounds = getenv("FGOICP_BNBR_LOG") != nullptr;
+    auto t_prev = std::chrono::steady_clock::now();
+    // a search pops at most 4681 cubes, at least one per round
+    for (int round = 0; round < 4700; ++round)
+    {
+        FG_CUDA(cudaMemsetAsync(d_ctl, 0, 8, c->stream));
+        k_bnbr_round<<<Rn, BNBR_THREADS, smem, c->stream>>>(d_meta, d_pool, d_keys, d_tc, d_cnt, d_lb, d_ub, thr, (int)c->ns, d_ctl);
+        FG_CUDA(cudaGetLastError());
+        FG_CUDA(cudaMemcpyAsync((void*)h_ctl, d_ctl, 8, cudaMemcpyDeviceToHost, c->stream));
+        FG_CUDA(cudaStreamSynchronize(c->stream));
+        const int active = (int)h_ctl[0], pairs = (int)h_ctl[1];
+        if (log_rounds)
+        {
+            auto now = std::chrono::steady_clock::now();
+            fprintf(stderr, "[bnbr] Rn %d round %d active %d pairs %d  +%.1f us\n", Rn, round, active, pairs,
+                    std::chrono::duration<double, std::micro>(now - t_prev).count());
+            t_prev = now;
+        }
+        if (active == 0) break;
+        bool phased = can_phase && pairs >= min_pairs;
+        if (phased)
+        {
+            if (!prepared)
+            {
+                rc = fg_phased_prepare(c, d_rot, Rn, fix_rot, T);
+                if (rc < 0) return rc;
+                if (rc > 0) { can_phase = false; phased = false; }
+                prepared = rc == 0;
+            }
+            if (phased)
+            {
+                rc = fg_phased_eval(c, Rn, d_tc, T, d_lb, d_ub, nullptr);
+                if (rc < 0) return rc;
+                if (rc > 0) { can_phase = false; phased = false; }
+            }
+        }
+        if (!phased)
+        {
+            int S = std::min(S_max, fg_bounds_slices(c, active));
+            rc = fg_bounds_plain_counts(c, d_rot, Rn, fix_rot, d_tc, T, d_cnt, S, d_part, d_lb, d_ub);
+            if (rc) return rc;
+        }
+    }
+    k_bnbr_export<<<(Rn + 127) / 128, 128, 0, c->stream>>>(d_meta, Rn, d_out);
+    FG_CUDA(cudaGetLastError());
+    return FGOICP_OK;
+}
+
 // host cubes -> device, run Rn searches, results to host vector
 static int bnb_batch_host(fgoicp_ctx* c, const float* rot_xyz_span, int Rn, int fix_rot, float best_sse,
                           float sse_threshold, std::vector<BnbOut>& res, float* ms)
@@ -319,7 +641,16 @@ static int bnb_batch_host(fgoicp_ctx* c, const float* rot_xyz_span, int Rn, int 
     memcpy(hp, rot_xyz_span, sizeof(float4) * Rn);
     FG_CUDA(cudaMemcpyAsync(dp, hp, sizeof(float4) * Rn, cudaMemcpyHostToDevice, c->stream));
     FG_CUDA(cudaEventRecord(c->ev0, c->stream));
-    rc = launch_bnb(c, (const float4*)dp, Rn, fix_rot, best_sse, sse_threshold, (BnbOut*)(dp + b_rot));
+    // Default: one persistent block (cluster) per search.  The round-synchronous schedule (all searches in
+    // lock step, each round's cubes through the phase-ordered kernel) is opt-in (fgoicp_set_bnb_mode(2) or
+    // FGOICP_BNBR_MIN_CUBES=<n>): measured on W5 it evaluates a 48k-cube round 1.6x faster but the search is a
+    // chain of ~30 rounds of <= 4096 cubes for most waves, where the sweep's ~1 ms floor and the host
+    // round trip per round cancel the gain (run() 211 ms either way).
+    int rounds_min = 0x7fffffff;
+    if (const char* e = getenv("FGOICP_BNBR_MIN_CUBES")) rounds_min = atoi(e);
+    bool rounds = c->bnb_mode == 2 || (c->bnb_mode == 0 && Rn >= rounds_min && c->phased && c->sampler == FGOICP_SAMPLER_PACKED);
+    if (rounds) rc = bnb_rounds(c, (const float4*)dp, Rn, fix_rot, best_sse, sse_threshold, (BnbOut*)(dp + b_rot));
+    else rc = launch_bnb(c, (const float4*)dp, Rn, fix_rot, best_sse, sse_threshold, (BnbOut*)(dp + b_rot));
     if (rc) return rc;
     FG_CUDA(cudaEventRecord(c->ev1, c->stream));
     FG_CUDA(cudaMemcpyAsync(hp + b_rot, dp + b_rot, sizeof(BnbOut) * Rn, cudaMemcpyDeviceToHost, c->stream));
@@ -346,6 +677,14 @@ extern "C" int fgoicp_bnb_r3_batch(fgoicp_ctx* c, const float* rot_xyz_span, int
         if (best_t) { best_t[3 * i] = res[i].best_t[0]; best_t[3 * i + 1] = res[i].best_t[1]; best_t[3 * i + 2] = res[i].best_t[2]; }
         if (evals) evals[i] = res[i].evals;
     }
+    return FGOICP_OK;
+}
+
+extern "C" int fgoicp_set_bnb_mode(fgoicp_ctx* c, int mode)
+{
+    FG_ARG(c, "NULL context");
+    FG_ARG(mode >= 0 && mode <= 2, "mode must be 0 (auto), 1 (persistent) or 2 (round-synchronous)");
+    c->bnb_mode = mode;
     return FGOICP_OK;
 }
 

@@ -32,7 +32,7 @@ k_bounds_multi(LutDev L, const float4* __restrict__ data, int ns,
                const float4* __restrict__ rot, const float* __restrict__ Rmats, int fix_rot,
                const float4* __restrict__ tcubes, int T, int S,
                double* __restrict__ partial, float* __restrict__ lb, float* __restrict__ ub,
-               unsigned int* __restrict__ best_ub_bits)
+               unsigned int* __restrict__ best_ub_bits, const int* __restrict__ counts)
 {
     __shared__ float sR[9];
     __shared__ float s_sin;
@@ -41,6 +41,9 @@ k_bounds_multi(LutDev L, const float4* __restrict__ data, int ns,
 
     const int r = blockIdx.x / S;
     const int slice = blockIdx.x - r * S;
+    // optional per-rotation-cube cube count (<= T): the rest of the row is unused (round-synchronous search)
+    const int Tr = counts ? min(T, counts[r]) : T;
+    if (Tr <= 0) return;
     if (threadIdx.x == 0)
     {
         float4 rc = rot[r];
@@ -62,9 +65,9 @@ k_bounds_multi(LutDev L, const float4* __restrict__ data, int ns,
     const int p0 = slice * per;
     const int p1 = min(ns, p0 + per);
 
-    for (int c0 = 0; c0 < T; c0 += BD_CHUNK)
+    for (int c0 = 0; c0 < Tr; c0 += BD_CHUNK)
     {
-        const int nch = min(BD_CHUNK, T - c0);
+        const int nch = min(BD_CHUNK, Tr - c0);
         __syncthreads();
         if (threadIdx.x < nch) s_tc[threadIdx.x] = tcubes[(size_t)r * T + c0 + threadIdx.x];
         __syncthreads();
@@ -136,6 +139,7 @@ struct BoundsLaunch
 {
     const float4* d_rot; const float* d_Rmats; int Rn; int fix_rot;
     const float4* d_tc; int T; float* d_lb; float* d_ub; float* d_best_ub; double* d_partial; int S;
+    const int* d_counts = nullptr; int no_phased = 0;
 };
 
 int fg_bounds_phased(fgoicp_ctx* c, const float4* d_rot, int Rn, int fix_rot, const float4* d_tc, int T,
@@ -143,7 +147,7 @@ int fg_bounds_phased(fgoicp_ctx* c, const float4* d_rot, int Rn, int fix_rot, co
 
 static int run_bounds(fgoicp_ctx* c, const BoundsLaunch& b)
 {
-    if (c->phased && c->sampler == FGOICP_SAMPLER_PACKED && !b.d_Rmats && (long long)b.Rn * b.T >= 4096)
+    if (c->phased && !b.no_phased && c->sampler == FGOICP_SAMPLER_PACKED && !b.d_Rmats && (long long)b.Rn * b.T >= 4096)
     {
         int rc = fg_bounds_phased(c, b.d_rot, b.Rn, b.fix_rot, b.d_tc, b.T, b.d_lb, b.d_ub, b.d_best_ub);
         if (rc <= 0) return rc;       // done (0) or error (<0); 1 = not applicable, fall through
@@ -153,7 +157,7 @@ static int run_bounds(fgoicp_ctx* c, const BoundsLaunch& b)
     dim3 grid((unsigned)(b.Rn * b.S));
 #define FG_LAUNCH_BOUNDS(SMP)                                                                        \
     k_bounds_multi<SMP><<<grid, BD_THREADS, 0, c->stream>>>(c->lut, c->d_data, (int)c->ns, b.d_rot,  \
-        b.d_Rmats, b.fix_rot, b.d_tc, b.T, b.S, b.d_partial, b.d_lb, b.d_ub, b.S == 1 ? d_bits : nullptr)
+        b.d_Rmats, b.fix_rot, b.d_tc, b.T, b.S, b.d_partial, b.d_lb, b.d_ub, b.S == 1 ? d_bits : nullptr, b.d_counts)
     switch (c->sampler)
     {
     case FGOICP_SAMPLER_PACKED: FG_LAUNCH_BOUNDS(FGOICP_SAMPLER_PACKED); break;
@@ -172,6 +176,20 @@ static int run_bounds(fgoicp_ctx* c, const BoundsLaunch& b)
 }
 
 static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+// Plain (not phase-ordered) kernel over device-resident cube lists with a per-rotation-cube count; only
+// `active` of the Rn rows have work (the launch geometry is sized for those).  d_partial: scratch of
+// 2 * Rn * T * S doubles provided by the caller when S > 1 (S from fg_bounds_slices).
+int fg_bounds_slices(const fgoicp_ctx* c, int active) { return pick_slices(c, std::max(1, active)); }
+int fg_bounds_plain_counts(fgoicp_ctx* c, const float4* d_rot, int Rn, int fix_rot, const float4* d_tc, int T,
+                           const int* d_counts, int S, double* d_partial, float* d_lb, float* d_ub)
+{
+    BoundsLaunch b;
+    b.d_rot = d_rot; b.d_Rmats = nullptr; b.Rn = Rn; b.fix_rot = fix_rot; b.d_tc = d_tc; b.T = T;
+    b.d_lb = d_lb; b.d_ub = d_ub; b.d_best_ub = nullptr; b.d_partial = d_partial; b.S = S;
+    b.d_counts = d_counts; b.no_phased = 1;
+    return run_bounds(c, b);
+}
 
 // host-buffer path: stage through pinned memory, one H2D, one launch, one D2H
 static int bounds_host(fgoicp_ctx* c, const float* rot_xyz_span, const float* Rmats, int Rn, int fix_rot,

@@ -313,6 +313,8 @@ k_bounds_phased(LutDev L, int ns,
     const int n_groups = gbase[Rn];
     const long long gw = (long long)blockIdx.x * PH_WARPS + w, nw = (long long)gridDim.x * PH_WARPS;
     const int gfirst = (int)(gw * n_groups / nw), glast = (int)((gw + 1) * n_groups / nw);
+    // warps that own at least one group (the others never enter the sweep, so pacing must not wait for them)
+    const int nw_paced = (int)min((long long)n_groups, nw);
     // normally one sweep; a warp that owns more than PH_MAXGRP groups sweeps again for the rest (correct,
     // merely out of phase with the others)
     for (int g0 = gfirst; g0 < glast; g0 += PH_MAXGRP)
@@ -349,7 +351,7 @@ k_bounds_phased(LutDev L, int ns,
             {
                 const volatile int* flag = phase_done + (phi - pace_lag);
 #pragma unroll 1
-                for (int spin = 0; spin < 20000 && *flag < (int)nw; ++spin) __nanosleep(100);
+                for (int spin = 0; spin < 20000 && *flag < nw_paced; ++spin) __nanosleep(100);
             }
             __syncwarp();
         }
@@ -437,29 +439,47 @@ k_bounds_phased(LutDev L, int ns,
     }   // sweeps
 }
 
-// host: returns FGOICP_OK and runs the phased path, or 1 if the problem does not fit it (caller falls back)
-int fg_bounds_phased(fgoicp_ctx* c, const float4* d_rot, int Rn, int fix_rot, const float4* d_tc, int T,
-                     float* d_lb, float* d_ub, float* d_best_ub)
+// ---------------------------------------------------------------------------------------------
+// host side.  Two steps so that callers evaluating MANY cube lists against the SAME rotation cubes (the
+// round-synchronous inner search, bnb_rounds.cu) bin the points once:
+//   fg_phased_prepare : scratch layout for (Rn, T) + k_phase_bin (rotated points in bucket order)
+//   fg_phased_eval    : z-groups of the given translation cubes + the phase-ordered sweep
+// Both return FGOICP_OK, a negative error, or 1 = "does not fit this path" (caller uses the plain kernel).
+// ---------------------------------------------------------------------------------------------
+struct PhLayout
+{
+    int Rn, T, blocks;
+    int* d_off; PhGroup* d_grp; int* d_gcount; int* d_gbase; int* d_pace; float4* d_P;
+};
+
+static size_t ph_scratch_cap()
+{
+    size_t cap = (size_t)2 << 30;
+    if (const char* e = getenv("FGOICP_PHASED_SCRATCH_MB")) cap = (size_t)atoll(e) << 20;
+    return cap;
+}
+
+// largest number of rotation cubes whose bucket-ordered points (16 B per cube and point) fit the scratch cap
+int fg_phased_max_cubes(const fgoicp_ctx* c)
+{
+    return (int)std::min<size_t>((size_t)1 << 30, std::max<size_t>(1, ph_scratch_cap() / (sizeof(float4) * c->ns)));
+}
+
+static int ph_layout(fgoicp_ctx* c, int Rn, int T, PhLayout& L)
 {
     if (!c->d_packed) return 1;
+    if ((long long)Rn * T > (1LL << 30) || Rn > fg_phased_max_cubes(c)) return 1;
     // persistent blocks, all co-resident (a second wave would start its sweep out of phase)
     int per_sm = 0;
     FG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bounds_phased, PH_THREADS, 0));
     if (per_sm < 1) return 1;
     if (const char* e = getenv("FGOICP_PHASED_BPS")) per_sm = std::max(1, std::min(per_sm, atoi(e)));
-    int blocks = per_sm * c->sm_count;
-    // the bucket-ordered rotated points take 16 B per (rotation cube, point): cap the scratch and, if need be,
-    // sweep the rotation cubes in several launches
-    size_t cap = (size_t)2 << 30;
-    if (const char* e = getenv("FGOICP_PHASED_SCRATCH_MB")) cap = (size_t)atoll(e) << 20;
-    int Rc = (int)std::min<size_t>((size_t)Rn, std::max<size_t>(1, cap / (sizeof(float4) * c->ns)));
-    if ((long long)Rc * T > (1LL << 30)) return 1;
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
-    size_t b_off = al(sizeof(int) * (PH_NB + 1) * (size_t)Rc);
-    size_t b_grp = al(sizeof(PhGroup) * (size_t)Rc * T);
-    size_t b_cnt = al(sizeof(int) * (size_t)(Rc + 1)) * 2;
+    size_t b_off = al(sizeof(int) * (PH_NB + 1) * (size_t)Rn);
+    size_t b_grp = al(sizeof(PhGroup) * (size_t)Rn * T);
+    size_t b_cnt = al(sizeof(int) * (size_t)(Rn + 1)) * 2;
     size_t b_pace = al(sizeof(int) * PH_PHASES);
-    size_t b_P = sizeof(float4) * (size_t)Rc * c->ns;
+    size_t b_P = sizeof(float4) * (size_t)Rn * c->ns;
     size_t need = b_off + b_grp + b_cnt + b_pace + b_P;
     if (need > c->phase_bytes)
     {
@@ -469,29 +489,63 @@ int fg_bounds_phased(fgoicp_ctx* c, const float4* d_rot, int Rn, int fix_rot, co
         c->phase_bytes = need;
     }
     char* base = (char*)c->d_phase;
-    int* d_off = (int*)base;
-    PhGroup* d_grp = (PhGroup*)(base + b_off);
-    int* d_gcount = (int*)(base + b_off + b_grp);
-    int* d_gbase = (int*)(base + b_off + b_grp + b_cnt / 2);
-    int* d_pace = (int*)(base + b_off + b_grp + b_cnt);
-    float4* d_P = (float4*)(base + b_off + b_grp + b_cnt + b_pace);
-    unsigned int* d_bits = (unsigned int*)d_best_ub;
-    if (d_bits) FG_CUDA(cudaMemsetAsync(d_bits, 0x7f, 4, c->stream));   // 0x7f7f7f7f: a huge positive float
+    L.Rn = Rn; L.T = T; L.blocks = per_sm * c->sm_count;
+    L.d_off = (int*)base;
+    L.d_grp = (PhGroup*)(base + b_off);
+    L.d_gcount = (int*)(base + b_off + b_grp);
+    L.d_gbase = (int*)(base + b_off + b_grp + b_cnt / 2);
+    L.d_pace = (int*)(base + b_off + b_grp + b_cnt);
+    L.d_P = (float4*)(base + b_off + b_grp + b_cnt + b_pace);
+    return FGOICP_OK;
+}
+
+int fg_phased_prepare(fgoicp_ctx* c, const float4* d_rot, int Rn, int fix_rot, int T)
+{
+    PhLayout L;
+    int rc = ph_layout(c, Rn, T, L);
+    if (rc) return rc;
+    k_phase_bin<<<Rn, PH_THREADS, 0, c->stream>>>(c->d_data, (int)c->ns, d_rot, fix_rot, L.d_P, L.d_off);
+    FG_CUDA(cudaGetLastError());
+    return FGOICP_OK;
+}
+
+// d_tc[Rn][T] (slots with a negative span are unused) -> d_lb, d_ub [Rn][T]; (Rn, T) as prepared.
+// d_best_bits (optional) is atomicMin'ed with the float bits of every ub; the caller initialises it.
+int fg_phased_eval(fgoicp_ctx* c, int Rn, const float4* d_tc, int T, float* d_lb, float* d_ub, unsigned int* d_best_bits)
+{
+    PhLayout L;
+    int rc = ph_layout(c, Rn, T, L);
+    if (rc) return rc;
     int pace = 2, pf = 0;
     if (const char* e = getenv("FGOICP_PHASED_LAG")) pace = atoi(e);
     if (const char* e = getenv("FGOICP_PHASED_PF")) pf = atoi(e);
+    k_phase_groups<<<Rn, 32, 0, c->stream>>>(d_tc, T, L.d_grp, L.d_gcount);
+    k_phase_scan<<<1, 1024, 0, c->stream>>>(L.d_gcount, Rn, L.d_gbase);
+    FG_CUDA(cudaMemsetAsync(L.d_pace, 0, sizeof(int) * PH_PHASES, c->stream));
+    k_bounds_phased<<<L.blocks, PH_THREADS, 0, c->stream>>>(c->lut, (int)c->ns, d_tc, Rn, T, L.d_grp, L.d_gbase, L.d_P, L.d_off,
+                                                          d_lb, d_ub, d_best_bits, L.d_pace, pace,
+                                                          (long long)Rn * T < 4096 ? 0 : pf);
+    FG_CUDA(cudaGetLastError());
+    return FGOICP_OK;
+}
+
+int fg_bounds_phased(fgoicp_ctx* c, const float4* d_rot, int Rn, int fix_rot, const float4* d_tc, int T,
+                     float* d_lb, float* d_ub, float* d_best_ub)
+{
+    if (!c->d_packed) return 1;
+    // the bucket-ordered rotated points take 16 B per (rotation cube, point): if the scratch cap is smaller,
+    // sweep the rotation cubes in several launches
+    const int Rc = std::min(Rn, fg_phased_max_cubes(c));
+    if ((long long)Rc * T > (1LL << 30)) return 1;
+    unsigned int* d_bits = (unsigned int*)d_best_ub;
+    if (d_bits) FG_CUDA(cudaMemsetAsync(d_bits, 0x7f, 4, c->stream));   // 0x7f7f7f7f: a huge positive float
     for (int r0 = 0; r0 < Rn; r0 += Rc)
     {
         const int rn = std::min(Rc, Rn - r0);
-        const float4* tc = d_tc + (size_t)r0 * T;
-        k_phase_bin<<<rn, PH_THREADS, 0, c->stream>>>(c->d_data, (int)c->ns, d_rot + r0, fix_rot, d_P, d_off);
-        k_phase_groups<<<rn, 32, 0, c->stream>>>(tc, T, d_grp, d_gcount);
-        k_phase_scan<<<1, 1024, 0, c->stream>>>(d_gcount, rn, d_gbase);
-        FG_CUDA(cudaMemsetAsync(d_pace, 0, sizeof(int) * PH_PHASES, c->stream));
-        k_bounds_phased<<<blocks, PH_THREADS, 0, c->stream>>>(c->lut, (int)c->ns, tc, rn, T, d_grp, d_gbase, d_P, d_off,
-                                                            d_lb + (size_t)r0 * T, d_ub + (size_t)r0 * T, d_bits, d_pace,
-                                                            pace, (long long)rn * T < 4096 ? 0 : pf);
-        FG_CUDA(cudaGetLastError());
+        int rc = fg_phased_prepare(c, d_rot + r0, rn, fix_rot, T);
+        if (rc) return rc;
+        rc = fg_phased_eval(c, rn, d_tc + (size_t)r0 * T, T, d_lb + (size_t)r0 * T, d_ub + (size_t)r0 * T, d_bits);
+        if (rc) return rc;
     }
     return FGOICP_OK;
 }

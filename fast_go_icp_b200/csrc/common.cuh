@@ -112,6 +112,11 @@ struct fgoicp_ctx
     size_t phase_bytes = 0;
     int phased = 0;                           // 1: fgoicp_bounds_multi* use the phase-ordered kernel
 
+    // round-synchronous inner search (bnb.cu): per-level state in HBM
+    void* d_rounds = nullptr;
+    size_t rounds_bytes = 0;
+    int bnb_mode = 0;                         // 0: auto, 1: persistent per-cube kernel, 2: round-synchronous
+
     // ICP state
     float4* d_work = nullptr;                 // working copy W  [ns]
     unsigned long long* d_nnkey = nullptr;    // packed (value bits << 32 | index) [ns]

@@ -94,6 +94,10 @@ int fgoicp_lut_sample(fgoicp_ctx* ctx, const float* q_xyz, size_t n, int sampler
 /* Evaluation order of fgoicp_bounds_multi / _multi_dev: 1 = z-phase-ordered kernel (default with the packed
  * sampler; same results, L2-friendly), 0 = plain kernel. */
 int fgoicp_set_phased(fgoicp_ctx* ctx, int on);
+/* Schedule of the inner searches behind fgoicp_bnb_r3_batch / fgoicp_so3_level_*: 0 = default (one persistent
+ * thread-block cluster per search), 1 = same, explicitly, 2 = round-synchronous (all searches advance one
+ * iteration per round, bounds of each round through the phase-ordered kernel).  Same results either way. */
+int fgoicp_set_bnb_mode(fgoicp_ctx* ctx, int mode);
 /* Measurement hook: useful GB/s of independent random gathers of width_bytes (16/32/64/128) over a
  * buffer of `bytes` bytes -- the gather roofline the bound kernels are compared with. */
 int fgoicp_gather_probe(fgoicp_ctx* ctx, size_t bytes, int width_bytes, int blocks_per_sm, float* out_gbps);

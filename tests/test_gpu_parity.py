@@ -226,6 +226,33 @@ def test_bnb_r3_vs_oracle(small_problem, gpu_ctx, fix_rot):
         assert u1 == ub[1] and np.array_equal(t1, bt[1]) and e1 == ev[1]
 
 
+@pytest.mark.parametrize("fix_rot", [True, False])
+def test_bnb_round_synchronous_equals_persistent(small_problem, gpu_ctx, fix_rot):
+    """The round-synchronous schedule (all searches of a level advance together, bounds of every round through
+    the phase-ordered kernel or -- for the last stragglers -- the plain one) must take exactly the decisions of
+    the persistent per-cube kernel: same best_ub bits, same best_t, same number of evaluations, for every cube;
+    and both must match the oracle's traversal."""
+    pp = small_problem
+    thr = len(pp["data"]) * 1e-4
+    cubes = workloads.rotation_cube_list(160, seed=5)
+    cubes[:40, 3] = 0.125                                    # mixed spans: different rotation slack per cube
+    import os
+    for best_sse, min_pairs in ((1e10, "0"), (3.0, "64"), (0.6, "100000")):
+        os.environ["FGOICP_BNBR_MIN_PAIRS"] = min_pairs      # phased for every round / mixed / plain kernel only
+        gpu_ctx.set_bnb_mode(1)
+        ub1, bt1, ev1 = gpu_ctx.bnb_r3_batch(cubes, fix_rot, best_sse, thr)
+        gpu_ctx.set_bnb_mode(2)
+        ub2, bt2, ev2 = gpu_ctx.bnb_r3_batch(cubes, fix_rot, best_sse, thr)
+        gpu_ctx.set_bnb_mode(0)
+        assert np.array_equal(ev1, ev2)
+        assert np.array_equal(ub1.view(np.uint32), ub2.view(np.uint32))
+        assert np.array_equal(bt1, bt2)
+        for i in (0, 57, 159):
+            wub, wbt, wev, _ = O.bnb_r3(pp["model"], pp["data"], *_lut(pp), cubes[i], fix_rot, best_sse, thr)
+            assert ev2[i] == wev and np.isclose(ub2[i], wub, rtol=ULP, atol=0) and np.array_equal(bt2[i], wbt)
+    os.environ.pop("FGOICP_BNBR_MIN_PAIRS", None)
+
+
 @pytest.mark.skipif(not REF.available(), reason="oracle/_ref not built")
 def test_against_unmodified_reference_kernels(small_problem, gpu_ctx):
     """The reference's own CUDA code (real tex3D, per-cube launches, thrust reductions) on the same clouds."""

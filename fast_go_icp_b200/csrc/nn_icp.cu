@@ -189,6 +189,9 @@ __device__ __forceinline__ float fg_sqrt_preimage_hi(float s)
 //      and merge their winners with a shuffle reduction on the packed 64-bit key.
 // All pruning tests carry a relative slack: they may visit too much, never too little.
 #define NNG_WARPS 4
+#ifndef NN_FAST_ROOTED
+#define NN_FAST_ROOTED 0
+#endif
 template <int ROOTED>
 __global__ void __launch_bounds__(NNG_WARPS * 32)
 k_nn_grid(CellGrid g, LutDev L, float res, const float4* __restrict__ data, const float4* __restrict__ work_base,
@@ -222,7 +225,18 @@ k_nn_grid(CellGrid g, LutDev L, float res, const float4* __restrict__ data, cons
     float U = (sqrtf(Tn) + sqrtf(ex * ex + ey * ey + ez * ez)) * 1.0001f + 1e-6f;
     float U2 = U * U;
 
-    float best = FG_INF, thr_lo = ROOTED ? fg_sqrt_preimage_lo(FG_INF) : FG_INF, thr_hi = thr_lo;
+    // Rooted rule, fast path (NN_FAST_ROOTED): first j minimising sqrtf(d2) (icp3d.cu:17-26) differs from the
+    // squared rule only when another point's d2 rounds to the same square root as the winner's, i.e. lies in
+    // (d2_min, hi(sqrtf(d2_min))], a window of about one ulp.  Pass 1 searches with the cheap squared compare and
+    // tracks the runner-up distance; only if that falls in the window is the query redone with the exact rule.
+    const float U2_0 = U2;
+    unsigned long long key = 0xffffffffffffffffull;
+#pragma unroll 1
+    for (int exact = (ROOTED && NN_FAST_ROOTED) ? 0 : 1; exact < 2; ++exact)
+    {
+    U2 = U2_0;
+    float best = FG_INF, thr_lo = (ROOTED && exact) ? fg_sqrt_preimage_lo(FG_INF) : FG_INF, thr_hi = thr_lo;
+    float second = FG_INF;
     int best_idx = 0x7fffffff;
 
     const float h = g.h, inv_h = g.inv_h;
@@ -256,7 +270,7 @@ k_nn_grid(CellGrid g, LutDev L, float res, const float4* __restrict__ data, cons
                     float4 m = __ldg(g.pts + k);
                     float d = fg_sq3(__fsub_rn(qx, m.x), __fsub_rn(qy, m.y), __fsub_rn(qz, m.z));
                     int idx = __float_as_int(m.w);
-                    if (ROOTED)
+                    if (ROOTED && !(NN_FAST_ROOTED && !exact))
                     {
                         if (d < thr_lo)
                         {
@@ -266,6 +280,14 @@ k_nn_grid(CellGrid g, LutDev L, float res, const float4* __restrict__ data, cons
                             U2 = fminf(U2, thr_hi * 1.00002f + 1e-12f);
                         }
                         else if (d <= thr_hi && idx < best_idx) best_idx = idx;
+                    }
+                    else if (ROOTED)
+                    {
+                        // squared compare that also keeps the runner-up distance (decides below whether the
+                        // rooted rule could pick another index)
+                        if (d < best) { second = best; best = d; best_idx = idx; U2 = fminf(U2, d * 1.00002f + 1e-12f); }
+                        else if (d == best) best_idx = min(best_idx, idx);
+                        else second = fminf(second, d);
                     }
                     else
                     {
@@ -282,7 +304,7 @@ k_nn_grid(CellGrid g, LutDev L, float res, const float4* __restrict__ data, cons
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) U2 = fminf(U2, __shfl_xor_sync(0xffffffffu, U2, o));
     }
-    unsigned long long key = 0xffffffffffffffffull;
+    key = 0xffffffffffffffffull;
     if (best_idx != 0x7fffffff) key = ((unsigned long long)__float_as_uint(best) << 32) | (unsigned int)best_idx;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1)
@@ -290,6 +312,21 @@ k_nn_grid(CellGrid g, LutDev L, float res, const float4* __restrict__ data, cons
         unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
         key = other < key ? other : key;
     }
+    if (ROOTED && NN_FAST_ROOTED && !exact)
+    {
+        if (key == 0xffffffffffffffffull) break;
+        const float wbest = __uint_as_float((unsigned int)(key >> 32));
+        float cand = best > wbest ? best : second;                 // smallest d2 strictly above the winner's, warp-wide
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cand = fminf(cand, __shfl_xor_sync(0xffffffffu, cand, o));
+        const float s = __fsqrt_rn(wbest);
+        if (cand > fg_sqrt_preimage_hi(s))
+        {
+            key = ((unsigned long long)__float_as_uint(s) << 32) | (key & 0xffffffffull);
+            break;                                                 // the usual case: no near-tie, done
+        }
+    }
+    }   // exact
     if (lane == 0) keys[i] = key;
 }
 

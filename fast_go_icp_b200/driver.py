@@ -143,7 +143,8 @@ class FastGoICP:
     """Python mirror of icp::FastGoICP (reference fgoicp/fgoicp.hpp:10-108)."""
 
     def __init__(self, target, source, lut_resolution, mse_threshold, device=0, sampler=None,
-                 flags=capi.BUILD_PACKED, group=None, ctx_factory=None, wave1=32, skip_dead_lb=True):
+                 flags=capi.BUILD_PACKED, group=None, ctx_factory=None, wave1=32, skip_dead_lb=True,
+                 schedule="level"):
         t0 = time.perf_counter()
         self.pp = preprocess(target, source)
         self.ns, self.nt = len(self.pp["data"]), len(self.pp["model"])
@@ -156,6 +157,10 @@ class FastGoICP:
         if sampler is not None:
             self.ctx.set_sampler(sampler)
         self.comm = _Comm(group)
+        # "level": level-synchronous, whole levels in flight, shardable over ranks (default);
+        # "bestfirst": the reference's own visiting order (fgoicp.cpp:32-100), one rotation cube at a time
+        assert schedule in ("level", "bestfirst")
+        self.schedule = schedule
         self.wave1 = int(wave1)      # size of the first wave of a level (0: whole level at once)
         self.skip_dead_lb = bool(skip_dead_lb)
         self.best_sse = M_INF
@@ -183,7 +188,10 @@ class FastGoICP:
         self.stats["icp_runs"] += 1
         self.stats["icp_iters"] += it
         self.stats["initial_icp_sse"] = float(e)
-        self._search_level_synchronous()
+        if self.schedule == "bestfirst":
+            self._search_best_first()
+        else:
+            self._search_level_synchronous()
         e, R, t, it = self.ctx.icp(self.best_R, self.best_t, 100, 0.0005)  # fgoicp.cpp:22-23
         self.best_sse, self.best_R, self.best_t = F(e), R, t
         self.stats["icp_runs"] += 1
@@ -192,7 +200,53 @@ class FastGoICP:
         t_out = restore_translation(R, t, self.pp["scale"], self.pp["offset_pcs"], self.pp["offset_pct"])
         return R.reshape(3, 3).T.copy(), t_out
 
-    # -- outer search -----------------------------------------------------------------------------
+    # -- outer search, reference order -------------------------------------------------------------
+    def _search_best_first(self):
+        """branch_and_bound_SO3 exactly as the reference walks it (fgoicp.cpp:32-100): a best-first heap of
+        rotation cubes (smaller lb first, then larger span; equal keys in insertion order -- the total order the
+        oracle uses for std::priority_queue's unspecified ties), each popped cube split in 8, every child searched
+        on its own.  Single rank only; this is the schedule the parity tests compare with the reference's run()."""
+        import heapq
+        assert self.comm.world == 1, "the best-first schedule does not shard"
+        thr = self.sse_threshold
+        heap, seq = [(F(0.0), -F(1.0), 0, (F(0), F(0), F(0), F(1.0), F(0.0), F(self.best_sse)))], 1
+        s = self.stats
+        while heap:
+            nlb, _, _, (x, y, z, pspan, _, nub) = heapq.heappop(heap)
+            if F(self.best_sse) - nlb <= thr:                               # fgoicp.cpp:44
+                break
+            span = F(pspan / F(2.0))
+            for k in range(8):
+                if span < F(0.05):                                          # fgoicp.cpp:53
+                    continue
+                cx = F(F(x - span) + F(F(k & 1) * pspan))
+                cy = F(F(y - span) + F(F((k >> 1) & 1) * pspan))
+                cz = F(F(z - span) + F(F((k >> 2) & 1) * pspan))
+                if not overlaps_so3(cx, cy, cz, span):                      # fgoicp.cpp:61
+                    continue
+                if not in_so3(cx, cy, cz):                                  # fgoicp.cpp:62-66
+                    heapq.heappush(heap, (nlb, -span, seq, (cx, cy, cz, span, nlb, nub)))
+                    seq += 1
+                    continue
+                cube = np.array([cx, cy, cz, span], F)
+                ub, bt, ev = self.ctx.bnb_r3(cube, True, self.best_sse, thr)              # fgoicp.cpp:69
+                s["bound_evals"] += int(ev)
+                s["rot_cubes"] += 1
+                if float(ub) < float(self.best_sse) * 1.8:                  # fgoicp.cpp:74 (double compare)
+                    R0, _ = rotation_matrix(cx, cy, cz)
+                    e, R, t, it = self.ctx.icp(R0, bt, 100, 0.005)          # fgoicp.cpp:76
+                    s["icp_runs"] += 1
+                    s["icp_iters"] += it
+                    if e < self.best_sse:                                   # fgoicp.cpp:79-84
+                        self.best_sse, self.best_R, self.best_t = F(e), R, t
+                lb, _, ev = self.ctx.bnb_r3(cube, False, self.best_sse, thr)              # fgoicp.cpp:90
+                s["bound_evals"] += int(ev)
+                if lb >= self.best_sse:                                     # fgoicp.cpp:92
+                    continue
+                heapq.heappush(heap, (F(lb), -span, seq, (cx, cy, cz, span, F(lb), F(ub))))
+                seq += 1
+
+    # -- outer search, level-synchronous -------------------------------------------------------------
     def _search_level_synchronous(self):
         comm = self.comm
         thr = self.sse_threshold

@@ -165,13 +165,22 @@ def test_cuda_vs_reference_and_oracle(name, ctxs):
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", PAIRS)
 def test_cuda_full_run_vs_reference(name):
-    """run() of the Python driver (level-synchronous schedule) against the reference's own run() on the same pair:
-    final SSE within 1e-3 relative, pose within 3e-3 (normalised frame) / the equivalent in original units."""
+    """run() through the Python driver against the reference's own run() on the same pair.
+    * reference visiting order ("bestfirst"): final SSE within 1e-3 relative (the final ICP stops at a 0.05 %
+      improvement), pose within 3e-3 in the normalised frame;
+    * level-synchronous schedule (default; whole levels in flight): the search stops as soon as
+      best_sse - lb <= sse_threshold, so a different visiting order may stop at a different incumbent; both are
+      optimal to within sse_threshold, which is what is asserted."""
     from fast_go_icp_b200 import driver
     P = name + "_"
-    g = driver.FastGoICP(CLOUDS[name + "_model"], CLOUDS[name + "_data"], float(G[P + "res"]), float(G[P + "mse"]))
+    g = driver.FastGoICP(CLOUDS[name + "_model"], CLOUDS[name + "_data"], float(G[P + "res"]), float(G[P + "mse"]),
+                         schedule="bestfirst")
     R, t = g.run()
     assert abs(g.best_sse - G[P + "run_sse"]) <= 1e-3 * G[P + "run_sse"]
     assert np.allclose(g.best_R, G[P + "run_Rn"], atol=3e-3) and np.allclose(g.best_t, G[P + "run_tn"], atol=3e-3)
-    assert np.allclose(t, G[P + "run_t"], atol=3e-3 / float(g.pp["scale"]) * 3)
+    assert np.allclose(t, G[P + "run_t"], atol=1e-2 / float(g.pp["scale"]))
+    g.close()
+    g = driver.FastGoICP(CLOUDS[name + "_model"], CLOUDS[name + "_data"], float(G[P + "res"]), float(G[P + "mse"]))
+    g.run()
+    assert g.best_sse <= G[P + "run_sse"] + float(G[P + "sse_threshold"])
     g.close()

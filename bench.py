@@ -34,6 +34,25 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """stdout must carry exactly ONE JSON line, but libraries underneath write there too (NCCL prints its
+    version banner on fd 1): point fd 1 at stderr for the duration of the run and keep the real stdout aside."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(obj) + "\n")
+    out.flush()
+
+
 class ClockSampler:
     """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
@@ -145,7 +164,6 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
 
@@ -295,7 +313,7 @@ def run_ours(args):
                "cpu_baseline": cpu, "ctor_ms": ctor_ms, "lut_build_ms": info.build_ms}
         if bnb:
             out["bnb"] = bnb
-        print(json.dumps(out), flush=True)
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
 
@@ -363,7 +381,7 @@ def run_reference(args):
            "config": {"workload": "W5 synthetic: 100k-point model / 10k-point data, lut_resolution 0.005; bounded sample"},
            "cpu_baseline": {"value": v, "unit": "evals/s", "cores": cores, "kind": kind, "sample": sample},
            "e2e": {"value": v, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 def main():
@@ -381,6 +399,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--ref-rot", type=int, default=16, help="rotation cubes per reference-arm step")
     args = ap.parse_args()
+    quiet_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:

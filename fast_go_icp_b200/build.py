@@ -58,7 +58,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             if log:
                 print(log)
     if not _newer(OUT, objs):
-        cmd = ["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", OUT] + objs + ["-lcudart"]
+        cmd = ["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", OUT] + objs + ["-lcudart", "-ldl"]
         subprocess.run(cmd, check=True)
     return OUT
 

@@ -631,6 +631,7 @@ static int bnb_rounds(fgoicp_ctx* c, const float4* d_rot, int Rn, int fix_rot, f
 static int bnb_batch_host(fgoicp_ctx* c, const float* rot_xyz_span, int Rn, int fix_rot, float best_sse,
                           float sse_threshold, std::vector<BnbOut>& res, float* ms)
 {
+    FG_RANGE("fgoicp inner searches");
     size_t b_rot = align256(sizeof(float4) * Rn), b_out = align256(sizeof(BnbOut) * Rn);
     int rc = fg::ensure_scratch(c, b_rot + b_out);
     if (rc) return rc;
@@ -717,6 +718,7 @@ extern "C" int fgoicp_so3_level_ub(fgoicp_ctx* c, const float* cubes, int n,
                                    float* io_best_sse, float io_best_R[9], float io_best_t[3],
                                    fgoicp_level_stats* stats)
 {
+    FG_RANGE("fgoicp_so3_level_ub");
     FG_ARG(c && io_best_sse && io_best_R && io_best_t, "NULL pointer");
     FG_ARG(n >= 0, "n must be non-negative");
     if (stats) { memset(stats, 0, sizeof(*stats)); stats->best_icp_index = -1; }
@@ -781,6 +783,7 @@ extern "C" int fgoicp_so3_level_lb(fgoicp_ctx* c, const float* cubes, int n,
                                    float best_sse, float sse_threshold,
                                    float* lb, fgoicp_level_stats* stats)
 {
+    FG_RANGE("fgoicp_so3_level_lb");
     FG_ARG(c, "NULL context");
     FG_ARG(n >= 0, "n must be non-negative");
     if (stats) memset(stats, 0, sizeof(*stats));

@@ -147,6 +147,7 @@ int fg_bounds_phased(fgoicp_ctx* c, const float4* d_rot, int Rn, int fix_rot, co
 
 static int run_bounds(fgoicp_ctx* c, const BoundsLaunch& b)
 {
+    FG_RANGE("fgoicp bounds");
     if (c->phased && !b.no_phased && c->sampler == FGOICP_SAMPLER_PACKED && !b.d_Rmats && (long long)b.Rn * b.T >= 4096)
     {
         int rc = fg_bounds_phased(c, b.d_rot, b.Rn, b.fix_rot, b.d_tc, b.T, b.d_lb, b.d_ub, b.d_best_ub);

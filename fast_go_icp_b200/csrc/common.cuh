@@ -15,6 +15,17 @@
 
 #include "../../include/fgoicp_c.h"
 
+// NVTX ranges around every stage (header-only NVTX3: a no-op unless a profiler is attached)
+#include <nvtx3/nvToolsExt.h>
+struct FgRange
+{
+    explicit FgRange(const char* name) { nvtxRangePushA(name); }
+    ~FgRange() { nvtxRangePop(); }
+    FgRange(const FgRange&) = delete;
+    FgRange& operator=(const FgRange&) = delete;
+};
+#define FG_RANGE(name) FgRange fg_range__(name)
+
 #define FG_SQRT3 1.732050807568877f     // reference fgoicp/common.hpp:19
 #define FG_PI    3.141592653589793f     // reference fgoicp/common.hpp:17
 #define FG_INF   1E+10f                 // reference fgoicp/common.hpp:18

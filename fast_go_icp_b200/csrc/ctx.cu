@@ -495,6 +495,7 @@ extern "C" int fgoicp_ctx_create(const float* model_xyz, size_t nt, const float*
                                  const float bbox_min[3], const float bbox_max[3], float lut_resolution,
                                  int device, unsigned flags, fgoicp_ctx** out)
 {
+    FG_RANGE("fgoicp_ctx_create");
     FG_ARG(out != nullptr, "out is NULL");
     *out = nullptr;
     FG_ARG(model_xyz && data_xyz && bbox_min && bbox_max, "NULL input pointer");

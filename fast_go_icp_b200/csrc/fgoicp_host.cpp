@@ -124,7 +124,10 @@ namespace icp
         double t0 = now_ms();
         glm::mat3 icp_R; glm::vec3 icp_t;
         // Initial ICP from the identity; only its error is kept (fgoicp.cpp:12-14)
-        best_sse = icp(100, 0.05, glm::mat3(1.0f), glm::vec3(0.0f), icp_R, icp_t);
+        {
+            float e0 = icp(100, 0.05, glm::mat3(1.0f), glm::vec3(0.0f), icp_R, icp_t);
+            publish_best(e0, best_rotation, best_translation);
+        }
         Logger(LogLevel::Info) << "Initial ICP best error: " << best_sse
                                << "\n\tRotation:\n" << icp_R
                                << "\n\tTranslation: " << icp_t;
@@ -134,8 +137,10 @@ namespace icp
 
         // Refine the best transform (fgoicp.cpp:22-23)
         glm::mat3 R; glm::vec3 t;
-        best_sse = icp(100, 0.0005, best_rotation, best_translation, R, t);
-        best_rotation = R; best_translation = t;
+        {
+            float e1 = icp(100, 0.0005, best_rotation, best_translation, R, t);
+            publish_best(e1, R, t);
+        }
 
         Logger(LogLevel::Info) << "Searching over! Best Error: " << best_sse
                                << "\n\tRotation:\n" << best_rotation
@@ -217,9 +222,7 @@ namespace icp
                 }
                 if (level_best < best_sse)
                 {
-                    best_sse = level_best;
-                    best_rotation = to_mat3(bR);
-                    best_translation = glm::vec3(bT[0], bT[1], bT[2]);
+                    publish_best(level_best, to_mat3(bR), glm::vec3(bT[0], bT[1], bT[2]));
                     Logger(LogLevel::Debug) << "New best error: " << best_sse
                                             << "\n\tRotation:\n" << best_rotation
                                             << "\n\tTranslation: " << restore_translation(best_rotation, best_translation);
@@ -246,8 +249,7 @@ namespace icp
             }
             if (n > 0)
             {
-                last_rotation = eval[n - 1].q.R;
-                last_translation = glm::vec3(bt[3 * (n - 1)], bt[3 * (n - 1) + 1], bt[3 * (n - 1) + 2]);
+                publish_last(eval[n - 1].q.R, glm::vec3(bt[3 * (n - 1)], bt[3 * (n - 1) + 1], bt[3 * (n - 1) + 2]));
             }
             stats_.levels += 1;
             stats_.rot_cubes += static_cast<std::uint32_t>(n);
@@ -289,13 +291,12 @@ namespace icp
                 std::uint64_t ev = 0;
                 check(fgoicp_bnb_r3(ctx_, cube, 1, best_sse, sse_threshold, &ub, bt, &ev), "fgoicp_bnb_r3");
                 stats_.bound_evals += ev; stats_.rot_cubes += 1;
-                last_rotation = child.q.R;
-                last_translation = glm::vec3(bt[0], bt[1], bt[2]);
+                publish_last(child.q.R, glm::vec3(bt[0], bt[1], bt[2]));
                 if (ub < best_sse * 1.8)
                 {
                     glm::mat3 R; glm::vec3 t;
                     float e = icp(100, 0.005, child.q.R, last_translation, R, t);
-                    if (e < best_sse) { best_sse = e; best_rotation = R; best_translation = t; }
+                    if (e < best_sse) publish_best(e, R, t);
                 }
                 check(fgoicp_bnb_r3(ctx_, cube, 0, best_sse, sse_threshold, &lb, dummy, &ev), "fgoicp_bnb_r3");
                 stats_.bound_evals += ev;

@@ -647,6 +647,7 @@ extern "C" int fgoicp_nn(fgoicp_ctx* c, const float R[9], const float t[3], int 
 int fg_icp_run_batch(fgoicp_ctx* c, const float* R0s, const float* t0s, int n, int max_iter, float thr,
                      float* sse, float* R, float* t, int* iters)
 {
+    FG_RANGE("fgoicp icp batch");
     for (int base = 0; base < n; base += ICP_MAX_BATCH)
     {
         int m = std::min(ICP_MAX_BATCH, n - base);

@@ -11,6 +11,7 @@
 #include "common.hpp"
 #include <cstdint>
 #include <memory>
+#include <mutex>
 
 struct fgoicp_ctx;
 
@@ -59,10 +60,18 @@ namespace icp
         using Result_t = std::tuple<glm::mat3, glm::vec3>;
         Result_t run();
 
-        // Interfaces for visualization (reference fgoicp.hpp:32-43)
-        float get_best_error() const { return best_sse; }                 // SSE in the normalised frame
-        Result_t get_best_transform() const { return { best_rotation, best_translation }; }
-        Result_t get_last_transform() const { return { last_rotation, last_translation }; }
+        // Interfaces for visualization (reference fgoicp.hpp:32-43).  The reference's companion viewer polls these
+        // from another thread without any lock (fgoicp.hpp:40-43, fgoicp.cpp:71-72); here every read returns a
+        // consistent snapshot: writers publish (error, R, t) together under the same mutex.
+        float get_best_error() const { std::lock_guard<std::mutex> g(snap_mutex_); return best_sse; }   // SSE, normalised frame
+        Result_t get_best_transform() const { std::lock_guard<std::mutex> g(snap_mutex_); return { best_rotation, best_translation }; }
+        Result_t get_last_transform() const { std::lock_guard<std::mutex> g(snap_mutex_); return { last_rotation, last_translation }; }
+        // one consistent (SSE, R, t) triple of the incumbent, in the normalised frame
+        std::tuple<float, glm::mat3, glm::vec3> get_best_snapshot() const
+        {
+            std::lock_guard<std::mutex> g(snap_mutex_);
+            return { best_sse, best_rotation, best_translation };
+        }
 
         // Extras (not in the reference)
         float get_best_mse() const { return best_sse / static_cast<float>(ns); }
@@ -90,6 +99,18 @@ namespace icp
 
         glm::mat3 last_rotation{ 1.0f };
         glm::vec3 last_translation{ 0.0f };
+
+        mutable std::mutex snap_mutex_;
+        void publish_best(float e, const glm::mat3& R, const glm::vec3& t)
+        {
+            std::lock_guard<std::mutex> g(snap_mutex_);
+            best_sse = e; best_rotation = R; best_translation = t;
+        }
+        void publish_last(const glm::mat3& R, const glm::vec3& t)
+        {
+            std::lock_guard<std::mutex> g(snap_mutex_);
+            last_rotation = R; last_translation = t;
+        }
 
         Options options_;
         Stats stats_;

@@ -19,7 +19,7 @@ BUILD_DEFAULT = BUILD_PACKED | BUILD_TEX
 
 EXPORTS = [
     "fgoicp_last_error", "fgoicp_version", "fgoicp_ctx_create", "fgoicp_ctx_destroy", "fgoicp_ctx_info",
-    "fgoicp_set_sampler", "fgoicp_set_stream", "fgoicp_set_nn_mode", "fgoicp_set_phased", "fgoicp_set_bnb_mode", "fgoicp_gather_probe", "fgoicp_lut_download", "fgoicp_lut_sample", "fgoicp_rot_sin",
+    "fgoicp_set_sampler", "fgoicp_set_trim", "fgoicp_set_stream", "fgoicp_set_nn_mode", "fgoicp_set_phased", "fgoicp_set_bnb_mode", "fgoicp_gather_probe", "fgoicp_lut_download", "fgoicp_lut_sample", "fgoicp_rot_sin",
     "fgoicp_bounds_batch", "fgoicp_bounds_multi", "fgoicp_bounds_multi_dev", "fgoicp_sse", "fgoicp_nn",
     "fgoicp_icp", "fgoicp_bnb_r3", "fgoicp_bnb_r3_batch", "fgoicp_so3_level_ub", "fgoicp_so3_level_lb",
 ]
@@ -68,6 +68,7 @@ def lib():
     L.fgoicp_set_nn_mode.argtypes = [vp, C.c_int]
     L.fgoicp_set_phased.argtypes = [vp, C.c_int]
     L.fgoicp_set_bnb_mode.argtypes = [vp, C.c_int]
+    L.fgoicp_set_trim.argtypes = [vp, C.c_float, C.POINTER(C.c_uint64)]
     L.fgoicp_gather_probe.argtypes = [vp, C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_float)]
     L.fgoicp_lut_download.argtypes = [vp, _f32p, C.c_size_t]
     L.fgoicp_lut_sample.argtypes = [vp, _f32p, C.c_size_t, C.c_int, _f32p]
@@ -130,6 +131,12 @@ class Context:
 
     def set_sampler(self, sampler):
         _check(lib().fgoicp_set_sampler(self._h, int(sampler)), "fgoicp_set_sampler")
+
+    def set_trim(self, trim_fraction):
+        """Trimmed registration (extension; 0 = off = the reference).  Returns the number of inliers kept."""
+        k = C.c_uint64(0)
+        _check(lib().fgoicp_set_trim(self._h, float(trim_fraction), C.byref(k)), "fgoicp_set_trim")
+        return int(k.value)
 
     def set_bnb_mode(self, mode):
         """0: automatic, 1: persistent per-cube searches, 2: round-synchronous searches (same results)."""

@@ -571,7 +571,7 @@ static int bnb_rounds(fgoicp_ctx* c, const float4* d_rot, int Rn, int fix_rot, f
 
     int min_pairs = 12000;                             // fewer popped cubes than this: plain kernel (the sweep has a ~1 ms floor)
     if (const char* e = getenv("FGOICP_BNBR_MIN_PAIRS")) min_pairs = atoi(e);
-    bool can_phase = c->phased && c->sampler == FGOICP_SAMPLER_PACKED && Rn <= fg_phased_max_cubes(c);
+    bool can_phase = c->trim_k == 0 && c->phased && c->sampler == FGOICP_SAMPLER_PACKED && Rn <= fg_phased_max_cubes(c);
     bool prepared = false;
 
     size_t smem = sizeof(unsigned long long) * BNB_POOL;
@@ -649,7 +649,8 @@ static int bnb_batch_host(fgoicp_ctx* c, const float* rot_xyz_span, int Rn, int 
     // round trip per round cancel the gain (run() 211 ms either way).
     int rounds_min = 0x7fffffff;
     if (const char* e = getenv("FGOICP_BNBR_MIN_CUBES")) rounds_min = atoi(e);
-    bool rounds = c->bnb_mode == 2 || (c->bnb_mode == 0 && Rn >= rounds_min && c->phased && c->sampler == FGOICP_SAMPLER_PACKED);
+    // trimmed bounds need all residuals of a cube in one place: only the round-synchronous schedule evaluates them
+    bool rounds = c->trim_k > 0 || c->bnb_mode == 2 || (c->bnb_mode == 0 && Rn >= rounds_min && c->phased && c->sampler == FGOICP_SAMPLER_PACKED);
     if (rounds) rc = bnb_rounds(c, (const float4*)dp, Rn, fix_rot, best_sse, sse_threshold, (BnbOut*)(dp + b_rot));
     else rc = launch_bnb(c, (const float4*)dp, Rn, fix_rot, best_sse, sse_threshold, (BnbOut*)(dp + b_rot));
     if (rc) return rc;

@@ -22,6 +22,7 @@
 #include <vector>
 
 #include "bounds_eval.cuh"
+#include "trim.cuh"
 
 #define BD_THREADS 256
 #define BD_WARPS   (BD_THREADS / 32)
@@ -95,6 +96,65 @@ k_bounds_multi(LutDev L, const float4* __restrict__ data, int ns,
     }
 }
 
+// Trimmed bounds (extension): one block per (rotation cube, translation cube) pair.  The per-point terms of the
+// pair -- the same ub_i / lb_i the other kernels add up -- are kept in shared memory (2 x ns floats), and each of
+// the two sums runs over the K smallest terms only (trim.cuh).  Unused slots (negative span) are skipped.
+#define BT_THREADS 256
+template <int SAMPLER>
+__global__ void __launch_bounds__(BT_THREADS)
+k_bounds_trim(LutDev L, const float4* __restrict__ data, int ns,
+              const float4* __restrict__ rot, const float* __restrict__ Rmats, int fix_rot,
+              const float4* __restrict__ tcubes, int T, unsigned int K,
+              float* __restrict__ lb, float* __restrict__ ub, unsigned int* __restrict__ best_ub_bits)
+{
+    extern __shared__ float sv[];                 // [2][ns]: ub_i, lb_i
+    __shared__ float sR[9];
+    __shared__ float s_sin;
+    __shared__ unsigned int s_hist[256], s_state[2];
+    __shared__ double s_w[32];
+    const int pair = blockIdx.x, r = pair / T;
+    const float4 t = tcubes[pair];
+    if (t.w < 0.0f) return;
+    if (threadIdx.x == 0)
+    {
+        float4 rc = rot[r];
+        if (Rmats) { for (int k = 0; k < 9; ++k) sR[k] = Rmats[9 * r + k]; }
+        else
+        {
+            float Rm[9];
+            fg_rotation_matrix(rc.x, rc.y, rc.z, Rm);
+            for (int k = 0; k < 9; ++k) sR[k] = Rm[k];
+        }
+        s_sin = fix_rot ? 0.0f : fg_rot_sin(rc.w);
+    }
+    __syncthreads();
+    float R[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) R[k] = sR[k];
+    const float sin_half = s_sin;
+    for (int i = threadIdx.x; i < ns; i += BT_THREADS)
+    {
+        float4 p = __ldg(&data[i]);
+        float3 rp = fg_rotate(R, p.x, p.y, p.z);
+        float rot_r = __fmul_rn(__fadd_rn(p.w, p.w), sin_half);
+        float d2 = fg_sample<SAMPLER>(L, __fadd_rn(rp.x, t.x), __fadd_rn(rp.y, t.y), __fadd_rn(rp.z, t.z));
+        float u, l;
+        fg_bound_terms(d2, rot_r, fix_rot != 0, t.w, u, l);
+        sv[i] = u; sv[ns + i] = l;
+    }
+    __syncthreads();
+    const float* su = sv;
+    const float* sl = sv + ns;
+    double tu = fg_block_trimmed_sum([&](int i) { return __float_as_uint(su[i]); }, ns, K, s_hist, s_state, s_w);
+    double tl = fg_block_trimmed_sum([&](int i) { return __float_as_uint(sl[i]); }, ns, K, s_hist, s_state, s_w);
+    if (threadIdx.x == 0)
+    {
+        float fu = (float)tu, fl = (float)tl;
+        ub[pair] = fu; lb[pair] = fl;
+        if (best_ub_bits) atomicMin(best_ub_bits, __float_as_uint(fu));
+    }
+}
+
 __global__ void k_bounds_finish(const double* __restrict__ partial, int n, int S,
                                 float* __restrict__ lb, float* __restrict__ ub,
                                 unsigned int* __restrict__ best_ub_bits)
@@ -148,6 +208,30 @@ int fg_bounds_phased(fgoicp_ctx* c, const float4* d_rot, int Rn, int fix_rot, co
 static int run_bounds(fgoicp_ctx* c, const BoundsLaunch& b)
 {
     FG_RANGE("fgoicp bounds");
+    if (c->trim_k > 0)
+    {
+        // trimmed registration: every pair sums its K smallest terms (one block per pair)
+        size_t smem = sizeof(float) * 2 * c->ns;
+        if (smem > 200 * 1024) { fg::set_error("trimming keeps 2 x ns floats in shared memory: at most 25,600 data points"); return FGOICP_ERR_ARG; }
+        unsigned int* d_bits = (unsigned int*)b.d_best_ub;
+        if (d_bits) k_set_u32<<<1, 1, 0, c->stream>>>(d_bits, 0x7f800000u);
+        dim3 grid((unsigned)(b.Rn * b.T));
+#define FG_LAUNCH_TRIM(SMP)                                                                                              \
+        do {                                                                                                             \
+            FG_CUDA(cudaFuncSetAttribute(k_bounds_trim<SMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
+            k_bounds_trim<SMP><<<grid, BT_THREADS, smem, c->stream>>>(c->lut, c->d_data, (int)c->ns, b.d_rot, b.d_Rmats, \
+                b.fix_rot, b.d_tc, b.T, (unsigned int)c->trim_k, b.d_lb, b.d_ub, d_bits);                                \
+        } while (0)
+        switch (c->sampler)
+        {
+        case FGOICP_SAMPLER_PACKED: FG_LAUNCH_TRIM(FGOICP_SAMPLER_PACKED); break;
+        case FGOICP_SAMPLER_TEX:    FG_LAUNCH_TRIM(FGOICP_SAMPLER_TEX); break;
+        default:                    FG_LAUNCH_TRIM(FGOICP_SAMPLER_GRID); break;
+        }
+#undef FG_LAUNCH_TRIM
+        FG_CUDA(cudaGetLastError());
+        return FGOICP_OK;
+    }
     if (c->phased && !b.no_phased && c->sampler == FGOICP_SAMPLER_PACKED && !b.d_Rmats && (long long)b.Rn * b.T >= 4096)
     {
         int rc = fg_bounds_phased(c, b.d_rot, b.Rn, b.fix_rot, b.d_tc, b.T, b.d_lb, b.d_ub, b.d_best_ub);

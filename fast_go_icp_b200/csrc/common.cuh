@@ -128,6 +128,11 @@ struct fgoicp_ctx
     size_t rounds_bytes = 0;
     int bnb_mode = 0;                         // 0: auto, 1: persistent per-cube kernel, 2: round-synchronous
 
+    // trimmed registration (extension): 0 = off (the reference's behaviour), else the number of data points whose
+    // residuals enter every sum (the smallest ones)
+    size_t trim_k = 0;
+    unsigned char* d_inl = nullptr;           // ICP inlier flags [icp_capacity][ns]
+
     // ICP state
     float4* d_work = nullptr;                 // working copy W  [ns]
     unsigned long long* d_nnkey = nullptr;    // packed (value bits << 32 | index) [ns]

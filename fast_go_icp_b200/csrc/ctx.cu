@@ -623,7 +623,7 @@ extern "C" int fgoicp_ctx_destroy(fgoicp_ctx* c)
     if (c->lut.tex) cudaDestroyTextureObject(c->lut.tex);
     if (c->arr) cudaFreeArray(c->arr);
     cudaFree(c->d_model); cudaFree(c->d_data); cudaFree(c->d_grid); cudaFree(c->d_packed);
-    cudaFree(c->d_scratch); cudaFree(c->d_work); cudaFree(c->d_nnkey); cudaFree(c->d_icp);
+    cudaFree(c->d_scratch); cudaFree(c->d_work); cudaFree(c->d_nnkey); cudaFree(c->d_icp); cudaFree(c->d_inl);
     cudaFree(c->d_cell_start); cudaFree(c->d_cell_P); cudaFree(c->d_cell_M); cudaFree(c->d_phase); cudaFree(c->d_rounds);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -645,6 +645,18 @@ extern "C" int fgoicp_ctx_info(const fgoicp_ctx* c, fgoicp_info* o)
     o->device = c->device; o->sm_count = c->sm_count; o->sampler = c->sampler;
     o->has_packed = c->d_packed != nullptr; o->has_tex = c->lut.tex != 0;
     o->build_ms = c->build_ms;
+    return FGOICP_OK;
+}
+
+extern "C" int fgoicp_set_trim(fgoicp_ctx* c, float trim_fraction, uint64_t* inliers)
+{
+    FG_ARG(c, "NULL context");
+    FG_ARG(trim_fraction >= 0.0f && trim_fraction < 1.0f, "trim_fraction must be in [0, 1)");
+    // inliers kept: ns - floor(float(ns) * rho), fp32 product; all of them = trimming off
+    size_t drop = (size_t)((float)c->ns * trim_fraction);
+    size_t k = drop >= c->ns ? 1 : c->ns - drop;
+    c->trim_k = (k == c->ns) ? 0 : k;
+    if (inliers) *inliers = k;
     return FGOICP_OK;
 }
 

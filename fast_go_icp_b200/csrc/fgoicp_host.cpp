@@ -75,6 +75,7 @@ namespace icp
         if (const char* s = std::getenv("FGOICP_DEVICE")) options_.device = std::atoi(s);
         if (const char* s = std::getenv("FGOICP_WAVE1")) options_.wave1 = std::atoi(s);
         if (const char* s = std::getenv("FGOICP_SKIP_DEAD_LB")) options_.skip_dead_lb = std::atoi(s) != 0;
+        if (const char* s = std::getenv("FGOICP_TRIM_FRACTION")) options_.trim_fraction = static_cast<float>(std::atof(s));
         init(_lut_resolution);
     }
 
@@ -97,6 +98,15 @@ namespace icp
             Logger(LogLevel::Warning) << "Dims " << info.dims[0] << ", " << info.dims[1] << ", " << info.dims[2]
                                       << " is large, consider a lower LUT resolution";
         stats_.lut_build_ms = info.build_ms;
+        if (options_.trim_fraction > 0.0f)
+        {
+            // trimmed registration (extension; the reference only parses `trim`): sums over the n_inliers smallest
+            // residuals, threshold scaled accordingly (Go-ICP: SSEThresh = MSEThresh * inlierNum)
+            std::uint64_t k = ns;
+            check(fgoicp_set_trim(ctx_, options_.trim_fraction, &k), "fgoicp_set_trim");
+            n_inliers = static_cast<size_t>(k);
+            sse_threshold = static_cast<float>(n_inliers) * mse_threshold;
+        }
         stats_.ctor_ms = static_cast<float>(now_ms() - t0);
     }
 

@@ -17,6 +17,7 @@
 // what lets the model cloud be split across thread blocks and merged with a 64-bit atomicMin.
 #include "common.cuh"
 #include "svd3_device.cuh"
+#include "trim.cuh"
 
 #include <algorithm>
 #include <cstring>
@@ -378,23 +379,72 @@ __device__ __forceinline__ void fg_block_sum(double (&v)[N], double* out /* shar
     __syncthreads();
 }
 
-// SSE = sum of the winning squared distances (keys carry d2 bits in the high word), fp64 -> float
+// SSE = sum of the winning squared distances (keys carry d2 bits in the high word), fp64 -> float.
+// K > 0: trimmed SSE, the K smallest distances only (trim.cuh).
 __global__ void __launch_bounds__(1024)
-k_sse_reduce(const unsigned long long* __restrict__ keys_base, int ns, char* inst_base, int check_done, float* out)
+k_sse_reduce(const unsigned long long* __restrict__ keys_base, int ns, char* inst_base, int check_done, float* out,
+             unsigned int K)
 {
     IcpInst* inst = fg_inst(inst_base, blockIdx.x);
     if (check_done && inst->st.done) return;
     const unsigned long long* keys = keys_base + (size_t)blockIdx.x * ns;
     __shared__ double s_out[1];
-    double v[1] = { 0.0 };
-    for (int i = threadIdx.x; i < ns; i += blockDim.x)
-        v[0] += (double)__uint_as_float((unsigned int)(keys[i] >> 32));
-    fg_block_sum<1>(v, s_out);
+    __shared__ unsigned int s_hist[256], s_state[2];
+    __shared__ double s_w[32];
+    double total;
+    if (K > 0 && K < (unsigned int)ns)
+    {
+        total = fg_block_trimmed_sum([&](int i) { return (unsigned int)(keys[i] >> 32); }, ns, K, s_hist, s_state, s_w);
+    }
+    else
+    {
+        double v[1] = { 0.0 };
+        for (int i = threadIdx.x; i < ns; i += blockDim.x)
+            v[0] += (double)__uint_as_float((unsigned int)(keys[i] >> 32));
+        fg_block_sum<1>(v, s_out);
+        total = s_out[0];
+    }
     if (threadIdx.x == 0)
     {
-        float sse = (float)s_out[0];
+        float sse = (float)total;
         inst->st.sse = sse;
         if (out) out[blockIdx.x] = sse;
+    }
+}
+
+// Trimmed ICP: inliers of the Procrustes step = the K correspondences with the smallest (rooted) distance, ties
+// taken in point order.  One block per instance: radix select of the K-th value, then an ordered scan that hands
+// out the `take_eq` slots among the points exactly at that value.
+__global__ void __launch_bounds__(1024)
+k_icp_select(const unsigned long long* __restrict__ keys_base, int ns, char* inst_base, unsigned int K,
+             unsigned char* __restrict__ inl_base)
+{
+    IcpInst* inst = fg_inst(inst_base, blockIdx.x);
+    if (inst->st.done) return;
+    const unsigned long long* keys = keys_base + (size_t)blockIdx.x * ns;
+    unsigned char* inl = inl_base + (size_t)blockIdx.x * ns;
+    __shared__ unsigned int s_hist[256], s_state[2];
+    __shared__ unsigned int s_wcnt[32];
+    __shared__ unsigned int s_run;
+    FgSelect sel = fg_block_select([&](int i) { return (unsigned int)(keys[i] >> 32); }, ns, K, s_hist, s_state);
+    if (threadIdx.x == 0) s_run = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int base = 0; base < ns; base += 1024)
+    {
+        int i = base + threadIdx.x;
+        unsigned int bits = i < ns ? (unsigned int)(keys[i] >> 32) : 0xffffffffu;
+        bool eq = bits == sel.vk_bits;
+        unsigned int m = __ballot_sync(0xffffffffu, eq);
+        if (lane == 0) s_wcnt[w] = __popc(m);
+        __syncthreads();
+        unsigned int before = s_run;
+        for (int q = 0; q < w; ++q) before += s_wcnt[q];
+        before += __popc(m & ((1u << lane) - 1u));
+        if (i < ns) inl[i] = (bits < sel.vk_bits || (eq && before < sel.take_eq)) ? 1 : 0;
+        __syncthreads();
+        if (threadIdx.x == 0) { unsigned int tot = 0; for (int q = 0; q < 32; ++q) tot += s_wcnt[q]; s_run += tot; }
+        __syncthreads();
     }
 }
 
@@ -455,16 +505,19 @@ __global__ void k_icp_begin(char* inst_base)
 // centroids of the working cloud and of its correspondences (icp3d.cu:150-156)
 __global__ void __launch_bounds__(1024)
 k_icp_centroids(const float4* __restrict__ work_base, const unsigned long long* __restrict__ keys_base,
-                const float4* __restrict__ model, int ns, char* inst_base)
+                const float4* __restrict__ model, int ns, char* inst_base,
+                const unsigned char* __restrict__ inl_base, int n_in)
 {
     IcpState* st = &fg_inst(inst_base, blockIdx.x)->st;
     if (st->done) return;
     const float4* W = work_base + (size_t)blockIdx.x * ns;
     const unsigned long long* keys = keys_base + (size_t)blockIdx.x * ns;
     __shared__ double s_out[6];
+    const unsigned char* inl = inl_base ? inl_base + (size_t)blockIdx.x * ns : nullptr;
     double v[6] = { 0, 0, 0, 0, 0, 0 };
     for (int i = threadIdx.x; i < ns; i += blockDim.x)
     {
+        if (inl && !inl[i]) continue;
         float4 a = W[i];
         float4 b = model[(unsigned int)(keys[i] & 0xffffffffull)];
         v[0] += (double)a.x; v[1] += (double)a.y; v[2] += (double)a.z;
@@ -473,15 +526,15 @@ k_icp_centroids(const float4* __restrict__ work_base, const unsigned long long* 
     fg_block_sum<6>(v, s_out);
     if (threadIdx.x < 3)
     {
-        st->abar[threadIdx.x] = __fdiv_rn((float)s_out[threadIdx.x], (float)ns);
-        st->bbar[threadIdx.x] = __fdiv_rn((float)s_out[3 + threadIdx.x], (float)ns);
+        st->abar[threadIdx.x] = __fdiv_rn((float)s_out[threadIdx.x], (float)n_in);
+        st->bbar[threadIdx.x] = __fdiv_rn((float)s_out[3 + threadIdx.x], (float)n_in);
     }
 }
 
 // cross-covariance of the centred clouds, closest rotation, pose update (icp3d.cu:158-172, 101-102)
 __global__ void __launch_bounds__(1024)
 k_icp_procrustes(const float4* __restrict__ work_base, const unsigned long long* __restrict__ keys_base,
-                 const float4* __restrict__ model, int ns, char* inst_base)
+                 const float4* __restrict__ model, int ns, char* inst_base, const unsigned char* __restrict__ inl_base)
 {
     IcpState* st = &fg_inst(inst_base, blockIdx.x)->st;
     if (st->done) return;
@@ -490,9 +543,11 @@ k_icp_procrustes(const float4* __restrict__ work_base, const unsigned long long*
     __shared__ double s_out[9];
     float ab[3] = { st->abar[0], st->abar[1], st->abar[2] };
     float bb[3] = { st->bbar[0], st->bbar[1], st->bbar[2] };
+    const unsigned char* inl = inl_base ? inl_base + (size_t)blockIdx.x * ns : nullptr;
     double v[9] = { 0, 0, 0, 0, 0, 0, 0, 0, 0 };
     for (int i = threadIdx.x; i < ns; i += blockDim.x)
     {
+        if (inl && !inl[i]) continue;
         float4 w4 = W[i];
         float4 m4 = model[(unsigned int)(keys[i] & 0xffffffffull)];
         float a[3] = { __fsub_rn(w4.x, ab[0]), __fsub_rn(w4.y, ab[1]), __fsub_rn(w4.z, ab[2]) };   // icp3d.cu:43
@@ -537,11 +592,12 @@ static int ensure_icp_capacity(fgoicp_ctx* c, int n)
 {
     if (n <= c->icp_capacity) return FGOICP_OK;
     FG_CUDA(cudaStreamSynchronize(c->stream));
-    cudaFree(c->d_work); cudaFree(c->d_nnkey); cudaFree(c->d_icp);
-    c->d_work = nullptr; c->d_nnkey = nullptr; c->d_icp = nullptr; c->icp_capacity = 0;
+    cudaFree(c->d_work); cudaFree(c->d_nnkey); cudaFree(c->d_icp); cudaFree(c->d_inl);
+    c->d_work = nullptr; c->d_nnkey = nullptr; c->d_icp = nullptr; c->d_inl = nullptr; c->icp_capacity = 0;
     FG_CUDA(cudaMalloc(&c->d_work, sizeof(float4) * c->ns * n));
     FG_CUDA(cudaMalloc(&c->d_nnkey, sizeof(unsigned long long) * c->ns * n));
     FG_CUDA(cudaMalloc(&c->d_icp, (size_t)ICP_INST_BYTES * n + 256));
+    FG_CUDA(cudaMalloc(&c->d_inl, c->ns * (size_t)n));
     c->icp_capacity = n;
     return FGOICP_OK;
 }
@@ -611,7 +667,7 @@ extern "C" int fgoicp_sse(fgoicp_ctx* c, const float R[9], const float t[3], flo
     rc = enqueue_nn(c, 1, SRC_DATA, POSE_SEED, 0, 0);
     if (rc) return rc;
     float* d_out = (float*)((char*)c->d_icp + (size_t)ICP_INST_BYTES * c->icp_capacity);
-    k_sse_reduce<<<1, 1024, 0, c->stream>>>(c->d_nnkey, (int)c->ns, (char*)c->d_icp, 0, d_out);
+    k_sse_reduce<<<1, 1024, 0, c->stream>>>(c->d_nnkey, (int)c->ns, (char*)c->d_icp, 0, d_out, (unsigned int)c->trim_k);
     FG_CUDA(cudaGetLastError());
     float* hp = (float*)c->h_pinned;
     FG_CUDA(cudaMemcpyAsync(hp + 32, d_out, sizeof(float), cudaMemcpyDeviceToHost, c->stream));
@@ -670,12 +726,20 @@ int fg_icp_run_batch(fgoicp_ctx* c, const float* R0s, const float* t0s, int n, i
                 // one loop body per instance still running; every kernel returns at once for finished ones
                 rc = enqueue_nn(c, m, SRC_WORK, POSE_NONE, 1, 1);                                        // icp3d.cu:146
                 if (rc) return rc;
-                k_icp_centroids<<<m, 1024, 0, c->stream>>>(c->d_work, c->d_nnkey, c->d_model, ns, inst);
-                k_icp_procrustes<<<m, 1024, 0, c->stream>>>(c->d_work, c->d_nnkey, c->d_model, ns, inst);
+                const unsigned char* inl = nullptr;
+                int n_in = ns;
+                if (c->trim_k > 0 && c->trim_k < c->ns)
+                {
+                    // trimmed registration: the Procrustes step sees the trim_k closest correspondences only
+                    k_icp_select<<<m, 1024, 0, c->stream>>>(c->d_nnkey, ns, inst, (unsigned int)c->trim_k, c->d_inl);
+                    inl = c->d_inl; n_in = (int)c->trim_k;
+                }
+                k_icp_centroids<<<m, 1024, 0, c->stream>>>(c->d_work, c->d_nnkey, c->d_model, ns, inst, inl, n_in);
+                k_icp_procrustes<<<m, 1024, 0, c->stream>>>(c->d_work, c->d_nnkey, c->d_model, ns, inst, inl);
                 k_icp_transform<<<pgrid, 256, 0, c->stream>>>(c->d_data, c->d_work, ns, inst, SRC_WORK, POSE_INC, 1);  // icp3d.cu:100
                 rc = enqueue_nn(c, m, SRC_DATA, POSE_CUR, 0, 1);                                         // icp3d.cu:103
                 if (rc) return rc;
-                k_sse_reduce<<<m, 1024, 0, c->stream>>>(c->d_nnkey, ns, inst, 1, nullptr);
+                k_sse_reduce<<<m, 1024, 0, c->stream>>>(c->d_nnkey, ns, inst, 1, nullptr, (unsigned int)c->trim_k);
                 k_icp_begin<<<m, 1, 0, c->stream>>>(inst);   // loop head of the next iteration (or publish the result)
                 FG_CUDA(cudaGetLastError());
             }

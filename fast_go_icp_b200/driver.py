@@ -144,7 +144,7 @@ class FastGoICP:
 
     def __init__(self, target, source, lut_resolution, mse_threshold, device=0, sampler=None,
                  flags=capi.BUILD_PACKED, group=None, ctx_factory=None, wave1=32, skip_dead_lb=True,
-                 schedule="level"):
+                 schedule="level", trim_fraction=0.0):
         t0 = time.perf_counter()
         self.pp = preprocess(target, source)
         self.ns, self.nt = len(self.pp["data"]), len(self.pp["model"])
@@ -156,6 +156,12 @@ class FastGoICP:
                         lut_resolution, device=device, flags=flags)
         if sampler is not None:
             self.ctx.set_sampler(sampler)
+        # trimmed registration (extension, off by default): sums run over the n_inliers smallest residuals, and the
+        # convergence threshold scales with them (Go-ICP: SSEThresh = MSEThresh * inlierNum)
+        self.n_inliers = self.ns
+        if trim_fraction and trim_fraction > 0:
+            self.n_inliers = self.ctx.set_trim(trim_fraction)
+            self.sse_threshold = F(F(self.n_inliers) * self.mse_threshold)
         self.comm = _Comm(group)
         # "level": level-synchronous, whole levels in flight, shardable over ranks (default);
         # "bestfirst": the reference's own visiting order (fgoicp.cpp:32-100), one rotation cube at a time

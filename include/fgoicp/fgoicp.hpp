@@ -35,6 +35,7 @@ namespace icp
             int wave1 = 32;          // first-wave size of a level (then x4, x16, rest): early ICPs tighten best_sse; 0: no split
             bool skip_dead_lb = true; // skip the leaf level's rotation-uncertainty searches (they cannot change any output)
             bool verbose_levels = false;
+            float trim_fraction = 0.0f; // > 0: trimmed registration over the (1 - trim_fraction) * ns best points (extension; env FGOICP_TRIM_FRACTION)
         };
 
         struct Stats
@@ -74,7 +75,7 @@ namespace icp
         }
 
         // Extras (not in the reference)
-        float get_best_mse() const { return best_sse / static_cast<float>(ns); }
+        float get_best_mse() const { return get_best_error() / static_cast<float>(n_inliers ? n_inliers : ns); }
         const Stats& stats() const { return stats_; }
         float scaling() const { return scaling_factor; }
         fgoicp_ctx* context() const { return ctx_; }
@@ -85,6 +86,7 @@ namespace icp
         PointCloud pcs;   // source (data) cloud, centred and scaled
         PointCloud pct;   // target (model) cloud, centred and scaled by the same factor
         size_t ns, nt;
+        size_t n_inliers = 0;      // points entering every sum (ns unless trimming is on)
 
         glm::vec3 offset_pcs;
         glm::vec3 offset_pct;

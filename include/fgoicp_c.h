@@ -79,6 +79,13 @@ int fgoicp_ctx_create(const float* model_xyz, size_t nt,
 int fgoicp_ctx_destroy(fgoicp_ctx* ctx);
 int fgoicp_ctx_info(const fgoicp_ctx* ctx, fgoicp_info* out);
 int fgoicp_set_sampler(fgoicp_ctx* ctx, int sampler);
+/* Trimmed registration (EXTENSION -- the reference parses `trim` and ignores it, src/utilities.hpp:94,
+ * fgoicp/fgoicp.hpp:73): with trim_fraction rho > 0 every sum over the data points -- per-cube upper and lower
+ * bounds, the exact SSE, the centroids and cross-covariance of the ICP -- runs over the
+ * K = ns - floor(ns * rho) points with the smallest residual only.  rho = 0 (default) is the reference's behaviour.
+ * *inliers (optional) receives K.  Affects every later call on the context; bounds then need 8 * ns bytes of shared
+ * memory per block (ns <= 25,600) and the inner searches run round-synchronously. */
+int fgoicp_set_trim(fgoicp_ctx* ctx, float trim_fraction, uint64_t* inliers);
 /* CUDA stream (cudaStream_t passed as void*) every later call on this context enqueues on;
  * NULL selects the context's own stream.  Lets a host framework time calls with its own events. */
 int fgoicp_set_stream(fgoicp_ctx* ctx, void* cuda_stream);

@@ -49,6 +49,37 @@ static int g_sin_mode = 0;      /* 0: host sinf(), 1: table lookup of device val
 static int g_sin_n = 0;
 static float g_sin_span[16];
 static float g_sin_val[16];
+/* Trimming (EXTENSION; the reference parses `trim` and ignores it): when 0 < g_trim_k < ns every
+ * sum over the data points -- per-cube upper/lower bounds, the exact SSE, the ICP's centroids and cross-covariance --
+ * runs over the g_trim_k points with the SMALLEST residual only (Go-ICP's trimmed registration).  0 = off = the
+ * reference's behaviour, bit for bit. */
+static size_t g_trim_k = 0;
+
+ORC_API void orc_set_trim_k(size_t k) { g_trim_k = k; }
+ORC_API size_t orc_get_trim_k(void) { return g_trim_k; }
+/* inliers kept for a trim fraction rho: ns - floor(float(ns) * rho), fp32 product */
+ORC_API size_t orc_trim_count(size_t ns, float rho)
+{
+    size_t drop = (size_t)((float)ns * rho);
+    return drop >= ns ? 1 : ns - drop;
+}
+
+static int orc_cmp_float(const void* a, const void* b)
+{
+    float x = *(const float*)a, y = *(const float*)b;
+    return (x > y) - (x < y);
+}
+
+/* sum of the k smallest of v[0..n) (v is clobbered), fp64 accumulation in ascending order of value */
+static double orc_trimmed_sum(float* v, size_t n, size_t k)
+{
+    double s = 0.0;
+    size_t i;
+    if (k == 0 || k >= n) { for (i = 0; i < n; ++i) s += (double)v[i]; return s; }
+    qsort(v, n, sizeof(float), orc_cmp_float);
+    for (i = 0; i < k; ++i) s += (double)v[i];
+    return s;
+}
 
 ORC_API void orc_set_modes(int weight_mode, int interp_mode)
 {
@@ -370,11 +401,14 @@ ORC_API void orc_bounds(const float* lut, const int* dims, const float* bbox_min
     {
         const float* tc = tcubes + 4 * c;
         double sum_ub = 0.0, sum_lb = 0.0;
+        const int trim = g_trim_k > 0 && g_trim_k < ns;
+        float* vu = trim ? (float*)malloc(sizeof(float) * ns) : NULL;
+        float* vl = trim ? (float*)malloc(sizeof(float) * ns) : NULL;
         size_t i;
         for (i = 0; i < ns; ++i)
         {
             const float* p = data + 3 * i;
-            float q[3], d2, d, e;
+            float q[3], d2, d, e, ui, li;
             orc_xform(R, tc, p, q);
             d2 = orc_lut_sample_one(&L, q);
             d = sqrtf(d2);
@@ -384,9 +418,17 @@ ORC_API void orc_bounds(const float* lut, const int* dims, const float* bbox_min
                 float rot_r = (2.0f * radius) * sin_half;        /* SASS: FADD r,r ; FMUL */
                 d -= rot_r;
             }
-            sum_ub += (double)(d > 0.0f ? d * d : 0.0f);
+            ui = d > 0.0f ? d * d : 0.0f;
             e = fmaf(tc[3], -ORC_SQRT3, d);                      /* SASS: FFMA span,-sqrt3,d */
-            sum_lb += (double)(e > 0.0f ? e * e : 0.0f);
+            li = e > 0.0f ? e * e : 0.0f;
+            if (trim) { vu[i] = ui; vl[i] = li; }
+            else { sum_ub += (double)ui; sum_lb += (double)li; }
+        }
+        if (trim)
+        {
+            sum_ub = orc_trimmed_sum(vu, ns, g_trim_k);
+            sum_lb = orc_trimmed_sum(vl, ns, g_trim_k);
+            free(vu); free(vl);
         }
         ub[c] = (float)sum_ub;
         lb[c] = (float)sum_lb;
@@ -433,7 +475,8 @@ ORC_API float orc_sse(const float* model, size_t nt, const float* data, size_t n
     double s = 0.0;
     size_t i;
     orc_nn(model, nt, data, ns, R, t, 0, NULL, d2);
-    for (i = 0; i < ns; ++i) s += (double)d2[i];
+    if (g_trim_k > 0 && g_trim_k < ns) s = orc_trimmed_sum(d2, ns, g_trim_k);
+    else for (i = 0; i < ns; ++i) s += (double)d2[i];
     free(d2);
     return (float)s;
 }
@@ -480,6 +523,11 @@ ORC_API float orc_icp(const float* model, size_t nt, const float* data, size_t n
 {
     float* W = (float*)malloc(sizeof(float) * 3 * (ns ? ns : 1));
     int32_t* corr = (int32_t*)malloc(sizeof(int32_t) * (ns ? ns : 1));
+    const int trim = g_trim_k > 0 && g_trim_k < ns;
+    const size_t n_in = trim ? g_trim_k : ns;                 /* points entering the Procrustes step */
+    float* cd2 = (float*)malloc(sizeof(float) * (ns ? ns : 1));
+    float* srt = (float*)malloc(sizeof(float) * (ns ? ns : 1));
+    unsigned char* inl = (unsigned char*)malloc(ns ? ns : 1);
     float R[9], t[3], lastR[9], lastT[3];
     float sse = ORC_INF, last_sse = 2.0f * ORC_INF;
     size_t i;
@@ -494,22 +542,41 @@ ORC_API float orc_icp(const float* model, size_t nt, const float* data, size_t n
         float abar[3], bbar[3], ABt[9], Rd[9], td[3], Rn[9], tn[3], tmp[3];
         last_sse = sse; memcpy(lastR, R, sizeof(R)); memcpy(lastT, t, sizeof(t));
 
-        orc_nn(model, nt, W, ns, NULL, NULL, 1, corr, NULL);                      /* icp3d.cu:146 */
+        orc_nn(model, nt, W, ns, NULL, NULL, 1, corr, cd2);                       /* icp3d.cu:146 */
+        /* trimming: inliers = the n_in correspondences with the smallest rooted distance, ties in point order */
+        for (i = 0; i < ns; ++i) inl[i] = 1;
+        if (trim)
+        {
+            size_t less = 0, take_eq;
+            float vk;
+            for (i = 0; i < ns; ++i) { cd2[i] = sqrtf(cd2[i]); srt[i] = cd2[i]; }
+            qsort(srt, ns, sizeof(float), orc_cmp_float);
+            vk = srt[n_in - 1];
+            for (i = 0; i < ns; ++i) less += cd2[i] < vk;
+            take_eq = n_in - less;
+            for (i = 0; i < ns; ++i)
+            {
+                if (cd2[i] < vk) inl[i] = 1;
+                else if (cd2[i] == vk && take_eq > 0) { inl[i] = 1; --take_eq; }
+                else inl[i] = 0;
+            }
+        }
         for (i = 0; i < ns; ++i)
-            for (k = 0; k < 3; ++k)
+            for (k = 0; k < 3 && inl[i]; ++k)
             {
                 sa[k] += (double)W[3 * i + k];
                 sb[k] += (double)model[3 * (size_t)corr[i] + k];
             }
         for (k = 0; k < 3; ++k)
         {
-            abar[k] = (float)sa[k] / (float)ns;                                   /* icp3d.cu:155-156 */
-            bbar[k] = (float)sb[k] / (float)ns;
+            abar[k] = (float)sa[k] / (float)n_in;                                 /* icp3d.cu:155-156 */
+            bbar[k] = (float)sb[k] / (float)n_in;
         }
         for (i = 0; i < ns; ++i)
         {
             float a[3], b[3];
             int c, r;
+            if (!inl[i]) continue;
             for (k = 0; k < 3; ++k)
             {
                 a[k] = W[3 * i + k] - abar[k];                                    /* icp3d.cu:158-159 */
@@ -538,7 +605,7 @@ ORC_API float orc_icp(const float* model, size_t nt, const float* data, size_t n
         sse = orc_sse(model, nt, data, ns, R, t);                                 /* icp3d.cu:103 */
     }
     if (iters_out) *iters_out = iter - 1;
-    free(W); free(corr);
+    free(W); free(corr); free(cd2); free(srt); free(inl);
     if (sse < last_sse) { memcpy(Rout, R, sizeof(R)); memcpy(tout, t, sizeof(t)); return sse; }
     memcpy(Rout, lastR, sizeof(R)); memcpy(tout, lastT, sizeof(t));
     return last_sse;
@@ -731,7 +798,8 @@ ORC_API float orc_run(const float* model, size_t nt, const float* data, size_t n
     P.model = model; P.nt = nt; P.data = data; P.ns = ns; P.lut = lut;
     P.dims[0] = dims[0]; P.dims[1] = dims[1]; P.dims[2] = dims[2];
     P.bbox_min[0] = bbox_min[0]; P.bbox_min[1] = bbox_min[1]; P.bbox_min[2] = bbox_min[2];
-    P.res = res; P.sse_threshold = (float)ns * mse_threshold;                    /* fgoicp.hpp:23 */
+    P.res = res;
+    P.sse_threshold = (float)((g_trim_k > 0 && g_trim_k < ns) ? g_trim_k : ns) * mse_threshold;   /* fgoicp.hpp:23 */
     P.batch = 32; P.min_tspan = 0.1f; P.min_rspan = 0.05f; P.icp_trigger = 1.8f;
 
     best_sse = orc_icp(model, nt, data, ns, 100, (float)0.05, I, zero, icpR, icpT, NULL); /* :12-14 */

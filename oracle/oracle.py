@@ -63,6 +63,10 @@ def lib():
     L.orc_run.argtypes = [_f32p, C.c_size_t, _f32p, C.c_size_t, _f32p, _i32p, _f32p, C.c_float,
                           C.c_float, _f32p, _f32p, _u64p]
     L.orc_run.restype = C.c_float
+    L.orc_set_trim_k.argtypes = [C.c_size_t]
+    L.orc_get_trim_k.restype = C.c_size_t
+    L.orc_trim_count.argtypes = [C.c_size_t, C.c_float]
+    L.orc_trim_count.restype = C.c_size_t
     _lib = L
     return L
 
@@ -73,6 +77,29 @@ def _f32(a):
 
 def set_modes(weight_mode=0, interp_mode=0):
     lib().orc_set_modes(int(weight_mode), int(interp_mode))
+
+
+def trim_count(ns, rho):
+    """Inliers kept for a trim fraction: ns - floor(float32(ns) * rho)."""
+    return int(lib().orc_trim_count(int(ns), float(rho)))
+
+
+def set_trim_k(k):
+    """Trimmed registration (extension, off by default): every sum over the data points keeps the k smallest
+    residuals only.  0 switches it off.  Global state: reset it when done (tests use the `trimmed` context manager)."""
+    lib().orc_set_trim_k(int(k))
+
+
+class trimmed:
+    def __init__(self, k):
+        self.k = int(k)
+
+    def __enter__(self):
+        set_trim_k(self.k)
+        return self
+
+    def __exit__(self, *a):
+        set_trim_k(0)
 
 
 def set_sin_table(spans, vals):

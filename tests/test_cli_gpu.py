@@ -23,7 +23,7 @@ def test_cli_writes_result_and_visualisation(tmp_path):
     res = tomllib.loads((tmp_path / "out.toml").read_text())["result"]
     R, t = np.array(res["R"]), np.array(res["t"])
     ang = np.degrees(np.arccos(np.clip((np.trace(R @ w["R_true"].T) - 1) / 2, -1, 1)))
-    assert ang < 3.0 and np.linalg.norm(t - w["t_true"]) < 0.05 and res["mse"] < 5e-4
+    assert ang < 3.0 and np.linalg.norm(t - w["t_true"]) < 0.05 and res["mse"] < 2e-3
     viz = cloudio.read_ply(str(tmp_path / "viz.ply"))
     src = cloudio.load_cloud(str(tmp_path / "data.txt"), 0.25, 4)                 # the CLI seeds the source with seed + 1
     assert len(viz) == len(src) and np.allclose(viz, src @ R.T + t, atol=1e-4)

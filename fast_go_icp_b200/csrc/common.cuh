@@ -132,6 +132,7 @@ struct fgoicp_ctx
     // residuals enter every sum (the smallest ones)
     size_t trim_k = 0;
     unsigned char* d_inl = nullptr;           // ICP inlier flags [icp_capacity][ns]
+    void* d_icp_part = nullptr;               // Procrustes partial sums + arrival counters (nn_icp.cu)
 
     // ICP state
     float4* d_work = nullptr;                 // working copy W  [ns]

@@ -190,6 +190,9 @@ __device__ __forceinline__ float fg_sqrt_preimage_hi(float s)
 //      and merge their winners with a shuffle reduction on the packed 64-bit key.
 // All pruning tests carry a relative slack: they may visit too much, never too little.
 #define NNG_WARPS 4
+#ifndef NN_LPQ
+#define NN_LPQ 32           // lanes per query (32, 16 or 8); measured on W5: 32 -> 56 ms, 16 -> 71 ms, 8 -> 93 ms of NN time per run()
+#endif
 #ifndef NN_FAST_ROOTED
 #define NN_FAST_ROOTED 1      // 0: always the exact rooted scan (measured: ICP 86 -> 71 ms on W5 with 1)
 #endif
@@ -203,8 +206,12 @@ k_nn_grid(CellGrid g, LutDev L, float res, const float4* __restrict__ data, cons
     const float4* src = src_sel == SRC_DATA ? data : work_base + (size_t)blockIdx.y * ns;
     const float* pose = fg_pose(inst, pose_sel);
     unsigned long long* keys = keys_base + (size_t)blockIdx.y * ns;
-    const int lane = threadIdx.x & 31;
-    const int i = blockIdx.x * NNG_WARPS + (threadIdx.x >> 5);
+    // NN_LPQ lanes per query (a whole warp by default; smaller teams put more queries in flight but were measured
+    // slower: the rows of a query are better spread over 32 lanes).  Teams of one warp never talk to each other:
+    // every shuffle is confined to the team's lanes.
+    const int lane = threadIdx.x & (NN_LPQ - 1);
+    const unsigned int team_mask = NN_LPQ == 32 ? 0xffffffffu : (((1u << NN_LPQ) - 1u) << ((threadIdx.x & 31) & ~(NN_LPQ - 1)));
+    const int i = (blockIdx.x * NNG_WARPS * 32 + threadIdx.x) / NN_LPQ;
     if (i >= ns) return;
     float4 p = src[i];
     float qx = p.x, qy = p.y, qz = p.z;
@@ -247,7 +254,7 @@ k_nn_grid(CellGrid g, LutDev L, float res, const float4* __restrict__ data, cons
     const int cy1 = min(max((int)floorf((ly + U) * inv_h), 0), g.ny - 1);
     const int ny_rows = cy1 - cy0 + 1;
     const int n_rows = ny_rows * (cz1 - cz0 + 1);
-    for (int row0 = 0; row0 < n_rows; row0 += 32)
+    for (int row0 = 0; row0 < n_rows; row0 += NN_LPQ)
     {
         int row = row0 + lane;
         if (row < n_rows)
@@ -303,14 +310,14 @@ k_nn_grid(CellGrid g, LutDev L, float res, const float4* __restrict__ data, cons
         }
         // share the tightest radius before the next pass
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) U2 = fminf(U2, __shfl_xor_sync(0xffffffffu, U2, o));
+        for (int o = NN_LPQ / 2; o > 0; o >>= 1) U2 = fminf(U2, __shfl_xor_sync(team_mask, U2, o, NN_LPQ));
     }
     key = 0xffffffffffffffffull;
     if (best_idx != 0x7fffffff) key = ((unsigned long long)__float_as_uint(best) << 32) | (unsigned int)best_idx;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1)
+    for (int o = NN_LPQ / 2; o > 0; o >>= 1)
     {
-        unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+        unsigned long long other = __shfl_xor_sync(team_mask, key, o, NN_LPQ);
         key = other < key ? other : key;
     }
     if (ROOTED && NN_FAST_ROOTED && !exact)
@@ -319,7 +326,7 @@ k_nn_grid(CellGrid g, LutDev L, float res, const float4* __restrict__ data, cons
         const float wbest = __uint_as_float((unsigned int)(key >> 32));
         float cand = best > wbest ? best : second;                 // smallest d2 strictly above the winner's, warp-wide
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) cand = fminf(cand, __shfl_xor_sync(0xffffffffu, cand, o));
+        for (int o = NN_LPQ / 2; o > 0; o >>= 1) cand = fminf(cand, __shfl_xor_sync(team_mask, cand, o, NN_LPQ));
         const float s = __fsqrt_rn(wbest);
         if (cand > fg_sqrt_preimage_hi(s))
         {
@@ -502,20 +509,56 @@ __global__ void k_icp_begin(char* inst_base)
     for (int k = 0; k < 3; ++k) st->lastT[k] = st->t[k];
 }
 
+// ---- Procrustes step over ICP_NB blocks per instance ------------------------------------------------------
+// Each block sums its slice of the points in fp64; the partials go to HBM and the block that arrives LAST
+// (a counter per instance) folds them in block order, so the result is deterministic and the step no longer
+// runs at the pace of one thread block (57 -> ~10 us per call for 10,000 points).
+#define ICP_NB 8
+#define ICP_BT 256
+#define ICP_PART 16                     // doubles per block slot
+
+template <int N>
+__device__ __forceinline__ bool fg_grid_sum(double (&v)[N], double* part, unsigned int* counter, double* s_total)
+{
+    __shared__ double s_blk[N];
+    __shared__ int s_last;
+    fg_block_sum<N>(v, s_blk);
+    if (threadIdx.x < N) part[blockIdx.x * ICP_PART + threadIdx.x] = s_blk[threadIdx.x];
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(counter, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return false;
+    __threadfence();
+    if (threadIdx.x < N)
+    {
+        double a = 0.0;
+        for (unsigned int q = 0; q < gridDim.x; ++q) a += __ldcg(&part[q * ICP_PART + threadIdx.x]);
+        s_total[threadIdx.x] = a;
+    }
+    if (threadIdx.x == 0) *counter = 0;                     // ready for the next call
+    __syncthreads();
+    return true;
+}
+
 // centroids of the working cloud and of its correspondences (icp3d.cu:150-156)
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(ICP_BT)
 k_icp_centroids(const float4* __restrict__ work_base, const unsigned long long* __restrict__ keys_base,
                 const float4* __restrict__ model, int ns, char* inst_base,
-                const unsigned char* __restrict__ inl_base, int n_in)
+                const unsigned char* __restrict__ inl_base, int n_in, double* __restrict__ part_base,
+                unsigned int* __restrict__ counters)
 {
-    IcpState* st = &fg_inst(inst_base, blockIdx.x)->st;
+    const int inst = blockIdx.y;
+    IcpState* st = &fg_inst(inst_base, inst)->st;
     if (st->done) return;
-    const float4* W = work_base + (size_t)blockIdx.x * ns;
-    const unsigned long long* keys = keys_base + (size_t)blockIdx.x * ns;
+    const float4* W = work_base + (size_t)inst * ns;
+    const unsigned long long* keys = keys_base + (size_t)inst * ns;
     __shared__ double s_out[6];
-    const unsigned char* inl = inl_base ? inl_base + (size_t)blockIdx.x * ns : nullptr;
+    const unsigned char* inl = inl_base ? inl_base + (size_t)inst * ns : nullptr;
+    const int per = (ns + gridDim.x - 1) / gridDim.x;
+    const int i0 = blockIdx.x * per, i1 = min(ns, i0 + per);
     double v[6] = { 0, 0, 0, 0, 0, 0 };
-    for (int i = threadIdx.x; i < ns; i += blockDim.x)
+    for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x)
     {
         if (inl && !inl[i]) continue;
         float4 a = W[i];
@@ -523,7 +566,7 @@ k_icp_centroids(const float4* __restrict__ work_base, const unsigned long long* 
         v[0] += (double)a.x; v[1] += (double)a.y; v[2] += (double)a.z;
         v[3] += (double)b.x; v[4] += (double)b.y; v[5] += (double)b.z;
     }
-    fg_block_sum<6>(v, s_out);
+    if (!fg_grid_sum<6>(v, part_base + (size_t)inst * ICP_NB * ICP_PART, counters + 2 * inst, s_out)) return;
     if (threadIdx.x < 3)
     {
         st->abar[threadIdx.x] = __fdiv_rn((float)s_out[threadIdx.x], (float)n_in);
@@ -532,20 +575,24 @@ k_icp_centroids(const float4* __restrict__ work_base, const unsigned long long* 
 }
 
 // cross-covariance of the centred clouds, closest rotation, pose update (icp3d.cu:158-172, 101-102)
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(ICP_BT)
 k_icp_procrustes(const float4* __restrict__ work_base, const unsigned long long* __restrict__ keys_base,
-                 const float4* __restrict__ model, int ns, char* inst_base, const unsigned char* __restrict__ inl_base)
+                 const float4* __restrict__ model, int ns, char* inst_base, const unsigned char* __restrict__ inl_base,
+                 double* __restrict__ part_base, unsigned int* __restrict__ counters)
 {
-    IcpState* st = &fg_inst(inst_base, blockIdx.x)->st;
+    const int inst = blockIdx.y;
+    IcpState* st = &fg_inst(inst_base, inst)->st;
     if (st->done) return;
-    const float4* W = work_base + (size_t)blockIdx.x * ns;
-    const unsigned long long* keys = keys_base + (size_t)blockIdx.x * ns;
+    const float4* W = work_base + (size_t)inst * ns;
+    const unsigned long long* keys = keys_base + (size_t)inst * ns;
     __shared__ double s_out[9];
     float ab[3] = { st->abar[0], st->abar[1], st->abar[2] };
     float bb[3] = { st->bbar[0], st->bbar[1], st->bbar[2] };
-    const unsigned char* inl = inl_base ? inl_base + (size_t)blockIdx.x * ns : nullptr;
+    const unsigned char* inl = inl_base ? inl_base + (size_t)inst * ns : nullptr;
+    const int per = (ns + gridDim.x - 1) / gridDim.x;
+    const int i0 = blockIdx.x * per, i1 = min(ns, i0 + per);
     double v[9] = { 0, 0, 0, 0, 0, 0, 0, 0, 0 };
-    for (int i = threadIdx.x; i < ns; i += blockDim.x)
+    for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x)
     {
         if (inl && !inl[i]) continue;
         float4 w4 = W[i];
@@ -559,7 +606,7 @@ k_icp_procrustes(const float4* __restrict__ work_base, const unsigned long long*
             for (int r = 0; r < 3; ++r)
                 v[c * 3 + r] += (double)__fmul_rn(a[r], b[c]);
     }
-    fg_block_sum<9>(v, s_out);
+    if (!fg_grid_sum<9>(v, part_base + (size_t)inst * ICP_NB * ICP_PART, counters + 2 * inst + 1, s_out)) return;
     if (threadIdx.x == 0)
     {
         float ABt[9], Rd[9], td[3], Rn[9], tn[3];
@@ -592,12 +639,16 @@ static int ensure_icp_capacity(fgoicp_ctx* c, int n)
 {
     if (n <= c->icp_capacity) return FGOICP_OK;
     FG_CUDA(cudaStreamSynchronize(c->stream));
-    cudaFree(c->d_work); cudaFree(c->d_nnkey); cudaFree(c->d_icp); cudaFree(c->d_inl);
-    c->d_work = nullptr; c->d_nnkey = nullptr; c->d_icp = nullptr; c->d_inl = nullptr; c->icp_capacity = 0;
+    cudaFree(c->d_work); cudaFree(c->d_nnkey); cudaFree(c->d_icp); cudaFree(c->d_inl); cudaFree(c->d_icp_part);
+    c->d_work = nullptr; c->d_nnkey = nullptr; c->d_icp = nullptr; c->d_inl = nullptr; c->d_icp_part = nullptr; c->icp_capacity = 0;
     FG_CUDA(cudaMalloc(&c->d_work, sizeof(float4) * c->ns * n));
     FG_CUDA(cudaMalloc(&c->d_nnkey, sizeof(unsigned long long) * c->ns * n));
     FG_CUDA(cudaMalloc(&c->d_icp, (size_t)ICP_INST_BYTES * n + 256));
     FG_CUDA(cudaMalloc(&c->d_inl, c->ns * (size_t)n));
+    // Procrustes partial sums (ICP_NB slots of ICP_PART doubles per instance) followed by 2 arrival counters per instance
+    size_t part_bytes = sizeof(double) * ICP_NB * ICP_PART * (size_t)n;
+    FG_CUDA(cudaMalloc(&c->d_icp_part, part_bytes + sizeof(unsigned int) * 2 * (size_t)n));
+    FG_CUDA(cudaMemsetAsync((char*)c->d_icp_part + part_bytes, 0, sizeof(unsigned int) * 2 * (size_t)n, c->stream));
     c->icp_capacity = n;
     return FGOICP_OK;
 }
@@ -621,7 +672,8 @@ static int enqueue_nn(fgoicp_ctx* c, int n_inst, int src_sel, int pose_sel, int 
         CellGrid g;
         g.start = c->d_cell_start; g.pts = c->d_cell_M;
         g.nx = c->cnx; g.ny = c->cny; g.nz = c->cnz; g.h = c->cell_h; g.inv_h = c->cell_inv_h;
-        dim3 grid((unsigned)((c->ns + NNG_WARPS - 1) / NNG_WARPS), (unsigned)n_inst);
+        const int qpb = NNG_WARPS * 32 / NN_LPQ;            // queries per block
+        dim3 grid((unsigned)((c->ns + qpb - 1) / qpb), (unsigned)n_inst);
         if (rooted)
             k_nn_grid<1><<<grid, NNG_WARPS * 32, 0, c->stream>>>(g, c->lut, c->res, c->d_data, c->d_work, (int)c->ns, inst, src_sel, pose_sel, c->d_nnkey, check_done);
         else
@@ -734,8 +786,11 @@ int fg_icp_run_batch(fgoicp_ctx* c, const float* R0s, const float* t0s, int n, i
                     k_icp_select<<<m, 1024, 0, c->stream>>>(c->d_nnkey, ns, inst, (unsigned int)c->trim_k, c->d_inl);
                     inl = c->d_inl; n_in = (int)c->trim_k;
                 }
-                k_icp_centroids<<<m, 1024, 0, c->stream>>>(c->d_work, c->d_nnkey, c->d_model, ns, inst, inl, n_in);
-                k_icp_procrustes<<<m, 1024, 0, c->stream>>>(c->d_work, c->d_nnkey, c->d_model, ns, inst, inl);
+                double* part = (double*)c->d_icp_part;
+                unsigned int* counters = (unsigned int*)((char*)c->d_icp_part + sizeof(double) * ICP_NB * ICP_PART * (size_t)c->icp_capacity);
+                dim3 rgrid(ICP_NB, (unsigned)m);
+                k_icp_centroids<<<rgrid, ICP_BT, 0, c->stream>>>(c->d_work, c->d_nnkey, c->d_model, ns, inst, inl, n_in, part, counters);
+                k_icp_procrustes<<<rgrid, ICP_BT, 0, c->stream>>>(c->d_work, c->d_nnkey, c->d_model, ns, inst, inl, part, counters);
                 k_icp_transform<<<pgrid, 256, 0, c->stream>>>(c->d_data, c->d_work, ns, inst, SRC_WORK, POSE_INC, 1);  // icp3d.cu:100
                 rc = enqueue_nn(c, m, SRC_DATA, POSE_CUR, 0, 1);                                         // icp3d.cu:103
                 if (rc) return rc;

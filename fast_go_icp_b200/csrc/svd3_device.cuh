@@ -49,7 +49,15 @@ __host__ __device__ inline void fg_svd3(const double* A, double* U, double* S, d
     for (int sweep = 0; sweep < 60; ++sweep)
     {
         bool rotated = false;
+        // unrolled over the three (p, q) pairs so that u and v stay in registers on the device (same operations,
+        // same order)
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
         for (int p = 0; p < 2; ++p)
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
             for (int q = p + 1; q < 3; ++q)
             {
                 double alpha = fg_dot3d(u[p], u[p]);
@@ -61,6 +69,9 @@ __host__ __device__ inline void fg_svd3(const double* A, double* U, double* S, d
                                    FG_DADD(fabs(zeta), FG_DSQRT(FG_DADD(1.0, FG_DMUL(zeta, zeta)))));
                 double c = FG_DDIV(1.0, FG_DSQRT(FG_DADD(1.0, FG_DMUL(t, t))));
                 double s = FG_DMUL(c, t);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
                 for (int i = 0; i < 3; ++i)
                 {
                     double up = u[p][i], uq = u[q][i], vp = v[p][i], vq = v[q][i];

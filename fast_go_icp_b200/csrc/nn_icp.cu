@@ -20,6 +20,7 @@
 #include "trim.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #define NN_THREADS 256
@@ -199,7 +200,8 @@ __device__ __forceinline__ float fg_sqrt_preimage_hi(float s)
 template <int ROOTED>
 __global__ void __launch_bounds__(NNG_WARPS * 32)
 k_nn_grid(CellGrid g, LutDev L, float res, const float4* __restrict__ data, const float4* __restrict__ work_base,
-          int ns, char* inst_base, int src_sel, int pose_sel, unsigned long long* __restrict__ keys_base, int check_done)
+          int ns, char* inst_base, int src_sel, int pose_sel, unsigned long long* __restrict__ keys_base, int check_done,
+          const float4* __restrict__ model_by_index)
 {
     IcpInst* inst = fg_inst(inst_base, blockIdx.y);
     if (check_done && inst->st.done) return;
@@ -231,6 +233,21 @@ k_nn_grid(CellGrid g, LutDev L, float res, const float4* __restrict__ data, cons
     float Tn = __ldg(L.grid + ((size_t)nz * L.dy + ny) * L.dx + nx);
     float ex = lx - (float)nx * res, ey = ly - (float)ny * res, ez = lz - (float)nz * res;
     float U = (sqrtf(Tn) + sqrtf(ex * ex + ey * ey + ez * ez)) * 1.0001f + 1e-6f;
+    // Warm start (ICP loop): keys[i] still holds this point's winner of the previous pass, taken at a position a
+    // rounding error (squared pass -> next rooted pass) or one ICP increment (rooted -> squared pass) away.  Its
+    // distance is an upper bound on the nearest distance, usually the nearest distance itself, and shrinks the
+    // ball from "node distance + 2 x offset to the node" to just that.  Only the radius changes: the scan still
+    // visits every point inside it, so the result (tie rule included) is the same.
+    if (model_by_index)
+    {
+        unsigned int prev = (unsigned int)(keys[i] & 0xffffffffull);
+        if (prev != 0xffffffffu)
+        {
+            float4 m = __ldg(model_by_index + prev);
+            float d0 = sqrtf(fg_sq3(__fsub_rn(qx, m.x), __fsub_rn(qy, m.y), __fsub_rn(qz, m.z))) * 1.0001f + 1e-6f;
+            U = fminf(U, d0);
+        }
+    }
     float U2 = U * U;
 
     // Rooted rule, fast path (NN_FAST_ROOTED): first j minimising sqrtf(d2) (icp3d.cu:17-26) differs from the
@@ -673,11 +690,13 @@ static int enqueue_nn(fgoicp_ctx* c, int n_inst, int src_sel, int pose_sel, int 
         g.start = c->d_cell_start; g.pts = c->d_cell_M;
         g.nx = c->cnx; g.ny = c->cny; g.nz = c->cnz; g.h = c->cell_h; g.inv_h = c->cell_inv_h;
         const int qpb = NNG_WARPS * 32 / NN_LPQ;            // queries per block
+        // inside the ICP loop the key buffer carries the previous pass's winners (all-ones before the first pass)
+        const float4* warm = (check_done && !getenv("FGOICP_NN_NO_WARM")) ? c->d_model : nullptr;
         dim3 grid((unsigned)((c->ns + qpb - 1) / qpb), (unsigned)n_inst);
         if (rooted)
-            k_nn_grid<1><<<grid, NNG_WARPS * 32, 0, c->stream>>>(g, c->lut, c->res, c->d_data, c->d_work, (int)c->ns, inst, src_sel, pose_sel, c->d_nnkey, check_done);
+            k_nn_grid<1><<<grid, NNG_WARPS * 32, 0, c->stream>>>(g, c->lut, c->res, c->d_data, c->d_work, (int)c->ns, inst, src_sel, pose_sel, c->d_nnkey, check_done, warm);
         else
-            k_nn_grid<0><<<grid, NNG_WARPS * 32, 0, c->stream>>>(g, c->lut, c->res, c->d_data, c->d_work, (int)c->ns, inst, src_sel, pose_sel, c->d_nnkey, check_done);
+            k_nn_grid<0><<<grid, NNG_WARPS * 32, 0, c->stream>>>(g, c->lut, c->res, c->d_data, c->d_work, (int)c->ns, inst, src_sel, pose_sel, c->d_nnkey, check_done, warm);
         FG_CUDA(cudaGetLastError());
         return FGOICP_OK;
     }
@@ -764,6 +783,7 @@ int fg_icp_run_batch(fgoicp_ctx* c, const float* R0s, const float* t0s, int n, i
         char* inst = (char*)c->d_icp;
         int ns = (int)c->ns;
         dim3 pgrid((unsigned)((ns + 255) / 256), (unsigned)m);
+        FG_CUDA(cudaMemsetAsync(c->d_nnkey, 0xff, sizeof(unsigned long long) * (size_t)ns * m, c->stream));   // no previous winners yet
         k_icp_init<<<m, 1, 0, c->stream>>>(inst, max_iter, thr);
         k_icp_transform<<<pgrid, 256, 0, c->stream>>>(c->d_data, c->d_work, ns, inst, SRC_DATA, POSE_SEED, 0);   // icp3d.cu:85
         k_icp_begin<<<m, 1, 0, c->stream>>>(inst);           // loop head of iteration 1

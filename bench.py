@@ -274,19 +274,33 @@ def run_ours(args):
         gw = driver.FastGoICP(ws["model"], ws["data"], 0.03, MSE_THR, device=local, flags=capi.BUILD_PACKED)
         gw.run()
         gw.close()
-        g = driver.FastGoICP(w["model"], w["data"], RES, MSE_THR, device=local, flags=capi.BUILD_PACKED,
-                             wave1=args.wave1, skip_dead_lb=not args.keep_dead_lb)
-        barrier()
-        R, t = g.run()
-        barrier()
-        st = g.stats
-        err_R = float(np.degrees(np.arccos(np.clip((np.trace(R @ w["R_true"].T) - 1) / 2, -1, 1))))
-        bnb = {"bnb_ms": st["run_ms"], "ctor_ms": st["ctor_ms"], "lut_build_ms": st["lut_build_ms"],
-               "best_mse": float(g.best_sse) / NS, "rot_err_deg": err_R,
-               "t_err": float(np.linalg.norm(t - w["t_true"])), "rot_cubes_local": st["rot_cubes"],
-               "bound_evals_local": st["bound_evals"], "icp_runs_local": st["icp_runs"],
-               "ms_bnb_ub": st["ms_bnb_ub"], "ms_icp": st["ms_icp"], "ms_bnb_lb": st["ms_bnb_lb"],
-               "levels": st["level_log"]}
+        # three runs on fresh contexts; the reported one is the MEDIAN by wall time (all three are listed): run() is a
+        # chain of ~300 host round trips and a single descheduling of the host thread shows up as tens of ms
+        runs = []
+        for rep in range(3):
+            g = driver.FastGoICP(w["model"], w["data"], RES, MSE_THR, device=local, flags=capi.BUILD_PACKED,
+                                 wave1=args.wave1, skip_dead_lb=not args.keep_dead_lb)
+            barrier()
+            R, t = g.run()
+            barrier()
+            st = g.stats
+            run_ms = st["run_ms"]
+            if world > 1:
+                tr = torch.tensor([run_ms], device=dev)
+                dist.all_reduce(tr, op=dist.ReduceOp.MAX)
+                run_ms = float(tr.item())
+            err_R = float(np.degrees(np.arccos(np.clip((np.trace(R @ w["R_true"].T) - 1) / 2, -1, 1))))
+            runs.append({"bnb_ms": run_ms, "ctor_ms": st["ctor_ms"], "lut_build_ms": st["lut_build_ms"],
+                         "best_mse": float(g.best_sse) / NS, "rot_err_deg": err_R,
+                         "t_err": float(np.linalg.norm(t - w["t_true"])), "rot_cubes_local": st["rot_cubes"],
+                         "bound_evals_local": st["bound_evals"], "icp_runs_local": st["icp_runs"],
+                         "ms_bnb_ub": st["ms_bnb_ub"], "ms_icp": st["ms_icp"], "ms_bnb_lb": st["ms_bnb_lb"],
+                         "levels": st["level_log"]})
+            if rep < 2:
+                g.close()
+        order = sorted(range(3), key=lambda k: runs[k]["bnb_ms"])
+        bnb = dict(runs[order[1]])
+        bnb["bnb_ms_all_runs"] = [runs[k]["bnb_ms"] for k in range(3)]
         if rank == 0 and world == 1 and not args.no_cpu:
             lut, dims = g.ctx.lut_download()
             pp["lut"], pp["dims"] = lut, dims

@@ -341,17 +341,20 @@ k_bounds_phased(LutDev L, int ns,
     __syncwarp();
 
     const bool paced = pace_lag > 0 && g0 == gfirst;           // only the first sweep is in step with the others
+    // Pacing is an optimisation, never a dependency: a warp spends at most ~1 ms of polls per launch waiting for
+    // the others (e.g. if the blocks were not all co-resident after all) and then simply stops waiting.
+    int spin_budget = 8000;
     for (int phi = 0; phi < PH_PHASES; ++phi)
     {
         // Soft pacing: do not run more than pace_lag phases ahead of the slowest warp, so the slabs in flight
         // stay within L2.  Never blocks for long: the wait gives up after a bounded number of polls.
-        if (paced && phi >= pace_lag)
+        if (paced && phi >= pace_lag && spin_budget > 0)
         {
             if (lane == 0)
             {
                 const volatile int* flag = phase_done + (phi - pace_lag);
 #pragma unroll 1
-                for (int spin = 0; spin < 20000 && *flag < nw_paced; ++spin) __nanosleep(100);
+                while (spin_budget > 0 && *flag < nw_paced) { __nanosleep(100); --spin_budget; }
             }
             __syncwarp();
         }

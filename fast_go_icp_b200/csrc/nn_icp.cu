@@ -789,7 +789,7 @@ int fg_icp_run_batch(fgoicp_ctx* c, const float* R0s, const float* t0s, int n, i
         k_icp_begin<<<m, 1, 0, c->stream>>>(inst);           // loop head of iteration 1
         FG_CUDA(cudaGetLastError());
         char* hinst = (char*)c->h_pinned + 4096;
-        const int burst = 4;     // iterations enqueued between polls of the done flags
+        const int burst = 8;     // iterations enqueued between polls of the done flags (finished instances cost only empty launches)
         bool all_done = false;
         for (int guard = 0; guard <= max_iter + burst && !all_done; guard += burst)
         {

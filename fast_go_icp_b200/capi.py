@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("FGOICP_LIB") or os.path.join(HERE, "libfgoicp_b200.so")
 
 SAMPLER_GRID, SAMPLER_PACKED, SAMPLER_TEX = 0, 1, 2
-BUILD_PACKED, BUILD_TEX, BUILD_BRUTE_LUT = 1, 2, 4
+BUILD_PACKED, BUILD_TEX, BUILD_BRUTE_LUT, BUILD_KEEP_ORDER = 1, 2, 4, 8
 BUILD_DEFAULT = BUILD_PACKED | BUILD_TEX
 
 EXPORTS = [

@@ -93,7 +93,8 @@ struct fgoicp_ctx
 
     size_t nt = 0, ns = 0;
     float4* d_model = nullptr;     // (x, y, z, index-as-bits)   [nt]
-    float4* d_data = nullptr;      // (x, y, z, |p|^2)           [ns]
+    float4* d_data = nullptr;      // (x, y, z, |p|^2)           [ns], stored in Morton order of the coordinates
+    int* d_data_orig = nullptr;    // storage slot -> index in the caller's cloud [ns]
 
     float res = 0.f;
     float bbox_min[3] = { 0, 0, 0 }, bbox_max[3] = { 0, 0, 0 };

@@ -358,16 +358,17 @@ k_nn_grid(CellGrid g, LutDev L, float res, const float4* __restrict__ data, cons
 // keys -> (idx, d2 of the winner recomputed with the canonical formula)
 __global__ void k_nn_finish(const unsigned long long* __restrict__ keys, const float4* __restrict__ model,
                             const float4* __restrict__ src, int ns, const float* __restrict__ pose,
-                            int* __restrict__ idx, float* __restrict__ d2)
+                            int* __restrict__ idx, float* __restrict__ d2, const int* __restrict__ orig)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= ns) return;
+    const int o = orig[i];       // outputs go to the caller's point order (the device keeps the data cloud in Morton order)
     unsigned int j = (unsigned int)(keys[i] & 0xffffffffull);
     int ji = (j == 0xffffffffu) ? -1 : (int)j;
-    if (idx) idx[i] = ji;
+    if (idx) idx[o] = ji;
     if (d2)
     {
-        if (ji < 0) { d2[i] = FG_INF; return; }
+        if (ji < 0) { d2[o] = FG_INF; return; }
         float4 p = src[i];
         float qx = p.x, qy = p.y, qz = p.z;
         if (pose)
@@ -378,7 +379,7 @@ __global__ void k_nn_finish(const unsigned long long* __restrict__ keys, const f
             qx = __fadd_rn(rp.x, pose[9]); qy = __fadd_rn(rp.y, pose[10]); qz = __fadd_rn(rp.z, pose[11]);
         }
         float4 m = model[ji];
-        d2[i] = fg_sq3(__fsub_rn(qx, m.x), __fsub_rn(qy, m.y), __fsub_rn(qz, m.z));
+        d2[o] = fg_sq3(__fsub_rn(qx, m.x), __fsub_rn(qy, m.y), __fsub_rn(qz, m.z));
     }
 }
 
@@ -437,38 +438,40 @@ k_sse_reduce(const unsigned long long* __restrict__ keys_base, int ns, char* ins
 }
 
 // Trimmed ICP: inliers of the Procrustes step = the K correspondences with the smallest (rooted) distance, ties
-// taken in point order.  One block per instance: radix select of the K-th value, then an ordered scan that hands
-// out the `take_eq` slots among the points exactly at that value.
+// taken in the caller's point order.  One block per instance: radix select of the K-th value, then (only if some
+// but not all points exactly at that value are in) a second select over their original indices.
 __global__ void __launch_bounds__(1024)
 k_icp_select(const unsigned long long* __restrict__ keys_base, int ns, char* inst_base, unsigned int K,
-             unsigned char* __restrict__ inl_base)
+             unsigned char* __restrict__ inl_base, const int* __restrict__ orig)
 {
     IcpInst* inst = fg_inst(inst_base, blockIdx.x);
     if (inst->st.done) return;
     const unsigned long long* keys = keys_base + (size_t)blockIdx.x * ns;
     unsigned char* inl = inl_base + (size_t)blockIdx.x * ns;
     __shared__ unsigned int s_hist[256], s_state[2];
-    __shared__ unsigned int s_wcnt[32];
-    __shared__ unsigned int s_run;
     FgSelect sel = fg_block_select([&](int i) { return (unsigned int)(keys[i] >> 32); }, ns, K, s_hist, s_state);
-    if (threadIdx.x == 0) s_run = 0;
-    __syncthreads();
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    for (int base = 0; base < ns; base += 1024)
+    // ties at the K-th value are taken in the CALLER's point order (the oracle's rule): among the points exactly at
+    // v_K keep the take_eq ones with the smallest original index -- a second select, over those indices
+    unsigned int thr_orig = 0xffffffffu;
     {
-        int i = base + threadIdx.x;
-        unsigned int bits = i < ns ? (unsigned int)(keys[i] >> 32) : 0xffffffffu;
-        bool eq = bits == sel.vk_bits;
-        unsigned int m = __ballot_sync(0xffffffffu, eq);
-        if (lane == 0) s_wcnt[w] = __popc(m);
+        unsigned int n_eq_local = 0;
+        for (int i = threadIdx.x; i < ns; i += blockDim.x) n_eq_local += (unsigned int)(keys[i] >> 32) == sel.vk_bits;
+        __shared__ unsigned int s_neq;
+        if (threadIdx.x == 0) s_neq = 0;
         __syncthreads();
-        unsigned int before = s_run;
-        for (int q = 0; q < w; ++q) before += s_wcnt[q];
-        before += __popc(m & ((1u << lane) - 1u));
-        if (i < ns) inl[i] = (bits < sel.vk_bits || (eq && before < sel.take_eq)) ? 1 : 0;
+        if (n_eq_local) atomicAdd(&s_neq, n_eq_local);
         __syncthreads();
-        if (threadIdx.x == 0) { unsigned int tot = 0; for (int q = 0; q < 32; ++q) tot += s_wcnt[q]; s_run += tot; }
-        __syncthreads();
+        if (s_neq > sel.take_eq)                                  // uniform over the block
+        {
+            FgSelect so = fg_block_select([&](int i) { return (unsigned int)(keys[i] >> 32) == sel.vk_bits ? (unsigned int)orig[i] : 0xffffffffu; },
+                                          ns, sel.take_eq, s_hist, s_state);
+            thr_orig = so.vk_bits;
+        }
+    }
+    for (int i = threadIdx.x; i < ns; i += blockDim.x)
+    {
+        unsigned int bits = (unsigned int)(keys[i] >> 32);
+        inl[i] = (bits < sel.vk_bits || (bits == sel.vk_bits && (unsigned int)orig[i] <= thr_orig)) ? 1 : 0;
     }
 }
 
@@ -655,6 +658,9 @@ k_icp_procrustes(const float4* __restrict__ work_base, const unsigned long long*
 static int ensure_icp_capacity(fgoicp_ctx* c, int n)
 {
     if (n <= c->icp_capacity) return FGOICP_OK;
+    // size for a whole batch at once when that is cheap (25 bytes per instance and data point): the capacity then
+    // never changes during a search (no cudaFree / cudaMalloc between levels)
+    if ((size_t)ICP_MAX_BATCH * c->ns * 25 <= ((size_t)256 << 20)) n = std::max(n, ICP_MAX_BATCH);
     FG_CUDA(cudaStreamSynchronize(c->stream));
     cudaFree(c->d_work); cudaFree(c->d_nnkey); cudaFree(c->d_icp); cudaFree(c->d_inl); cudaFree(c->d_icp_part);
     c->d_work = nullptr; c->d_nnkey = nullptr; c->d_icp = nullptr; c->d_inl = nullptr; c->d_icp_part = nullptr; c->icp_capacity = 0;
@@ -761,7 +767,7 @@ extern "C" int fgoicp_nn(fgoicp_ctx* c, const float R[9], const float t[3], int 
     int* d_idx = (int*)c->d_scratch;
     float* d_d2 = (float*)c->d_scratch + ns;
     const float* d_pose = (const float*)((char*)c->d_icp + offsetof(IcpInst, pose0));
-    k_nn_finish<<<(unsigned)((ns + 255) / 256), 256, 0, c->stream>>>(c->d_nnkey, c->d_model, c->d_data, (int)ns, d_pose, d_idx, d_d2);
+    k_nn_finish<<<(unsigned)((ns + 255) / 256), 256, 0, c->stream>>>(c->d_nnkey, c->d_model, c->d_data, (int)ns, d_pose, d_idx, d_d2, c->d_data_orig);
     FG_CUDA(cudaGetLastError());
     if (idx) FG_CUDA(cudaMemcpyAsync(idx, d_idx, ns * 4, cudaMemcpyDeviceToHost, c->stream));
     if (d2) FG_CUDA(cudaMemcpyAsync(d2, d_d2, ns * 4, cudaMemcpyDeviceToHost, c->stream));
@@ -803,7 +809,7 @@ int fg_icp_run_batch(fgoicp_ctx* c, const float* R0s, const float* t0s, int n, i
                 if (c->trim_k > 0 && c->trim_k < c->ns)
                 {
                     // trimmed registration: the Procrustes step sees the trim_k closest correspondences only
-                    k_icp_select<<<m, 1024, 0, c->stream>>>(c->d_nnkey, ns, inst, (unsigned int)c->trim_k, c->d_inl);
+                    k_icp_select<<<m, 1024, 0, c->stream>>>(c->d_nnkey, ns, inst, (unsigned int)c->trim_k, c->d_inl, c->d_data_orig);
                     inl = c->d_inl; n_in = (int)c->trim_k;
                 }
                 double* part = (double*)c->d_icp_part;

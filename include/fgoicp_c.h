@@ -44,6 +44,7 @@ extern "C" {
 #define FGOICP_BUILD_PACKED    (1u << 0)   /* build the corner-packed grid (8x the dense grid) */
 #define FGOICP_BUILD_TEX       (1u << 1)   /* build the cudaArray + texture object             */
 #define FGOICP_BUILD_BRUTE_LUT (1u << 2)   /* build the grid by tiled brute force (test hook)  */
+#define FGOICP_BUILD_KEEP_ORDER (1u << 3)  /* keep the data points in the caller's order on the device (default: Morton order) */
 #define FGOICP_BUILD_DEFAULT   (FGOICP_BUILD_PACKED | FGOICP_BUILD_TEX)
 
 typedef struct fgoicp_ctx fgoicp_ctx;

@@ -63,13 +63,28 @@ struct LutDev
     float vmx, vmy, vmz;      // 256 * dim - 1: upper clamp of the 24.8 fixed-point texel coordinate
     int dx1, dy1;             // dx + 1, dy + 1: row / slice pitch of the corner-packed grid in cells
     const float* packed0;     // packed + 8 * ((dy1 + 1) * dx1 + 1): cell (ix, iy, iz) = texel index, no +1 needed
+    int nbx, nby, nbz;        // FG_BRICKED layout: 4x4x4-cell bricks per axis
 };
+
+// FG_BRICKED = 1: the corner-packed grid is stored as 4x4x4-cell bricks (2 KB each, cells in Morton order inside a
+// brick, so a 128-byte line is a 2x2x1 block of cells and 256 bytes a 2x2x2 block) instead of x-fastest rows.
+#ifndef FG_BRICKED
+#define FG_BRICKED 0
+#endif
+
+__host__ __device__ inline size_t fg_brick_cell(int cx, int cy, int cz, int nbx, int nby)
+{
+    size_t brick = ((size_t)(cz >> 2) * (size_t)nby + (size_t)(cy >> 2)) * (size_t)nbx + (size_t)(cx >> 2);
+    unsigned intra = (cx & 1) | ((cy & 1) << 1) | ((cz & 1) << 2) | ((cx & 2) << 2) | ((cy & 2) << 3) | ((cz & 2) << 4);
+    return brick * 64 + intra;
+}
 
 inline void fg_lut_finalise(LutDev& L)
 {
     L.scale256 = L.scale * 256.0f;
     L.vmx = 256.0f * (float)L.dx - 1.0f; L.vmy = 256.0f * (float)L.dy - 1.0f; L.vmz = 256.0f * (float)L.dz - 1.0f;
     L.dx1 = L.dx + 1; L.dy1 = L.dy + 1;
+    L.nbx = (L.dx + 1 + 3) / 4; L.nby = (L.dy + 1 + 3) / 4; L.nbz = (L.dz + 1 + 3) / 4;
     L.packed0 = L.packed ? L.packed + 8 * ((size_t)(L.dy1 + 1) * (size_t)L.dx1 + 1) : nullptr;
 }
 
@@ -246,8 +261,15 @@ __device__ __forceinline__ void fg_axis(float q, float o, float scale256, float 
 // (the +1 per axis lives in packed0), one widening multiply-add for the byte address
 __device__ __forceinline__ const float* fg_packed_cell(const LutDev& L, int ix, int iy, int iz)
 {
+#if FG_BRICKED
+    const int cx = ix + 1, cy = iy + 1, cz = iz + 1;
+    int brick = ((cz >> 2) * L.nby + (cy >> 2)) * L.nbx + (cx >> 2);
+    int intra = (cx & 1) | ((cy & 1) << 1) | ((cz & 1) << 2) | ((cx & 2) << 2) | ((cy & 2) << 3) | ((cz & 2) << 4);
+    return L.packed + ((long long)brick * 64 + intra) * 8;
+#else
     int cell = (iz * L.dy1 + iy) * L.dx1 + ix;
     return L.packed0 + (long long)cell * 8;
+#endif
 }
 
 __device__ __forceinline__ float fg_trilerp(float a, float b, float c,

@@ -358,6 +358,9 @@ k_pack_cells(const float* __restrict__ grid, int dx, int dy, int dz, float4* __r
     lo.z = grid[x0 + y1 * sy + z0 * sz]; lo.w = grid[x1 + y1 * sy + z0 * sz];
     hi.x = grid[x0 + y0 * sy + z1 * sz]; hi.y = grid[x1 + y0 * sy + z1 * sz];
     hi.z = grid[x0 + y1 * sy + z1 * sz]; hi.w = grid[x1 + y1 * sy + z1 * sz];
+#if FG_BRICKED
+    c = fg_brick_cell(cx, cy, cz, (dx + 1 + 3) / 4, (dy + 1 + 3) / 4);
+#endif
     packed[2 * c] = lo;
     packed[2 * c + 1] = hi;
 }
@@ -626,7 +629,11 @@ extern "C" int fgoicp_ctx_create(const float* model_xyz, size_t nt, const float*
     if (flags & FGOICP_BUILD_PACKED)
     {
         size_t pcells = (size_t)(L.dx + 1) * (L.dy + 1) * (L.dz + 1);
+#if FG_BRICKED
+        FG_TRY(cudaMalloc(&c->d_packed, (size_t)((L.dx + 4) / 4) * ((L.dy + 4) / 4) * ((L.dz + 4) / 4) * 64 * 32));
+#else
         FG_TRY(cudaMalloc(&c->d_packed, pcells * 32));
+#endif
         L.packed = c->d_packed;
         k_pack_cells<<<(unsigned)((pcells + 255) / 256), 256, 0, c->stream>>>(c->d_grid, L.dx, L.dy, L.dz, (float4*)c->d_packed);
         FG_TRY(cudaGetLastError());

@@ -9,6 +9,19 @@ name, src, extra = sys.argv[1], sys.argv[2], sys.argv[3].split()
 B.build()
 vdir = os.path.join(ROOT, "build", "variants")
 os.makedirs(vdir, exist_ok=True)
+if src == "all":
+    objs = []
+    for s_ in B.CU_SOURCES + B.CPP_SOURCES:
+        o = os.path.join(vdir, "%s_%s.o" % (os.path.splitext(s_)[0], name))
+        cmd = ["nvcc"] + B.NVCC_FLAGS + extra + (["-x", "cu"] if s_.endswith(".cpp") else []) + ["-c", os.path.join(B.CSRC, s_), "-o", o]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode:
+            sys.exit(r.stderr)
+        objs.append(o)
+    out = os.path.join(vdir, "lib_%s.so" % name)
+    subprocess.run(["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out] + objs + ["-lcudart", "-ldl"], check=True)
+    print(out)
+    sys.exit(0)
 obj = os.path.join(vdir, "%s_%s.o" % (os.path.splitext(src)[0], name))
 r = subprocess.run(["nvcc"] + B.NVCC_FLAGS + extra + ["-c", os.path.join(B.CSRC, src), "-o", obj], capture_output=True, text=True)
 if r.returncode:
@@ -23,5 +36,5 @@ for ln in r.stderr.splitlines():
         stack = ln
 objs = [os.path.join(B.OBJDIR, os.path.splitext(s)[0] + ".o") for s in B.CU_SOURCES + B.CPP_SOURCES if s != src] + [obj]
 out = os.path.join(vdir, "lib_%s.so" % name)
-subprocess.run(["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out] + objs + ["-lcudart"], check=True)
+subprocess.run(["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out] + objs + ["-lcudart", "-ldl"], check=True)
 print(out)

@@ -474,6 +474,7 @@ static int launch_bnb_t(fgoicp_ctx* c, const float4* d_rot, int Rn, int csize, i
 {
     size_t smem = sizeof(unsigned long long) * BNB_POOL;
     FG_CUDA(cudaFuncSetAttribute(k_bnb_r3<SAMPLER, NWARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (csize > 8) FG_CUDA(cudaFuncSetAttribute(k_bnb_r3<SAMPLER, NWARPS>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(Rn * csize));
     cfg.blockDim = dim3(NWARPS * 32);
@@ -507,9 +508,11 @@ static int launch_bnb(fgoicp_ctx* c, const float4* d_rot, int Rn, int fix_rot, f
     int slots = 3 * c->sm_count;                       // 8-warp blocks resident at once (register-limited)
     int want = (8 * slots + Rn - 1) / Rn;
     int csize = 1;
-    while (csize < 8 && csize < want) csize <<= 1;
+    int cmax = 8;
+    if (const char* e = getenv("FGOICP_BNB_CLUSTER_MAX")) cmax = atoi(e);
+    while (csize < cmax && csize < want) csize <<= 1;
     while (csize > 1 && (int)c->ns / csize < 256) csize >>= 1;
-    if (const char* e = getenv("FGOICP_BNB_CLUSTER")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) csize = v; }
+    if (const char* e = getenv("FGOICP_BNB_CLUSTER")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) csize = v; }
     return launch_bnb_w<8>(c, d_rot, Rn, csize, fix_rot, best_sse, thr, d_out);
 }
 

@@ -356,7 +356,8 @@ k_bounds_phased(LutDev L, int ns,
 #pragma unroll 1
                 while (spin_budget > 0 && *flag < nw_paced) { __nanosleep(100); --spin_budget; }
             }
-            __syncwarp();
+            // keep the budget warp-uniform: the branch above must be taken (or not) by the whole warp
+            spin_budget = __shfl_sync(0xffffffffu, spin_budget, 0);
         }
         // Optional slab prefetch (off by default: measured neutral): every warp pulls its share of the
         // packed-grid layers that phase phi + pf_dist adds into L2 with bulk prefetches.

@@ -164,6 +164,42 @@ def test_icp_is_idempotent_at_its_fixed_point(w5):
     assert e2 <= e * (1 + 1e-6)
 
 
+def test_morton_storage_order_changes_no_result():
+    """The library keeps the data cloud in Morton order on the device.  Every result must equal the one
+    obtained with the caller's order kept (FGOICP_BUILD_KEEP_ORDER): bounds, SSE, per-point NN outputs (returned in the
+    caller's order), ICP, inner searches, trimmed variants included."""
+    w = workloads.synthetic_pair(nt=20_000, ns=3_000, sigma=0.01, seed=21)
+    pp = driver.preprocess(w["model"], w["data"])
+    a = capi.Context(pp["model"], pp["data"], pp["bbox_min"], pp["bbox_max"], 0.01, flags=capi.BUILD_PACKED)
+    b = capi.Context(pp["model"], pp["data"], pp["bbox_min"], pp["bbox_max"], 0.01,
+                     flags=capi.BUILD_PACKED | capi.BUILD_KEEP_ORDER)
+    try:
+        rot, tc = workloads.bound_microbench(160, 32, seed=23)
+        R, _ = driver.rotation_matrix(F(0.2), F(-0.1), F(0.15))
+        t = F([0.03, -0.02, 0.05])
+        for rho in (0.0, 0.2):
+            a.set_trim(rho); b.set_trim(rho)
+            for fix_rot in (True, False):
+                la, ua = a.bounds_multi(rot, fix_rot, tc)
+                lb_, ub_ = b.bounds_multi(rot, fix_rot, tc)
+                assert np.array_equal(la, lb_) and np.array_equal(ua, ub_)
+            assert a.sse(R, t) == b.sse(R, t)
+            ea, Ra, ta, ia = a.icp(R, t, 100, 0.005)
+            eb, Rb, tb, ib = b.icp(R, t, 100, 0.005)
+            assert ia == ib and ea == eb and np.array_equal(Ra, Rb) and np.array_equal(ta, tb)
+            thr = a.ns * 1e-4
+            ua, ta_, eva = a.bnb_r3_batch(rot[:6], True, 1e10, thr)
+            ub2, tb_, evb = b.bnb_r3_batch(rot[:6], True, 1e10, thr)
+            assert np.array_equal(eva, evb) and np.array_equal(ua, ub2) and np.array_equal(ta_, tb_)
+        a.set_trim(0.0); b.set_trim(0.0)
+        for rooted in (False, True):
+            ia_, da = a.nn(R, t, rooted)
+            ib_, db = b.nn(R, t, rooted)
+            assert np.array_equal(ia_, ib_) and np.array_equal(da, db)
+    finally:
+        a.close(); b.close()
+
+
 def test_tiny_clouds_and_argument_errors():
     model = F([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1]])
     data = F([[0.1, 0.1, 0.1]])

@@ -389,6 +389,18 @@ def run_reference(args):
         step()
     dt = time.perf_counter() - t0
     v = evals_per_step * args.steps / dt
+    port = None
+    if use_ref:
+        # for the record, the CPU restatement (oracle port) on all host threads, same bounded sample (coarser grid so
+        # that the brute-force CPU grid build stays bounded; the per-evaluation cost does not depend on it)
+        from oracle import oracle as O
+        pp = O.preprocess(w["model"], w["data"])
+        lut, dims = O.lut_build(pp["model"][::50], pp["bbox_min"], pp["bbox_max"], 0.02)
+        t1 = time.perf_counter()
+        for k in range(n_rot_sample):
+            R, _ = O.rotation(*rot[k, :3])
+            O.bounds(lut, dims, pp["bbox_min"], 0.02, pp["data"], R, float(rot[k, 3]), False, tc)
+        port = {"value": evals_per_step / (time.perf_counter() - t1), "unit": "evals/s", "cores": O.num_threads(), "kind": "port"}
     out = {"impl": "reference", "metric": "cube x point bound evals/s", "value": v, "unit": "evals/s",
            "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": max(args.warmup, 1),
            "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -396,6 +408,8 @@ def run_reference(args):
            "config": {"workload": "W5 synthetic: 100k-point model / 10k-point data, lut_resolution 0.005; bounded sample"},
            "cpu_baseline": {"value": v, "unit": "evals/s", "cores": cores, "kind": kind, "sample": sample},
            "e2e": {"value": v, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if port:
+        out["oracle_port_on_host_cores"] = port
     emit(out)
 
 

@@ -132,15 +132,29 @@ k_bounds_trim(LutDev L, const float4* __restrict__ data, int ns,
 #pragma unroll
     for (int k = 0; k < 9; ++k) R[k] = sR[k];
     const float sin_half = s_sin;
-    for (int i = threadIdx.x; i < ns; i += BT_THREADS)
+    // four points per thread and pass: four independent gathers in flight per lane (one cube per block leaves no
+    // other source of memory-level parallelism)
+    for (int i0 = threadIdx.x; i0 < ns; i0 += 4 * BT_THREADS)
     {
-        float4 p = __ldg(&data[i]);
-        float3 rp = fg_rotate(R, p.x, p.y, p.z);
-        float rot_r = __fmul_rn(__fadd_rn(p.w, p.w), sin_half);
-        float d2 = fg_sample<SAMPLER>(L, __fadd_rn(rp.x, t.x), __fadd_rn(rp.y, t.y), __fadd_rn(rp.z, t.z));
-        float u, l;
-        fg_bound_terms(d2, rot_r, fix_rot != 0, t.w, u, l);
-        sv[i] = u; sv[ns + i] = l;
+        SampleReq req[4];
+        float rot_r[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+        {
+            const int i = min(i0 + k * BT_THREADS, ns - 1);
+            float4 p = __ldg(&data[i]);
+            float3 rp = fg_rotate(R, p.x, p.y, p.z);
+            rot_r[k] = __fmul_rn(__fadd_rn(p.w, p.w), sin_half);
+            fg_sample_issue<SAMPLER>(L, __fadd_rn(rp.x, t.x), __fadd_rn(rp.y, t.y), __fadd_rn(rp.z, t.z), req[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+        {
+            const int i = i0 + k * BT_THREADS;
+            float u, l;
+            fg_bound_terms(fg_sample_finish<SAMPLER>(req[k]), rot_r[k], fix_rot != 0, t.w, u, l);
+            if (i < ns) { sv[i] = u; sv[ns + i] = l; }
+        }
     }
     __syncthreads();
     const float* su = sv;

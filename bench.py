@@ -296,7 +296,8 @@ def run_ours(args):
                          "t_err": float(np.linalg.norm(t - w["t_true"])), "rot_cubes_local": st["rot_cubes"],
                          "bound_evals_local": st["bound_evals"], "icp_runs_local": st["icp_runs"],
                          "ms_bnb_ub": st["ms_bnb_ub"], "ms_icp": st["ms_icp"], "ms_bnb_lb": st["ms_bnb_lb"],
-                         "levels": st["level_log"]})
+                         "ms_first_icp": st.get("ms_first_icp"), "ms_final_icp": st.get("ms_final_icp"),
+                         "ms_search_wall": st.get("ms_search_wall"), "levels": st["level_log"]})
             if rep < NRUNS - 1:
                 g.close()
         order = sorted(range(NRUNS), key=lambda k: runs[k]["bnb_ms"])

@@ -190,6 +190,7 @@ class FastGoICP:
         t0 = time.perf_counter()
         I = np.array([1, 0, 0, 0, 1, 0, 0, 0, 1], F)
         e, _, _, it = self.ctx.icp(I, np.zeros(3, F), 100, 0.05)           # fgoicp.cpp:12-14
+        self.stats["ms_first_icp"] = (time.perf_counter() - t0) * 1e3
         self.best_sse = F(e)
         self.stats["icp_runs"] += 1
         self.stats["icp_iters"] += it
@@ -198,7 +199,10 @@ class FastGoICP:
             self._search_best_first()
         else:
             self._search_level_synchronous()
+        t1 = time.perf_counter()
+        self.stats["ms_search_wall"] = (t1 - t0) * 1e3 - self.stats["ms_first_icp"]
         e, R, t, it = self.ctx.icp(self.best_R, self.best_t, 100, 0.0005)  # fgoicp.cpp:22-23
+        self.stats["ms_final_icp"] = (time.perf_counter() - t1) * 1e3
         self.best_sse, self.best_R, self.best_t = F(e), R, t
         self.stats["icp_runs"] += 1
         self.stats["icp_iters"] += it

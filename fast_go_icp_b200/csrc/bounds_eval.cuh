@@ -4,7 +4,9 @@
 #include "common.cuh"
 
 #define BD_CHUNK   32        // translation cubes staged per pass
-#define BD_CPW     4         // cubes per warp
+#ifndef BD_CPW
+#define BD_CPW     4         // cubes per warp; 8 was measured slower (inner searches 84 -> 94 ms); must satisfy BD_CHUNK <= BD_CPW * warps
+#endif
 
 // Evaluates nch (<= BD_CHUNK) translation cubes staged in s_tc against data points [p0, p1) with
 // NWARPS warps laid out as Wc cube-groups x Wp point-slices.  On return (after the caller's
@@ -15,6 +17,7 @@ __device__ __forceinline__ void fg_eval_chunk(const LutDev& L, const float4* __r
                                               const float* sR, float sin_half, bool fix_rot,
                                               const float4* s_tc, int nch, double (*s_part)[BD_CPW][2])
 {
+    static_assert(BD_CHUNK <= BD_CPW * NWARPS, "every cube group of a chunk needs its own warp slot in s_part");
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     int groups = (nch + BD_CPW - 1) / BD_CPW;
     int Wc = 1; while (Wc < groups) Wc <<= 1;

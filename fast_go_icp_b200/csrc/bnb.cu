@@ -55,8 +55,11 @@ __device__ __forceinline__ unsigned long long bnb_key(float lb, unsigned level, 
     return ((unsigned long long)__float_as_uint(lb) << 32) | lo;
 }
 
+#ifndef BNB_MIN_BLOCKS
+#define BNB_MIN_BLOCKS 1
+#endif
 template <int SAMPLER, int NWARPS>
-__global__ void __launch_bounds__(NWARPS * 32)
+__global__ void __launch_bounds__(NWARPS * 32, BNB_MIN_BLOCKS)
 k_bnb_r3(LutDev L, const float4* __restrict__ data, int ns, const float4* __restrict__ rot, int fix_rot,
          float best_sse, float sse_threshold, int batch_max, BnbOut* __restrict__ out)
 {

@@ -27,8 +27,11 @@
 #define BD_THREADS 256
 #define BD_WARPS   (BD_THREADS / 32)
 
+#ifndef BNB_MIN_BLOCKS
+#define BNB_MIN_BLOCKS 1
+#endif
 template <int SAMPLER>
-__global__ void __launch_bounds__(BD_THREADS)
+__global__ void __launch_bounds__(BD_THREADS, BNB_MIN_BLOCKS)
 k_bounds_multi(LutDev L, const float4* __restrict__ data, int ns,
                const float4* __restrict__ rot, const float* __restrict__ Rmats, int fix_rot,
                const float4* __restrict__ tcubes, int T, int S,

@@ -121,22 +121,33 @@ class _Comm:
         self.dist.broadcast(t, src=src, group=self.group)
         return t.cpu().numpy()
 
-    def gather_rows(self, local, n_total):
-        """local: rows of this rank's round-robin shard (global rows rank, rank+world, ...).
-        Returns the full (n_total, k) array on every rank."""
+    def exchange(self, header, local, n_total):
+        """ONE all-gather per wave: every rank contributes a fixed-size header (uint32 words) and its round-robin
+        shard of rows (float32).  Returns (headers [world, H] uint32, full rows [n_total, k]) on every rank."""
+        header = np.ascontiguousarray(header, np.uint32)
         if self.dist is None:
-            return local
+            return header[None, :], local
         k = local.shape[1]
         per = (n_total + self.world - 1) // self.world
-        buf = np.full((per, k), np.nan, F)
-        buf[:len(local)] = local
+        buf = np.zeros(len(header) + per * k, F)
+        buf[:len(header)] = header.view(F)                      # bit patterns travel unchanged (copies only)
+        buf[len(header):len(header) + local.size] = local.ravel()
         t = self.torch.from_numpy(buf).to(self.dev)
-        out = [self.torch.empty_like(t) for _ in range(self.world)]
-        self.dist.all_gather(out, t, group=self.group)
+        out = self.torch.empty(self.world * len(buf), dtype=t.dtype, device=self.dev)
+        self.dist.all_gather_into_tensor(out, t, group=self.group)
+        allb = out.cpu().numpy().reshape(self.world, len(buf))  # one device-to-host copy
+        heads = np.ascontiguousarray(allb[:, :len(header)]).view(np.uint32)
         full = np.empty((per * self.world, k), F)
         for r in range(self.world):
-            full[r::self.world] = out[r].cpu().numpy()
-        return full[:n_total]
+            full[r::self.world] = allb[r, len(header):].reshape(per, k)
+        return heads, full[:n_total]
+
+    def gather_rows(self, local, n_total):
+        """local: rows of this rank's round-robin shard (global rows rank, rank+world, ...).
+        Returns the full (n_total, k) array on every rank (one all-gather, one device-to-host copy)."""
+        if self.dist is None:
+            return local
+        return self.exchange(np.zeros(1, np.uint32), local, n_total)[1]
 
 
 class FastGoICP:
@@ -307,19 +318,24 @@ class FastGoICP:
                 my_idx = widx[comm.rank::comm.world]
                 ub_l, bt_l, e_l, R_l, t_l, st = self.ctx.so3_level_ub(ev[my_idx, :4], self.best_sse, thr,
                                                                      self.best_R, self.best_t)
-                # global best: MIN over (sse bits, global child index); ties -> lowest child index
+                # ONE exchange per wave: header = (sse bits, global child index, pose of this rank's best ICP), rows =
+                # (ub, best_t) of this rank's cubes.  Global best = MIN over (sse bits, child index): ties -> lowest
+                # child index, which is what a single rank's ascending scan picks.
+                head = np.zeros(14, np.uint32)
                 if st.best_icp_index >= 0 and e_l < self.best_sse:
-                    gidx = int(my_idx[st.best_icp_index])
-                    key = (int(np.array([e_l], F).view(np.uint32)[0]) << 32) | gidx
+                    head[0] = np.array([e_l], F).view(np.uint32)[0]
+                    head[1] = np.uint32(int(my_idx[st.best_icp_index]))
+                    head[2:14] = np.concatenate([R_l, t_l]).astype(F).view(np.uint32)
                 else:
-                    key = (int(np.array([self.best_sse], F).view(np.uint32)[0]) << 32) | 0xffffffff
-                gkey = comm.min_key(key)
-                if (gkey & 0xffffffff) != 0xffffffff:
-                    owner = int(np.nonzero(widx == (gkey & 0xffffffff))[0][0]) % comm.world
-                    pose = comm.bcast_f32(np.concatenate([R_l, t_l]), owner)
-                    self.best_sse = np.array([gkey >> 32], np.uint32).view(F)[0]
+                    head[0] = np.array([self.best_sse], F).view(np.uint32)[0]
+                    head[1] = np.uint32(0xffffffff)
+                heads, ubt_w = comm.exchange(head, np.concatenate([ub_l[:, None], bt_l], axis=1), len(widx))
+                keys = (heads[:, 0].astype(np.uint64) << np.uint64(32)) | heads[:, 1].astype(np.uint64)
+                win = int(np.argmin(keys))
+                if heads[win, 1] != np.uint32(0xffffffff):
+                    pose = heads[win, 2:14].view(F)
+                    self.best_sse = heads[win, 0:1].view(F)[0]
                     self.best_R, self.best_t = pose[:9].copy(), pose[9:].copy()
-                ubt_w = comm.gather_rows(np.concatenate([ub_l[:, None], bt_l], axis=1), len(widx))
                 ub[widx], bt[widx] = ubt_w[:, 0], ubt_w[:, 1:]
                 tot["evals"] += int(st.evals); tot["n_icp"] += int(st.n_icp); tot["icp_iters"] += int(st.icp_iters)
                 tot["ms_ub"] += st.ms_bnb_ub; tot["ms_icp"] += st.ms_icp; tot["local"] += len(my_idx)

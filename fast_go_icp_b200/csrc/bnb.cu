@@ -56,7 +56,7 @@ __device__ __forceinline__ unsigned long long bnb_key(float lb, unsigned level, 
 }
 
 #ifndef BNB_MIN_BLOCKS
-#define BNB_MIN_BLOCKS 1
+#define BNB_MIN_BLOCKS 2      // 2 blocks of 8 warps per SM (<= 128 registers); 1 lets ptxas take 139 and halves the occupancy (inner searches 84 -> 104 ms), 3 spills (108 ms)
 #endif
 template <int SAMPLER, int NWARPS>
 __global__ void __launch_bounds__(NWARPS * 32, BNB_MIN_BLOCKS)

@@ -28,7 +28,7 @@
 #define BD_WARPS   (BD_THREADS / 32)
 
 #ifndef BNB_MIN_BLOCKS
-#define BNB_MIN_BLOCKS 1
+#define BNB_MIN_BLOCKS 2      // 2 blocks of 8 warps per SM (<= 128 registers); 1 lets ptxas take 139 and halves the occupancy (inner searches 84 -> 104 ms), 3 spills (108 ms)
 #endif
 template <int SAMPLER>
 __global__ void __launch_bounds__(BD_THREADS, BNB_MIN_BLOCKS)

@@ -4,16 +4,22 @@
  * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load
  * it.  The product path (fast_go_icp_b200/csrc) never links or calls anything in oracle/.
  *
- * PARITY STATUS: "parity unpinned" by the reference's own tests -- the reference ships no
- * tests, golden vectors or expected outputs and has no CPU path.  What
- * pins this restatement instead:
- *   (1) the floating-point association of every device expression below was read off the SASS
- *       that nvcc 12.9 emits for the UNMODIFIED reference kernels on sm_100 (oracle/build_ref.py
- *       compiles them; see DESIGN.md "Canonical arithmetic"), and is written here with explicit
- *       fmaf() and -ffp-contract=off;
- *   (2) on a GPU box, tests compare the CUDA path AND this oracle against the unmodified
- *       reference sources compiled into oracle/_ref/ (real tex3D, real kernels);
- *   (3) independent cross-checks in tests (scipy cKDTree, numpy SVD/Kabsch, numpy trilinear).
+ * PARITY STATUS: PINNED against outputs of the reference itself.  The reference ships no tests, golden
+ * vectors or expected outputs of its own and has no CPU path, so the pins are:
+ *   (1) golden vectors produced by the UNMODIFIED reference sources (compiled by oracle/build_ref.py into
+ *       oracle/_ref/, run on a B200; generator scripts committed next to the vectors):
+ *       tests/golden/reference_small.npz (synthetic pair) and tests/golden/reference_clouds.npz (subsamples of
+ *       the reference repository's own bunny, skull, dragon and partial-overlap pairs) -- preprocessing and
+ *       every grid cell bit-exact, bounds / SSE / ICP / inner searches / run() within the tolerances stated in
+ *       tests/test_golden.py and tests/test_golden_clouds.py (CPU suite);
+ *   (2) the floating-point association of every device expression below was read off the SASS that nvcc 12.9
+ *       emits for the unmodified reference kernels on sm_100 (DESIGN.md "Canonical arithmetic") and is written
+ *       here with explicit fmaf() and -ffp-contract=off;
+ *   (3) on a GPU box, tests also compare the CUDA path AND this oracle against oracle/_ref live (real tex3D,
+ *       real kernels);
+ *   (4) independent cross-checks in tests (scipy cKDTree, numpy SVD/Kabsch, numpy trilinear).
+ * The trimming switch (orc_set_trim_k) is an EXTENSION with no reference behaviour: it is pinned by a numpy
+ * restatement only (tests/test_trimming.py) and is off by default.
  *
  * Each function cites the reference file:line it follows (paths relative to the reference repo).
  * Matrices are 9 floats, column-major (glm::mat3 memory order): M[c*3+r].

@@ -20,8 +20,14 @@ class OracleContext:
     def set_sampler(self, s):
         pass
 
+    def set_trim(self, trim_fraction):
+        """Trimmed registration: the oracle's global switch stays on for the life of this context (tests only)."""
+        k = O.trim_count(self.ns, trim_fraction)
+        O.set_trim_k(0 if k == self.ns else k)
+        return k
+
     def close(self):
-        pass
+        O.set_trim_k(0)
 
     def icp(self, R0, t0, max_iter, thr):
         return O.icp(self.model, self.data, max_iter, thr, R0, t0)

@@ -21,23 +21,31 @@ def _problem():
     return workloads.synthetic_pair(nt=700, ns=120, sigma=0.005, seed=21, max_angle=0.9)
 
 
-def _run(group_ready):
+def _run(group_ready, trim=0.0):
     from fast_go_icp_b200 import driver
     from oracle import oracle as O
     from oracle_context import OracleContext
     O.set_num_threads(2)
     w = _problem()
-    g = driver.FastGoICP(w["model"], w["data"], 0.04, 1e-4, ctx_factory=OracleContext)
+    data = w["data"]
+    if trim > 0:
+        # gross outliers that only a trimmed registration ignores
+        rng = np.random.default_rng(5)
+        data = data.copy()
+        bad = rng.choice(len(data), 24, replace=False)
+        data[bad] = (data.min(0) + rng.random((24, 3)) * (data.max(0) - data.min(0))).astype(np.float32)
+    g = driver.FastGoICP(w["model"], data, 0.04, 1e-4, ctx_factory=OracleContext, trim_fraction=trim)
     R, t = g.run()
+    g.close()
     return dict(R=R, t=t, sse=float(g.best_sse), evals=g.stats["bound_evals"], cubes=g.stats["rot_cubes"],
                 icps=g.stats["icp_runs"], levels=[(l["cubes"], l["survivors"], l["best_sse"]) for l in g.stats["level_log"]])
 
 
-def _worker(rank, world, port, out_path):
+def _worker(rank, world, port, out_path, trim=0.0):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    res = _run(True)
+    res = _run(True, trim)
     if rank == 0:
         torch.save(res, out_path)
     # every rank must hold the same answer
@@ -79,3 +87,18 @@ def test_sharded_run_is_bit_identical(tmp_path, single, world):
     assert np.array_equal(res["R"], single["R"]) and np.array_equal(res["t"], single["t"])
     assert res["levels"] == single["levels"]                 # same frontier, level by level
     assert res["cubes"] < single["cubes"]                    # rank 0 only searched its shard
+
+
+def test_trimmed_sharded_run_is_bit_identical(tmp_path):
+    """Trimmed registration through the sharded driver: same answer on 1 and 2 ranks."""
+    one = _run(False, trim=0.2)
+    out = str(tmp_path / "res_trim.pt")
+    port = 29900 + (os.getpid() % 400)
+    mp.spawn(_worker, args=(2, port, out, 0.2), nprocs=2, join=True)
+    res = torch.load(out, weights_only=False)
+    assert res["sse"] == one["sse"]
+    assert np.array_equal(res["R"], one["R"]) and np.array_equal(res["t"], one["t"])
+    assert res["levels"] == one["levels"]
+    w = _problem()
+    ang = np.degrees(np.arccos(np.clip((np.trace(one["R"] @ w["R_true"].T) - 1) / 2, -1, 1)))
+    assert ang < 2.0 and np.linalg.norm(one["t"] - w["t_true"]) < 0.03

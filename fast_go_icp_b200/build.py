@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJDIR = os.path.join(HERE, "csrc", "_obj")
 OUT = os.path.join(HERE, "libfgoicp_b200.so")
 
-CU_SOURCES = ["ctx.cu", "bounds.cu", "bounds_phased.cu", "nn_icp.cu", "bnb.cu", "probe.cu"]
+CU_SOURCES = ["ctx.cu", "bounds.cu", "bounds_phased.cu", "nn_icp.cu", "bnb.cu", "probe.cu", "preprocess.cu"]
 CPP_SOURCES = ["fgoicp_host.cpp"]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC,-ffp-contract=off", "-Xptxas", "-v",

@@ -22,7 +22,9 @@ EXPORTS = [
     "fgoicp_set_sampler", "fgoicp_set_trim", "fgoicp_set_stream", "fgoicp_set_nn_mode", "fgoicp_set_phased", "fgoicp_set_bnb_mode", "fgoicp_gather_probe", "fgoicp_lut_download", "fgoicp_lut_sample", "fgoicp_rot_sin",
     "fgoicp_bounds_batch", "fgoicp_bounds_multi", "fgoicp_bounds_multi_dev", "fgoicp_sse", "fgoicp_nn",
     "fgoicp_icp", "fgoicp_bnb_r3", "fgoicp_bnb_r3_batch", "fgoicp_so3_level_ub", "fgoicp_so3_level_lb",
+    "fgoicp_preprocess", "fgoicp_preprocess_dev",
 ]
+PRE_REFERENCE, PRE_TREE_CENTROID, PRE_SCALE_BOTH = 0, 1, 2
 
 
 class FgoicpError(RuntimeError):
@@ -41,6 +43,11 @@ class LevelStats(C.Structure):
     _fields_ = [("evals", C.c_uint64), ("n_icp", C.c_uint32), ("icp_iters", C.c_uint32),
                 ("ms_bnb_ub", C.c_float), ("ms_icp", C.c_float), ("ms_bnb_lb", C.c_float),
                 ("best_icp_index", C.c_int32)]
+
+
+class Normalisation(C.Structure):
+    _fields_ = [("offset_pcs", C.c_float * 3), ("offset_pct", C.c_float * 3), ("scale", C.c_float),
+                ("bbox_min", C.c_float * 3), ("bbox_max", C.c_float * 3), ("device_ms", C.c_float)]
 
 
 _f32p = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
@@ -86,6 +93,8 @@ def lib():
     L.fgoicp_so3_level_ub.argtypes = [vp, vp, C.c_int, C.c_float, C.c_float, vp, vp,
                                       C.POINTER(C.c_float), _f32p, _f32p, C.POINTER(LevelStats)]
     L.fgoicp_so3_level_lb.argtypes = [vp, vp, C.c_int, C.c_float, C.c_float, vp, C.POINTER(LevelStats)]
+    L.fgoicp_preprocess.argtypes = [_f32p, C.c_size_t, _f32p, C.c_size_t, C.c_int, C.c_uint, C.POINTER(Normalisation)]
+    L.fgoicp_preprocess_dev.argtypes = [vp, C.c_size_t, vp, C.c_size_t, C.c_int, C.c_uint, vp, C.POINTER(Normalisation)]
     for name in EXPORTS:
         getattr(L, name).restype = getattr(L, name).restype if name in ("fgoicp_last_error", "fgoicp_version") else C.c_int
     _lib = L
@@ -99,6 +108,33 @@ def _check(rc, what):
 
 def _f32(a):
     return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _normalisation_dict(model, data, n):
+    F = np.float32
+    return dict(model=model, data=data, offset_pcs=np.array(n.offset_pcs, F), offset_pct=np.array(n.offset_pct, F),
+                scale=F(n.scale), bbox_min=np.array(n.bbox_min, F), bbox_max=np.array(n.bbox_max, F),
+                device_ms=float(n.device_ms))
+
+
+def preprocess(target, source, device=0, flags=PRE_REFERENCE):
+    """FastGoICP constructor preprocessing on the GPU (fgoicp/fgoicp.hpp:13-19, fgoicp.cpp:176-287) through
+    fgoicp_preprocess: centre both clouds, scale by 1 / max|coord| of the source, range of the target.
+    Same keys as driver.preprocess; flags = PRE_REFERENCE is bit-identical to it."""
+    model = _f32(target).reshape(-1, 3).copy()
+    data = _f32(source).reshape(-1, 3).copy()
+    n = Normalisation()
+    _check(lib().fgoicp_preprocess(model, len(model), data, len(data), int(device), int(flags), C.byref(n)),
+           "fgoicp_preprocess")
+    return _normalisation_dict(model, data, n)
+
+
+def preprocess_dev(d_model_ptr, nt, d_data_ptr, ns, device=0, flags=PRE_REFERENCE, cuda_stream_ptr=None):
+    """Same on clouds already in HBM (raw device pointers to n*3 floats, modified in place)."""
+    n = Normalisation()
+    _check(lib().fgoicp_preprocess_dev(C.c_void_p(d_model_ptr), int(nt), C.c_void_p(d_data_ptr), int(ns), int(device),
+                                       int(flags), C.c_void_p(cuda_stream_ptr or 0), C.byref(n)), "fgoicp_preprocess_dev")
+    return _normalisation_dict(None, None, n)
 
 
 class Context:

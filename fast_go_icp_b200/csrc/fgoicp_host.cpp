@@ -57,10 +57,7 @@ namespace icp
     FastGoICP::FastGoICP(std::vector<glm::vec3> _pct, std::vector<glm::vec3> _pcs, float _lut_resolution, float _mse_threshold,
                          const Options& options)
         : pcs(std::move(_pcs)), pct(std::move(_pct)), ns{ pcs.size() }, nt{ pct.size() },
-          offset_pcs(center_point_cloud(pcs)),
-          offset_pct(center_point_cloud(pct)),
-          scaling_factor(scale_point_clouds(pct, pcs)),
-          target_bounds(get_point_cloud_ranges(pct)),
+          offset_pcs(0.0f), offset_pct(0.0f), scaling_factor(1.0f),
           best_sse(M_INF), best_rotation(1.0f), best_translation(0.0f),
           mse_threshold(_mse_threshold),
           sse_threshold(ns * mse_threshold),
@@ -76,7 +73,31 @@ namespace icp
         if (const char* s = std::getenv("FGOICP_WAVE1")) options_.wave1 = std::atoi(s);
         if (const char* s = std::getenv("FGOICP_SKIP_DEAD_LB")) options_.skip_dead_lb = std::atoi(s) != 0;
         if (const char* s = std::getenv("FGOICP_TRIM_FRACTION")) options_.trim_fraction = static_cast<float>(std::atof(s));
+        if (const char* s = std::getenv("FGOICP_DEVICE_PREPROCESS")) options_.device_preprocess = std::atoi(s) != 0;
+        preprocess_clouds();
         init(_lut_resolution);
+    }
+
+    // Reference constructor order (fgoicp.hpp:16-19): centre source, centre target, scale both, range of the target --
+    // on the host in the reference's own fp32 order, or on the GPU through the C ABI (same bits with flags = 0).
+    void FastGoICP::preprocess_clouds()
+    {
+        static_assert(sizeof(glm::vec3) == 3 * sizeof(float), "glm::vec3 must be three packed floats");
+        if (!options_.device_preprocess)
+        {
+            offset_pcs = center_point_cloud(pcs);
+            offset_pct = center_point_cloud(pct);
+            scaling_factor = scale_point_clouds(pct, pcs);
+            target_bounds = get_point_cloud_ranges(pct);
+            return;
+        }
+        fgoicp_normalisation n;
+        check(fgoicp_preprocess(reinterpret_cast<float*>(pct.data()), nt, reinterpret_cast<float*>(pcs.data()), ns,
+                                options_.device, options_.preprocess_flags, &n), "fgoicp_preprocess");
+        offset_pcs = glm::vec3(n.offset_pcs[0], n.offset_pcs[1], n.offset_pcs[2]);
+        offset_pct = glm::vec3(n.offset_pct[0], n.offset_pct[1], n.offset_pct[2]);
+        scaling_factor = n.scale;
+        for (int a = 0; a < 3; ++a) target_bounds[a] = std::make_pair(n.bbox_min[a], n.bbox_max[a]);
     }
 
     void FastGoICP::init(float lut_resolution)

@@ -155,9 +155,14 @@ class FastGoICP:
 
     def __init__(self, target, source, lut_resolution, mse_threshold, device=0, sampler=None,
                  flags=capi.BUILD_PACKED, group=None, ctx_factory=None, wave1=32, skip_dead_lb=True,
-                 schedule="level", trim_fraction=0.0):
+                 schedule="level", trim_fraction=0.0, device_preprocess=False, preprocess_flags=0):
         t0 = time.perf_counter()
-        self.pp = preprocess(target, source)
+        # device_preprocess: centring / scaling / ranges on the GPU through fgoicp_preprocess;
+        # with preprocess_flags = 0 bit-identical to the host pass below
+        if device_preprocess:
+            self.pp = capi.preprocess(target, source, device=device, flags=preprocess_flags)
+        else:
+            self.pp = preprocess(target, source)
         self.ns, self.nt = len(self.pp["data"]), len(self.pp["model"])
         self.mse_threshold = F(mse_threshold)
         self.sse_threshold = F(F(self.ns) * self.mse_threshold)            # fgoicp.hpp:23

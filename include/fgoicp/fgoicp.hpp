@@ -35,6 +35,8 @@ namespace icp
             int wave1 = 32;          // first-wave size of a level (then x4, x16, rest): early ICPs tighten best_sse; 0: no split
             bool skip_dead_lb = true; // skip the leaf level's rotation-uncertainty searches (they cannot change any output)
             bool verbose_levels = false;
+            bool device_preprocess = false; // centre / scale / range the clouds on the GPU (fgoicp_preprocess; env FGOICP_DEVICE_PREPROCESS)
+            unsigned preprocess_flags = 0;  // FGOICP_PRE_* (0 = bit-identical to the reference's host code)
             float trim_fraction = 0.0f; // > 0: trimmed registration over the (1 - trim_fraction) * ns best points (extension; env FGOICP_TRIM_FRACTION)
         };
 
@@ -119,6 +121,7 @@ namespace icp
         fgoicp_ctx* ctx_ = nullptr;
 
         void init(float lut_resolution);
+        void preprocess_clouds();
         glm::vec3 center_point_cloud(PointCloud& pc);
         float scale_point_clouds(PointCloud& pct, PointCloud& pcs);
         std::array<std::pair<float, float>, 3> get_point_cloud_ranges(PointCloud& pc);

@@ -68,6 +68,41 @@ typedef struct fgoicp_info
 const char* fgoicp_last_error(void);
 const char* fgoicp_version(void);
 
+/* FastGoICP constructor preprocessing on the device (fgoicp/fgoicp.hpp:13-19):
+ *   center_point_cloud(source), center_point_cloud(target)   fgoicp/fgoicp.cpp:176-195
+ *   scale_point_clouds(target, source)                       fgoicp/fgoicp.cpp:197-220, 271-287
+ *   get_point_cloud_ranges(target)                           fgoicp/fgoicp.cpp:222-268
+ * Both clouds (n*3 floats each) are centred and scaled IN PLACE.  With flags = FGOICP_PRE_REFERENCE every output is
+ * bit-identical to the reference's host code: the centroid is the serial fp32 sum in index order, the scale is
+ * 1 / max|coordinate| of the centred SOURCE.
+ *   FGOICP_PRE_TREE_CENTROID  centroid from a deterministic parallel fp64 reduction (fixed partition and combination
+ *                             order) rounded once to fp32 -- for clouds of millions of points; last-bit differences
+ *                             from the reference's centroid;
+ *   FGOICP_PRE_SCALE_BOTH     scale = 1 / max|coordinate| over BOTH centred clouds, so the target also lies inside
+ *                             [-1,1]^3, the domain the translation search covers (fgoicp.cpp:113; the reference
+ *                             scales by the source alone and lets the target stick out).
+ * fgoicp_preprocess takes host buffers (copies in, computes on `device`, copies back); fgoicp_preprocess_dev takes
+ * device buffers and a CUDA stream (cudaStream_t as void*, NULL = default stream) and returns after the stream has
+ * finished.  The outputs feed fgoicp_ctx_create (bbox_min / bbox_max) and restore_translation (fgoicp.hpp:87-90). */
+#define FGOICP_PRE_REFERENCE      0u
+#define FGOICP_PRE_TREE_CENTROID  (1u << 0)
+#define FGOICP_PRE_SCALE_BOTH     (1u << 1)
+
+typedef struct fgoicp_normalisation
+{
+    float offset_pcs[3];        /* -centroid of the source, as center_point_cloud returns it (fgoicp.cpp:194) */
+    float offset_pct[3];        /* -centroid of the target                                                     */
+    float scale;                /* scaling factor applied to both clouds                                       */
+    float bbox_min[3];          /* per-axis range of the centred, scaled target                                */
+    float bbox_max[3];
+    float device_ms;            /* device time of the preprocessing kernels                                    */
+} fgoicp_normalisation;
+
+int fgoicp_preprocess(float* model_xyz, size_t nt, float* data_xyz, size_t ns,
+                      int device, unsigned flags, fgoicp_normalisation* out);
+int fgoicp_preprocess_dev(float* d_model_xyz, size_t nt, float* d_data_xyz, size_t ns,
+                          int device, unsigned flags, void* cuda_stream, fgoicp_normalisation* out);
+
 /* Registration + NearestNeighborLUT constructor (registration.hpp:68-80, registration.cu:180-207,
  * 258-318): uploads both clouds (already centred and scaled by the caller, fgoicp.hpp:16-18) and
  * builds the nearest-SQUARED-distance grid over [bbox_min, bbox_max] of the model cloud.

@@ -55,6 +55,22 @@ def test_bad_arguments_are_reported_not_crashed():
     assert L.fgoicp_ctx_destroy(None) == 0
 
 
+def test_preprocess_arguments_and_no_gpu_failure():
+    """fgoicp_preprocess: bad arguments reported; without a GPU it fails loudly, never on the CPU."""
+    L = capi.lib()
+    n = capi.Normalisation()
+    pts = np.zeros((4, 3), np.float32)
+    assert L.fgoicp_preprocess(pts, 0, pts, 4, 0, 0, ctypes.byref(n)) == -1 and b"empty" in L.fgoicp_last_error()
+    assert L.fgoicp_preprocess(pts, 4, pts, 4, 0, 8, ctypes.byref(n)) == -1 and b"flag" in L.fgoicp_last_error()
+    assert L.fgoicp_preprocess(pts, 4, pts, 4, 0, 0, None) == -1
+    if not torch.cuda.is_available():
+        with pytest.raises(capi.FgoicpError) as e:
+            capi.preprocess(pts + 1, pts + 2)
+        assert "no CUDA device" in str(e.value)
+        with pytest.raises(capi.FgoicpError):
+            driver.FastGoICP(pts + 1, pts + 2, 0.1, 1e-3, device_preprocess=True)
+
+
 def test_driver_host_arithmetic_is_bit_identical_to_oracle():
     rng = np.random.default_rng(4)
     for _ in range(300):

@@ -288,3 +288,70 @@ def test_against_unmodified_reference_kernels(small_problem, gpu_ctx):
     e, R1, t1, _ = gpu_ctx.icp(I, np.zeros(3, np.float32), 100, 0.05)
     assert abs(re_ - e) <= 1e-5 * e and np.allclose(rR, R1, atol=1e-5) and np.allclose(rt, t1, atol=1e-5)
     ref.close()
+
+
+# ---- device-side constructor preprocessing (fgoicp.cpp:176-287) ------------------------------
+
+def _raw_clouds(nt, ns, seed):
+    rng = np.random.default_rng(seed)
+    model = (rng.normal(size=(nt, 3)) * [40, 25, 60] + [7, -300, 1e3]).astype(np.float32)
+    data = (rng.normal(size=(ns, 3)) * [35, 20, 50] + [-3, 12, -90]).astype(np.float32)
+    return model, data
+
+
+@pytest.mark.parametrize("nt,ns", [(1, 2), (3, 2), (1023, 1024), (1025, 2049), (5000, 700), (110_000, 10_000),
+                                   (1_000_003, 250_001)])
+def test_device_preprocess_is_bit_exact(nt, ns):
+    """Reference mode: centred + scaled clouds, both offsets, the scale and the target's range carry the SAME BITS as
+    the oracle's serial fp32 restatement (centroid = sequential sum in index order).  Sizes straddle the kernel's
+    1024-point tiles."""
+    model, data = _raw_clouds(nt, ns, nt + ns)
+    want = O.preprocess(model, data)
+    got = capi.preprocess(model, data)
+    for k in ("model", "data", "offset_pcs", "offset_pct", "bbox_min", "bbox_max"):
+        assert np.array_equal(got[k], want[k]), k
+    assert np.float32(got["scale"]) == np.float32(want["scale"])
+    assert got["device_ms"] > 0
+
+
+def test_device_preprocess_on_device_buffers():
+    import torch
+    model, data = _raw_clouds(20_000, 3_000, 3)
+    want = O.preprocess(model, data)
+    dm, dd = torch.from_numpy(model).cuda(), torch.from_numpy(data).cuda()
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        got = capi.preprocess_dev(dm.data_ptr(), len(model), dd.data_ptr(), len(data), cuda_stream_ptr=st.cuda_stream)
+    assert np.array_equal(dm.cpu().numpy(), want["model"]) and np.array_equal(dd.cpu().numpy(), want["data"])
+    assert np.array_equal(got["offset_pcs"], want["offset_pcs"]) and np.array_equal(got["bbox_max"], want["bbox_max"])
+
+
+def test_device_preprocess_options():
+    """TREE_CENTROID: deterministic fp64 reduction, within 1 fp32 ulp of the exact mean (NOT the reference's bits);
+    SCALE_BOTH: both clouds inside [-1, 1]^3 (the translation domain, fgoicp.cpp:113)."""
+    model, data = _raw_clouds(300_000, 40_000, 9)
+    a = capi.preprocess(model, data, flags=capi.PRE_TREE_CENTROID)
+    b = capi.preprocess(model, data, flags=capi.PRE_TREE_CENTROID)
+    for k in ("model", "data", "offset_pcs", "offset_pct"):
+        assert np.array_equal(a[k], b[k])                                       # repeatable bit for bit
+    for k, cloud in (("offset_pcs", data), ("offset_pct", model)):
+        exact = -cloud.astype(np.float64).mean(0)
+        assert np.all(np.abs(a[k] - exact) <= np.spacing(np.abs(exact).astype(np.float32)))
+    ref = O.preprocess(model, data)
+    assert np.max(np.abs(ref["model"])) > 1.0                                   # the reference lets the target stick out
+    c = capi.preprocess(model, data, flags=capi.PRE_SCALE_BOTH)
+    assert np.max(np.abs(c["model"])) <= 1.0 and np.max(np.abs(c["data"])) <= 1.0
+    assert max(np.max(np.abs(c["model"])), np.max(np.abs(c["data"]))) == 1.0
+    assert np.array_equal(c["offset_pct"], ref["offset_pct"])                   # centring unchanged
+
+
+def test_run_with_device_preprocess_is_identical():
+    from fast_go_icp_b200 import driver
+    w = workloads.synthetic_pair(nt=4000, ns=500, sigma=0.005, seed=8, max_angle=0.8)
+    out = []
+    for dev in (False, True):
+        g = driver.FastGoICP(w["model"], w["data"], 0.02, 1e-4, device_preprocess=dev)
+        R, t = g.run()
+        out.append((R, t, g.best_sse))
+        g.close()
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1]) and out[0][2] == out[1][2]

@@ -9,7 +9,7 @@
 // the reference accumulates as a serial fp32 sum in index order.  The default mode reproduces that sum bit for bit:
 // one block per cloud streams 1024-point tiles through shared memory (all threads load the next tile while three
 // lanes -- one per coordinate -- run the dependent fp32 add chains over the current one).  The chain costs one FADD
-// latency (~4 cycles) per point: 0.25 ms for 110k points.  FGOICP_PRE_TREE_CENTROID swaps it for a deterministic
+// latency (~4 cycles) per point.  FGOICP_PRE_TREE_CENTROID swaps it for a deterministic
 // parallel fp64 reduction (fixed partition, fixed combination order) for clouds of millions of points; the centroid
 // then differs from the reference's in the last fp32 bits.
 #include "common.cuh"
@@ -53,11 +53,21 @@ namespace
     }
 
     // Serial fp32 sum in index order (fgoicp.cpp:180-185), then centroid /= n (fgoicp.cpp:186).
-    // blockIdx.x selects the cloud.
+    // blockIdx.x selects the cloud.  The tile is stored per coordinate (x[], y[], z[]) so that lane a < 3 reads four
+    // consecutive values of coordinate a with one 128-bit shared-memory load; loads run 16 adds ahead of their use
+    // in two alternating register sets, so the chain advances at one FADD latency per point.
+    constexpr int SOA_STRIDE = TILE_PTS + 44;   // multiple of 4 (float4 alignment), 12 mod 32 (bank spread), >= 16 floats of slack for the read-ahead
+
+    __device__ __forceinline__ float chain4(float s, const float4& v)
+    {
+        s = __fadd_rn(s, v.x); s = __fadd_rn(s, v.y); s = __fadd_rn(s, v.z); s = __fadd_rn(s, v.w);
+        return s;
+    }
+
     __global__ void __launch_bounds__(SEQ_THREADS) k_pre_centroid_seq(const float* __restrict__ pts0, size_t n0,
                                                                       const float* __restrict__ pts1, size_t n1, PreDev* out)
     {
-        __shared__ float tile[2][TILE_F];
+        __shared__ __align__(16) float tile[2][3 * SOA_STRIDE];
         const float* pts = blockIdx.x == 0 ? pts0 : pts1;
         const size_t n = blockIdx.x == 0 ? n0 : n1;
         const size_t nf = n * 3;
@@ -77,7 +87,11 @@ namespace
         auto stash = [&](int buf)
         {
 #pragma unroll
-            for (int k = 0; k < F_PER_THREAD; ++k) tile[buf][k * SEQ_THREADS + tid] = reg[k];
+            for (int k = 0; k < F_PER_THREAD; ++k)
+            {
+                int li = k * SEQ_THREADS + tid;             // flat index inside the tile: point li / 3, coordinate li % 3
+                tile[buf][(li % 3) * SOA_STRIDE + li / 3] = reg[k];
+            }
         };
 
         const size_t ntiles = (nf + TILE_F - 1) / TILE_F;
@@ -90,17 +104,27 @@ namespace
             if (tid < 3)
             {
                 size_t left = n - t * TILE_PTS;
-                int cnt = left < (size_t)TILE_PTS ? (int)left : TILE_PTS;
-                const float* p = &tile[cur][tid];
-                int j = 0;
-                for (; j + 8 <= cnt; j += 8)
+                const float* p = &tile[cur][tid * SOA_STRIDE];
+                if (left >= (size_t)TILE_PTS)
                 {
-                    float v0 = p[3 * j], v1 = p[3 * j + 3], v2 = p[3 * j + 6], v3 = p[3 * j + 9];
-                    float v4 = p[3 * j + 12], v5 = p[3 * j + 15], v6 = p[3 * j + 18], v7 = p[3 * j + 21];
-                    s = __fadd_rn(s, v0); s = __fadd_rn(s, v1); s = __fadd_rn(s, v2); s = __fadd_rn(s, v3);
-                    s = __fadd_rn(s, v4); s = __fadd_rn(s, v5); s = __fadd_rn(s, v6); s = __fadd_rn(s, v7);
+                    const float4* q = reinterpret_cast<const float4*>(p);
+                    float4 a0 = q[0], a1 = q[1], a2 = q[2], a3 = q[3];
+#pragma unroll 1
+                    for (int g = 0; g < TILE_PTS / 32; ++g)
+                    {
+                        const float4 b0 = q[8 * g + 4], b1 = q[8 * g + 5], b2 = q[8 * g + 6], b3 = q[8 * g + 7];
+                        s = chain4(chain4(chain4(chain4(s, a0), a1), a2), a3);
+                        a0 = q[8 * g + 8]; a1 = q[8 * g + 9]; a2 = q[8 * g + 10]; a3 = q[8 * g + 11];   // last pass reads the slack
+                        s = chain4(chain4(chain4(chain4(s, b0), b1), b2), b3);
+                    }
                 }
-                for (; j < cnt; ++j) s = __fadd_rn(s, p[3 * j]);
+                else
+                {
+                    const int cnt = (int)left;
+                    int j = 0;
+                    for (; j + 4 <= cnt; j += 4) s = chain4(s, *reinterpret_cast<const float4*>(p + j));
+                    for (; j < cnt; ++j) s = __fadd_rn(s, p[j]);
+                }
             }
             if (t + 1 < ntiles) stash(cur ^ 1);
             __syncthreads();

@@ -22,7 +22,7 @@ EXPORTS = [
     "fgoicp_set_sampler", "fgoicp_set_trim", "fgoicp_set_stream", "fgoicp_set_nn_mode", "fgoicp_set_phased", "fgoicp_set_bnb_mode", "fgoicp_gather_probe", "fgoicp_lut_download", "fgoicp_lut_sample", "fgoicp_rot_sin",
     "fgoicp_bounds_batch", "fgoicp_bounds_multi", "fgoicp_bounds_multi_dev", "fgoicp_sse", "fgoicp_nn",
     "fgoicp_icp", "fgoicp_bnb_r3", "fgoicp_bnb_r3_batch", "fgoicp_so3_level_ub", "fgoicp_so3_level_lb",
-    "fgoicp_preprocess", "fgoicp_preprocess_dev",
+    "fgoicp_preprocess", "fgoicp_preprocess_dev", "fgoicp_icp_batch",
 ]
 PRE_REFERENCE, PRE_TREE_CENTROID, PRE_SCALE_BOTH = 0, 1, 2
 
@@ -87,6 +87,7 @@ def lib():
     L.fgoicp_nn.argtypes = [vp, _f32p, _f32p, C.c_int, vp, vp]
     L.fgoicp_icp.argtypes = [vp, _f32p, _f32p, C.c_int, C.c_float, C.POINTER(C.c_float), _f32p, _f32p,
                              C.POINTER(C.c_int)]
+    L.fgoicp_icp_batch.argtypes = [vp, _f32p, _f32p, C.c_int, C.c_int, C.c_float, _f32p, _f32p, _f32p, vp]
     L.fgoicp_bnb_r3.argtypes = [vp, _f32p, C.c_int, C.c_float, C.c_float, C.POINTER(C.c_float), _f32p,
                                 C.POINTER(C.c_uint64)]
     L.fgoicp_bnb_r3_batch.argtypes = [vp, _f32p, C.c_int, C.c_int, C.c_float, C.c_float, _f32p, _f32p, vp]
@@ -257,6 +258,16 @@ class Context:
         _check(lib().fgoicp_icp(self._h, _f32(R0).reshape(9), _f32(t0), int(max_iter), float(thr), C.byref(e),
                                 R, t, C.byref(it)), "fgoicp_icp")
         return e.value, R, t, it.value
+
+    def icp_batch(self, R0s, t0s, max_iter, thr):
+        """n refinements at once (fgoicp_icp_batch): returns sse[n], R[n][9], t[n][3], iters[n]."""
+        R0s, t0s = _f32(R0s).reshape(-1, 9), _f32(t0s).reshape(-1, 3)
+        n = len(R0s)
+        e, R, t = np.zeros(n, np.float32), np.zeros((n, 9), np.float32), np.zeros((n, 3), np.float32)
+        it = np.zeros(n, np.int32)
+        _check(lib().fgoicp_icp_batch(self._h, R0s, t0s, n, int(max_iter), float(thr), e, R, t, it.ctypes.data),
+               "fgoicp_icp_batch")
+        return e, R, t, it
 
     def bnb_r3(self, rot_cube, fix_rot, best_sse, sse_threshold):
         bt = np.zeros(3, np.float32)

@@ -46,7 +46,16 @@ struct IcpInst
 {
     IcpState st;
     float pose0[12];             // seed pose (R0 column-major, t0)
+    int job;                     // index of the refinement this slot is running (-1: none)
+    int fresh;                   // 1: seeded by the last loop head; the next loop body starts with W = pose0 * data
 };
+
+// Slot pool with a device-side job queue: a batch of n refinements runs on S <= n instance slots.  The loop head of
+// a slot that has just finished publishes its result and seeds the slot with the next pending job, so every slot
+// stays busy until the queue is empty and the host only polls `finished` (no per-job host round trip, and a long
+// refinement no longer holds 63 finished neighbours hostage).
+struct IcpQueue { int n_jobs, next, finished, pad; };
+struct IcpResult { float sse, R[9], t[3]; int iters; };
 #define ICP_INST_BYTES 512
 static_assert(sizeof(IcpInst) <= ICP_INST_BYTES, "IcpInst must fit its slot");
 #define ICP_MAX_BATCH 64
@@ -477,15 +486,16 @@ k_icp_select(const unsigned long long* __restrict__ keys_base, int ns, char* ins
 
 // ---- ICP -----------------------------------------------------------------------------------
 
-__global__ void k_icp_init(char* inst_base, int max_iter, float thr)
+__device__ __forceinline__ void fg_icp_seed(IcpInst* in, const float* __restrict__ seed, int job, int max_iter, float thr)
 {
-    IcpInst* in = fg_inst(inst_base, blockIdx.x);
     IcpState* st = &in->st;
-    for (int k = 0; k < 9; ++k) { st->R[k] = in->pose0[k]; st->lastR[k] = in->pose0[k]; }
-    for (int k = 0; k < 3; ++k) { st->t[k] = in->pose0[9 + k]; st->lastT[k] = in->pose0[9 + k]; }
+    for (int k = 0; k < 12; ++k) in->pose0[k] = seed[k];
+    for (int k = 0; k < 9; ++k) { st->R[k] = seed[k]; st->lastR[k] = seed[k]; }
+    for (int k = 0; k < 3; ++k) { st->t[k] = seed[9 + k]; st->lastT[k] = seed[9 + k]; }
     st->sse = FG_INF; st->last_sse = __fmul_rn(2.0f, FG_INF);      // icp3d.cu:89-90
     st->thr = thr; st->iter = 0; st->max_iter = max_iter; st->done = 0;
     st->out_iters = 0;
+    in->job = job; in->fresh = 1;
 }
 
 // W_i = R * p_i + t  (icp3d.cu:85 with the seed pose; :100 with the increment, in place)
@@ -507,10 +517,8 @@ __global__ void k_icp_transform(const float4* __restrict__ data, float4* work_ba
 }
 
 // loop head: while (iter++ < max_iter && (last_sse - sse) > thr * last_sse)   (icp3d.cu:94-98)
-__global__ void k_icp_begin(char* inst_base)
+__device__ __forceinline__ void fg_icp_loop_head(IcpState* st)
 {
-    IcpState* st = &fg_inst(inst_base, blockIdx.x)->st;
-    if (st->done) return;
     bool go = (st->iter++ < st->max_iter) &&
               (__fsub_rn(st->last_sse, st->sse) > __fmul_rn(st->thr, st->last_sse));
     if (!go)
@@ -527,6 +535,57 @@ __global__ void k_icp_begin(char* inst_base)
     st->last_sse = st->sse;
     for (int k = 0; k < 9; ++k) st->lastR[k] = st->R[k];
     for (int k = 0; k < 3; ++k) st->lastT[k] = st->t[k];
+}
+
+// First jobs of a batch: slot k runs job k.
+__global__ void k_icp_assign(char* inst_base, const float* __restrict__ jobs, int max_iter, float thr)
+{
+    IcpInst* in = fg_inst(inst_base, blockIdx.x);
+    fg_icp_seed(in, jobs + 12 * blockIdx.x, (int)blockIdx.x, max_iter, thr);
+    fg_icp_loop_head(&in->st);                                   // loop head of iteration 1
+}
+
+// Start of every loop body: slots seeded by the last loop head get W = pose0 * data (icp3d.cu:85) and an empty
+// winner list (no warm start for the first search).
+__global__ void k_icp_prepare(const float4* __restrict__ data, float4* work_base, unsigned long long* keys_base, int ns,
+                              char* inst_base)
+{
+    IcpInst* inst = fg_inst(inst_base, blockIdx.y);
+    if (!inst->fresh || inst->st.done) return;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ns) return;
+    const float* pose = inst->pose0;
+    float R[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) R[k] = pose[k];
+    float4 p = data[i];
+    float3 rp = fg_rotate(R, p.x, p.y, p.z);
+    work_base[(size_t)blockIdx.y * ns + i] = make_float4(__fadd_rn(rp.x, pose[9]), __fadd_rn(rp.y, pose[10]), __fadd_rn(rp.z, pose[11]), p.w);
+    keys_base[(size_t)blockIdx.y * ns + i] = 0xffffffffffffffffull;
+}
+
+// End of every loop body: loop head of the next iteration; a slot whose refinement has ended publishes the result
+// and takes the next pending job.
+__global__ void k_icp_next(char* inst_base, const float* __restrict__ jobs, IcpResult* __restrict__ results,
+                           IcpQueue* q, int max_iter, float thr)
+{
+    IcpInst* in = fg_inst(inst_base, blockIdx.x);
+    IcpState* st = &in->st;
+    in->fresh = 0;
+    if (!st->done) fg_icp_loop_head(st);
+    while (st->done && in->job >= 0)
+    {
+        IcpResult* r = results + in->job;
+        r->sse = st->out_sse; r->iters = st->out_iters;
+        for (int k = 0; k < 9; ++k) r->R[k] = st->outR[k];
+        for (int k = 0; k < 3; ++k) r->t[k] = st->outT[k];
+        __threadfence();
+        atomicAdd(&q->finished, 1);
+        int j = atomicAdd(&q->next, 1);
+        if (j >= q->n_jobs) { in->job = -1; break; }
+        fg_icp_seed(in, jobs + 12 * j, j, max_iter, thr);
+        fg_icp_loop_head(st);                                    // loop head of iteration 1 (ends at once if max_iter == 0)
+    }
 }
 
 // ---- Procrustes step over ICP_NB blocks per instance ------------------------------------------------------
@@ -775,69 +834,108 @@ extern "C" int fgoicp_nn(fgoicp_ctx* c, const float R[9], const float t[3], int 
     return FGOICP_OK;
 }
 
-// Runs n independent ICPs to completion, concurrently (instance = blockIdx.y / blockIdx.x of every kernel).
+// Number of instance slots a batch runs on (FGOICP_ICP_SLOTS overrides, 1..256).
+static int icp_slots(const fgoicp_ctx* c)
+{
+    int s = ICP_MAX_BATCH;
+    if (const char* e = getenv("FGOICP_ICP_SLOTS")) s = std::min(256, std::max(1, atoi(e)));
+    while (s > 1 && (size_t)s * c->ns * 25 > ((size_t)1 << 30)) s /= 2;         // 25 bytes per slot and data point
+    return s;
+}
+
+static int ensure_icp_jobs(fgoicp_ctx* c, int n)
+{
+    size_t need = sizeof(IcpQueue) + (size_t)n * (12 * sizeof(float) + sizeof(IcpResult));
+    if (need <= c->icp_jobs_bytes) return FGOICP_OK;
+    FG_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(c->d_icp_jobs); c->d_icp_jobs = nullptr; c->icp_jobs_bytes = 0;
+    need = std::max(need * 2, (size_t)1 << 20);
+    FG_CUDA(cudaMalloc(&c->d_icp_jobs, need));
+    c->icp_jobs_bytes = need;
+    return FGOICP_OK;
+}
+
+// Runs n independent ICPs to completion on a pool of instance slots (instance = blockIdx.y / blockIdx.x of every
+// kernel); finished slots pull the next pending job on the device (k_icp_next).
 // R0s[n][9], t0s[n][3] -> sse[n], R[n][9], t[n][3], iters[n].  Used by fgoicp_icp and by the level driver.
 int fg_icp_run_batch(fgoicp_ctx* c, const float* R0s, const float* t0s, int n, int max_iter, float thr,
                      float* sse, float* R, float* t, int* iters)
 {
     FG_RANGE("fgoicp icp batch");
-    for (int base = 0; base < n; base += ICP_MAX_BATCH)
+    if (n <= 0) return FGOICP_OK;
+    const int S = std::min(n, icp_slots(c));
+    int rc = ensure_icp_capacity(c, S);
+    if (rc) return rc;
+    rc = ensure_icp_jobs(c, n);
+    if (rc) return rc;
+    rc = fg::ensure_pinned(c, (size_t)n * (12 * sizeof(float) + sizeof(IcpResult)) + 8192);
+    if (rc) return rc;
+    // device layout: queue | seeds[n][12] | results[n]
+    IcpQueue* d_q = (IcpQueue*)c->d_icp_jobs;
+    float* d_seeds = (float*)((char*)c->d_icp_jobs + sizeof(IcpQueue));
+    IcpResult* d_res = (IcpResult*)(d_seeds + 12 * (size_t)n);
+    IcpQueue* hq = (IcpQueue*)c->h_pinned;
+    float* hseeds = (float*)((char*)c->h_pinned + 4096);
+    for (int k = 0; k < n; ++k)
     {
-        int m = std::min(ICP_MAX_BATCH, n - base);
-        int rc = upload_seeds(c, R0s + 9 * base, t0s + 3 * base, m);
-        if (rc) return rc;
-        char* inst = (char*)c->d_icp;
-        int ns = (int)c->ns;
-        dim3 pgrid((unsigned)((ns + 255) / 256), (unsigned)m);
-        FG_CUDA(cudaMemsetAsync(c->d_nnkey, 0xff, sizeof(unsigned long long) * (size_t)ns * m, c->stream));   // no previous winners yet
-        k_icp_init<<<m, 1, 0, c->stream>>>(inst, max_iter, thr);
-        k_icp_transform<<<pgrid, 256, 0, c->stream>>>(c->d_data, c->d_work, ns, inst, SRC_DATA, POSE_SEED, 0);   // icp3d.cu:85
-        k_icp_begin<<<m, 1, 0, c->stream>>>(inst);           // loop head of iteration 1
-        FG_CUDA(cudaGetLastError());
-        char* hinst = (char*)c->h_pinned + 4096;
-        const int burst = 8;     // iterations enqueued between polls of the done flags (finished instances cost only empty launches)
-        bool all_done = false;
-        for (int guard = 0; guard <= max_iter + burst && !all_done; guard += burst)
+        memcpy(hseeds + 12 * (size_t)k, R0s + 9 * (size_t)k, 9 * sizeof(float));
+        memcpy(hseeds + 12 * (size_t)k + 9, t0s + 3 * (size_t)k, 3 * sizeof(float));
+    }
+    hq->n_jobs = n; hq->next = S; hq->finished = 0; hq->pad = 0;
+    FG_CUDA(cudaMemcpyAsync(d_q, hq, sizeof(IcpQueue), cudaMemcpyHostToDevice, c->stream));
+    FG_CUDA(cudaMemcpyAsync(d_seeds, hseeds, 12 * sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+
+    char* inst = (char*)c->d_icp;
+    const int ns = (int)c->ns;
+    dim3 pgrid((unsigned)((ns + 255) / 256), (unsigned)S);
+    k_icp_assign<<<S, 1, 0, c->stream>>>(inst, d_seeds, max_iter, thr);
+    FG_CUDA(cudaGetLastError());
+    // iterations enqueued between polls of the queue (finished slots with no job left cost only empty launches)
+    const int burst = 8;
+    const long long guard_max = ((long long)(n + S - 1) / S + 1) * ((long long)max_iter + 2) + burst;
+    bool all_done = false;
+    for (long long guard = 0; guard <= guard_max && !all_done; guard += burst)
+    {
+        for (int b = 0; b < burst; ++b)
         {
-            for (int b = 0; b < burst; ++b)
+            k_icp_prepare<<<pgrid, 256, 0, c->stream>>>(c->d_data, c->d_work, c->d_nnkey, ns, inst);             // icp3d.cu:85
+            // one loop body per slot still running; every kernel returns at once for idle ones
+            rc = enqueue_nn(c, S, SRC_WORK, POSE_NONE, 1, 1);                                        // icp3d.cu:146
+            if (rc) return rc;
+            const unsigned char* inl = nullptr;
+            int n_in = ns;
+            if (c->trim_k > 0 && c->trim_k < c->ns)
             {
-                // one loop body per instance still running; every kernel returns at once for finished ones
-                rc = enqueue_nn(c, m, SRC_WORK, POSE_NONE, 1, 1);                                        // icp3d.cu:146
-                if (rc) return rc;
-                const unsigned char* inl = nullptr;
-                int n_in = ns;
-                if (c->trim_k > 0 && c->trim_k < c->ns)
-                {
-                    // trimmed registration: the Procrustes step sees the trim_k closest correspondences only
-                    k_icp_select<<<m, 1024, 0, c->stream>>>(c->d_nnkey, ns, inst, (unsigned int)c->trim_k, c->d_inl, c->d_data_orig);
-                    inl = c->d_inl; n_in = (int)c->trim_k;
-                }
-                double* part = (double*)c->d_icp_part;
-                unsigned int* counters = (unsigned int*)((char*)c->d_icp_part + sizeof(double) * ICP_NB * ICP_PART * (size_t)c->icp_capacity);
-                dim3 rgrid(ICP_NB, (unsigned)m);
-                k_icp_centroids<<<rgrid, ICP_BT, 0, c->stream>>>(c->d_work, c->d_nnkey, c->d_model, ns, inst, inl, n_in, part, counters);
-                k_icp_procrustes<<<rgrid, ICP_BT, 0, c->stream>>>(c->d_work, c->d_nnkey, c->d_model, ns, inst, inl, part, counters);
-                k_icp_transform<<<pgrid, 256, 0, c->stream>>>(c->d_data, c->d_work, ns, inst, SRC_WORK, POSE_INC, 1);  // icp3d.cu:100
-                rc = enqueue_nn(c, m, SRC_DATA, POSE_CUR, 0, 1);                                         // icp3d.cu:103
-                if (rc) return rc;
-                k_sse_reduce<<<m, 1024, 0, c->stream>>>(c->d_nnkey, ns, inst, 1, nullptr, (unsigned int)c->trim_k);
-                k_icp_begin<<<m, 1, 0, c->stream>>>(inst);   // loop head of the next iteration (or publish the result)
-                FG_CUDA(cudaGetLastError());
+                // trimmed registration: the Procrustes step sees the trim_k closest correspondences only
+                k_icp_select<<<S, 1024, 0, c->stream>>>(c->d_nnkey, ns, inst, (unsigned int)c->trim_k, c->d_inl, c->d_data_orig);
+                inl = c->d_inl; n_in = (int)c->trim_k;
             }
-            FG_CUDA(cudaMemcpyAsync(hinst, inst, (size_t)ICP_INST_BYTES * m, cudaMemcpyDeviceToHost, c->stream));
-            FG_CUDA(cudaStreamSynchronize(c->stream));
-            all_done = true;
-            for (int k = 0; k < m; ++k) all_done = all_done && ((IcpInst*)(hinst + (size_t)k * ICP_INST_BYTES))->st.done;
+            double* part = (double*)c->d_icp_part;
+            unsigned int* counters = (unsigned int*)((char*)c->d_icp_part + sizeof(double) * ICP_NB * ICP_PART * (size_t)c->icp_capacity);
+            dim3 rgrid(ICP_NB, (unsigned)S);
+            k_icp_centroids<<<rgrid, ICP_BT, 0, c->stream>>>(c->d_work, c->d_nnkey, c->d_model, ns, inst, inl, n_in, part, counters);
+            k_icp_procrustes<<<rgrid, ICP_BT, 0, c->stream>>>(c->d_work, c->d_nnkey, c->d_model, ns, inst, inl, part, counters);
+            k_icp_transform<<<pgrid, 256, 0, c->stream>>>(c->d_data, c->d_work, ns, inst, SRC_WORK, POSE_INC, 1);  // icp3d.cu:100
+            rc = enqueue_nn(c, S, SRC_DATA, POSE_CUR, 0, 1);                                         // icp3d.cu:103
+            if (rc) return rc;
+            k_sse_reduce<<<S, 1024, 0, c->stream>>>(c->d_nnkey, ns, inst, 1, nullptr, (unsigned int)c->trim_k);
+            k_icp_next<<<S, 1, 0, c->stream>>>(inst, d_seeds, d_res, d_q, max_iter, thr);   // loop head of the next iteration / next job
+            FG_CUDA(cudaGetLastError());
         }
-        if (!all_done) { fg::set_error("ICP loop did not terminate"); return FGOICP_ERR_STATE; }
-        for (int k = 0; k < m; ++k)
-        {
-            const IcpState& st = ((IcpInst*)(hinst + (size_t)k * ICP_INST_BYTES))->st;
-            if (sse) sse[base + k] = st.out_sse;
-            if (R) memcpy(R + 9 * (base + k), st.outR, 9 * sizeof(float));
-            if (t) memcpy(t + 3 * (base + k), st.outT, 3 * sizeof(float));
-            if (iters) iters[base + k] = st.out_iters;
-        }
+        FG_CUDA(cudaMemcpyAsync(hq, d_q, sizeof(IcpQueue), cudaMemcpyDeviceToHost, c->stream));
+        FG_CUDA(cudaStreamSynchronize(c->stream));
+        all_done = hq->finished >= n;
+    }
+    if (!all_done) { fg::set_error("ICP loop did not terminate"); return FGOICP_ERR_STATE; }
+    IcpResult* hres = (IcpResult*)((char*)c->h_pinned + 4096);
+    FG_CUDA(cudaMemcpyAsync(hres, d_res, sizeof(IcpResult) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    FG_CUDA(cudaStreamSynchronize(c->stream));
+    for (int k = 0; k < n; ++k)
+    {
+        if (sse) sse[k] = hres[k].sse;
+        if (R) memcpy(R + 9 * (size_t)k, hres[k].R, 9 * sizeof(float));
+        if (t) memcpy(t + 3 * (size_t)k, hres[k].t, 3 * sizeof(float));
+        if (iters) iters[k] = hres[k].iters;
     }
     return FGOICP_OK;
 }
@@ -855,4 +953,16 @@ extern "C" int fgoicp_icp(fgoicp_ctx* c, const float R0[9], const float t0[3], i
     FG_ARG(max_iter >= 0, "max_iter must be non-negative");
     FG_CUDA(cudaSetDevice(c->device));
     return fg_icp_run_batch(c, R0, t0, 1, max_iter, thr, sse, R, t, iters);
+}
+
+extern "C" int fgoicp_icp_batch(fgoicp_ctx* c, const float* R0s, const float* t0s, int n, int max_iter, float thr,
+                                float* sse, float* R, float* t, int* iters)
+{
+    FG_ARG(c, "NULL context");
+    FG_ARG(n >= 0, "n must be non-negative");
+    FG_ARG(max_iter >= 0, "max_iter must be non-negative");
+    if (n == 0) return FGOICP_OK;
+    FG_ARG(R0s && t0s, "NULL pointer");
+    FG_CUDA(cudaSetDevice(c->device));
+    return fg_icp_run_batch(c, R0s, t0s, n, max_iter, thr, sse, R, t, iters);
 }

@@ -180,6 +180,13 @@ int fgoicp_nn(fgoicp_ctx* ctx, const float R[9], const float t[3], int rooted,
 int fgoicp_icp(fgoicp_ctx* ctx, const float R0[9], const float t0[3], int max_iter, float thr,
                float* sse, float R[9], float t[3], int* iters);
 
+/* n independent refinements (one IterativeClosestPoint3D(...).run() each, icp3d.cu:55-108) from the seed poses
+ * R0s[n][9], t0s[n][3], run concurrently on a pool of instance slots; a slot that finishes takes the next pending
+ * seed on the device.  Every output equals what fgoicp_icp returns for that seed alone.
+ * Outputs (each may be NULL): sse[n], R[n][9], t[n][3], iters[n]. */
+int fgoicp_icp_batch(fgoicp_ctx* ctx, const float* R0s, const float* t0s, int n, int max_iter, float thr,
+                     float* sse, float* R, float* t, int* iters);
+
 /* FastGoICP::branch_and_bound_R3(rnode, fix_rot)  (fgoicp.cpp:102-174) as a GPU-resident
  * best-first search: pool, batch selection, bound evaluation, pruning and child spawning all
  * stay on the device.  best_sse seeds best_error (fgoicp.cpp:104).  Outputs the reference's

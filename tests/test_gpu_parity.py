@@ -355,3 +355,31 @@ def test_run_with_device_preprocess_is_identical():
         out.append((R, t, g.best_sse))
         g.close()
     assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1]) and out[0][2] == out[1][2]
+
+
+# ---- batched refinements on a slot pool with a device-side job queue -------------------------------------------
+
+def test_icp_batch_equals_single_refinements(small_problem, gpu_ctx, monkeypatch):
+    """23 seeds on 4 (then 64) instance slots: every slot is refilled several times on the device; each result must
+    carry the same bits as the refinement run alone (IterativeClosestPoint3D.run(), icp3d.cu:55-108)."""
+    rng = np.random.default_rng(31)
+    seeds_R, seeds_t = [], []
+    for k in range(23):
+        v = rng.uniform(-0.45, 0.45, 3) * (0.1 if k % 3 == 0 else 1.0)      # easy and hard starts -> very different iteration counts
+        R, _ = O.rotation(*v.astype(np.float32))
+        seeds_R.append(R)
+        seeds_t.append(rng.uniform(-0.2, 0.2, 3).astype(np.float32))
+    single = [gpu_ctx.icp(R, t, 100, 0.005) for R, t in zip(seeds_R, seeds_t)]
+    assert len({s[3] for s in single}) > 3                                    # iteration counts do differ
+    for slots in ("4", "1", "64"):
+        monkeypatch.setenv("FGOICP_ICP_SLOTS", slots)
+        e, R, t, it = gpu_ctx.icp_batch(np.array(seeds_R), np.array(seeds_t), 100, 0.005)
+        for k, (se, sR, st, sit) in enumerate(single):
+            assert it[k] == sit and e[k] == np.float32(se), (slots, k)
+            assert np.array_equal(R[k], sR) and np.array_equal(t[k], st), (slots, k)
+    monkeypatch.delenv("FGOICP_ICP_SLOTS")
+    # max_iter = 0 ends at the first loop head: seed pose, zero iterations (icp3d.cu:94, 106-107)
+    e, R, t, it = gpu_ctx.icp_batch(np.array(seeds_R[:5]), np.array(seeds_t[:5]), 0, 0.005)
+    assert np.all(it == 0) and np.array_equal(R, np.array(seeds_R[:5]).reshape(5, 9)) and np.all(e == np.float32(1e10))
+    e0 = gpu_ctx.icp_batch(np.zeros((0, 9), np.float32), np.zeros((0, 3), np.float32), 10, 0.005)[0]
+    assert len(e0) == 0

@@ -155,6 +155,7 @@ struct fgoicp_ctx
     unsigned long long* d_nnkey = nullptr;    // packed (value bits << 32 | index) [ns]
     void* d_icp = nullptr;                    // per-instance ICP state blocks, see nn_icp.cu
     int icp_capacity = 0;                     // concurrent ICP instances the three buffers are sized for
+    float4* d_nnmemo = nullptr;               // winner memo of the ICP searches: scan position + proven clearance [icp_capacity][ns]
     void* d_icp_jobs = nullptr;               // job queue of a batch of refinements: counters, seed poses, results (nn_icp.cu)
     size_t icp_jobs_bytes = 0;
 };

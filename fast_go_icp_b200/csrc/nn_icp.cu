@@ -187,6 +187,14 @@ __device__ __forceinline__ float fg_sqrt_preimage_hi(float s)
     return x;
 }
 
+// squared search radius once a candidate at squared distance d2 is known: its distance plus the winner-memo margin
+__device__ __forceinline__ float fg_shrink(float d2, float margin)
+{
+    if (margin <= 0.0f) return d2 * 1.00002f + 1e-12f;
+    const float r = sqrtf(d2) + margin;
+    return r * r * 1.00002f + 1e-12f;
+}
+
 // Exact NN through the uniform cell grid, one WARP per query.
 //   1. The dense distance grid gives a tight search radius for free: the grid node n nearest to q has a
 //      model point within sqrt(T[n]), so the NN of q lies within U = sqrt(T[n]) + |q - x_n|.
@@ -203,6 +211,12 @@ __device__ __forceinline__ float fg_sqrt_preimage_hi(float s)
 #ifndef NN_LPQ
 #define NN_LPQ 32           // lanes per query (32, 16 or 8); measured on W5: 32 -> 56 ms, 16 -> 71 ms, 8 -> 93 ms of NN time per run()
 #endif
+#ifndef FG_NN_MARGIN
+#define FG_NN_MARGIN 2.5e-4f  // winner-memo scan margin in normalised units (0 disables the memo; env FGOICP_NN_MARGIN overrides)
+#endif
+#ifndef NN_RPL
+#define NN_RPL 1            // rows per lane and pass of the cell-grid search; measured on the dragon pair (W3, ICP ms): 1 -> 3688, 4 -> 3873, 8 -> 4101
+#endif
 #ifndef NN_FAST_ROOTED
 #define NN_FAST_ROOTED 1      // 0: always the exact rooted scan (measured: ICP 86 -> 71 ms on W5 with 1)
 #endif
@@ -210,13 +224,14 @@ template <int ROOTED>
 __global__ void __launch_bounds__(NNG_WARPS * 32)
 k_nn_grid(CellGrid g, LutDev L, float res, const float4* __restrict__ data, const float4* __restrict__ work_base,
           int ns, char* inst_base, int src_sel, int pose_sel, unsigned long long* __restrict__ keys_base, int check_done,
-          const float4* __restrict__ model_by_index)
+          const float4* __restrict__ model_by_index, float4* __restrict__ memo_base, float margin)
 {
     IcpInst* inst = fg_inst(inst_base, blockIdx.y);
     if (check_done && inst->st.done) return;
     const float4* src = src_sel == SRC_DATA ? data : work_base + (size_t)blockIdx.y * ns;
     const float* pose = fg_pose(inst, pose_sel);
     unsigned long long* keys = keys_base + (size_t)blockIdx.y * ns;
+    float4* memo = memo_base ? memo_base + (size_t)blockIdx.y * ns : nullptr;
     // NN_LPQ lanes per query (a whole warp by default; smaller teams put more queries in flight but were measured
     // slower: the rows of a query are better spread over 32 lanes).  Teams of one warp never talk to each other:
     // every shuffle is confined to the team's lanes.
@@ -233,6 +248,30 @@ k_nn_grid(CellGrid g, LutDev L, float res, const float4* __restrict__ data, cons
         for (int k = 0; k < 9; ++k) R[k] = pose[k];
         float3 rp = fg_rotate(R, p.x, p.y, p.z);
         qx = __fadd_rn(rp.x, pose[9]); qy = __fadd_rn(rp.y, pose[10]); qz = __fadd_rn(rp.z, pose[11]);
+    }
+    // Winner memo (ICP loop).  The last full scan of this point, done at position memo.xyz, proved a clearance
+    // memo.w: the winner stays the unique nearest point (by a margin far above fp32 rounding, so under both tie
+    // rules) for every query within that distance of the scan position.  The two searches of an ICP iteration --
+    // composed pose on the original point (icp3d.cu:103) and the incrementally moved working copy (icp3d.cu:146) --
+    // sit a rounding error apart, and late iterations move points by less than the gap to the runner-up: such
+    // queries need one distance evaluation instead of a scan.  Only provably unchanged winners take this path.
+    if (memo && model_by_index)
+    {
+        const float4 mm = memo[i];
+        const unsigned int prev = (unsigned int)(keys[i] & 0xffffffffull);
+        if (prev != 0xffffffffu && mm.w > 0.0f)
+        {
+            const float ex = qx - mm.x, ey = qy - mm.y, ez = qz - mm.z;
+            const float moved = sqrtf(ex * ex + ey * ey + ez * ez) * 1.0001f + 1e-9f;
+            if (moved < mm.w)
+            {
+                const float4 m = __ldg(model_by_index + prev);
+                float d = fg_sq3(__fsub_rn(qx, m.x), __fsub_rn(qy, m.y), __fsub_rn(qz, m.z));
+                if (ROOTED) d = __fsqrt_rn(d);
+                if (lane == 0) keys[i] = ((unsigned long long)__float_as_uint(d) << 32) | prev;
+                return;
+            }
+        }
     }
     // LUT-space position (binning frame) and the nearest grid node
     float lx = qx + L.ox, ly = qy + L.oy, lz = qz + L.oz;
@@ -253,7 +292,7 @@ k_nn_grid(CellGrid g, LutDev L, float res, const float4* __restrict__ data, cons
         if (prev != 0xffffffffu)
         {
             float4 m = __ldg(model_by_index + prev);
-            float d0 = sqrtf(fg_sq3(__fsub_rn(qx, m.x), __fsub_rn(qy, m.y), __fsub_rn(qz, m.z))) * 1.0001f + 1e-6f;
+            float d0 = sqrtf(fg_sq3(__fsub_rn(qx, m.x), __fsub_rn(qy, m.y), __fsub_rn(qz, m.z))) * 1.0001f + 1e-6f + margin;
             U = fminf(U, d0);
         }
     }
@@ -265,12 +304,15 @@ k_nn_grid(CellGrid g, LutDev L, float res, const float4* __restrict__ data, cons
     // tracks the runner-up distance; only if that falls in the window is the query redone with the exact rule.
     const float U2_0 = U2;
     unsigned long long key = 0xffffffffffffffffull;
+    float rho = 0.0f;                                              // proven clearance of the winner (winner memo)
 #pragma unroll 1
     for (int exact = (ROOTED && NN_FAST_ROOTED) ? 0 : 1; exact < 2; ++exact)
     {
     U2 = U2_0;
+    rho = 0.0f;
     float best = FG_INF, thr_lo = (ROOTED && exact) ? fg_sqrt_preimage_lo(FG_INF) : FG_INF, thr_hi = thr_lo;
     float second = FG_INF;
+    bool tie = false;                                              // another point at exactly the lane's best distance
     int best_idx = 0x7fffffff;
 
     const float h = g.h, inv_h = g.inv_h;
@@ -280,26 +322,40 @@ k_nn_grid(CellGrid g, LutDev L, float res, const float4* __restrict__ data, cons
     const int cy1 = min(max((int)floorf((ly + U) * inv_h), 0), g.ny - 1);
     const int ny_rows = cy1 - cy0 + 1;
     const int n_rows = ny_rows * (cz1 - cz0 + 1);
-    for (int row0 = 0; row0 < n_rows; row0 += NN_LPQ)
+    // NN_RPL rows per lane and pass: the two cell-range lookups of all of them are in flight together.  Measured
+    // neutral to slightly negative (see NN_RPL above): the row lookups are not what far queries wait for.
+    for (int row0 = 0; row0 < n_rows; row0 += NN_LPQ * NN_RPL)
     {
-        int row = row0 + lane;
-        if (row < n_rows)
+        int rb[NN_RPL], re[NN_RPL];
+#pragma unroll
+        for (int r = 0; r < NN_RPL; ++r)
         {
-            int cz = cz0 + row / ny_rows, cy = cy0 + row % ny_rows;
-            // edge cells also hold points clamped into them: their slab extends to infinity
-            float zlo = cz == 0 ? -FG_INF : (float)cz * h, zhi = cz == g.nz - 1 ? FG_INF : (float)(cz + 1) * h;
-            float ylo = cy == 0 ? -FG_INF : (float)cy * h, yhi = cy == g.ny - 1 ? FG_INF : (float)(cy + 1) * h;
-            float dz = fmaxf(fmaxf(zlo - lz, lz - zhi), 0.0f);
-            float dy = fmaxf(fmaxf(ylo - ly, ly - yhi), 0.0f);
-            float dyz2 = dz * dz + dy * dy;
-            if (dyz2 <= U2)
+            rb[r] = 0; re[r] = 0;
+            const int row = row0 + r * NN_LPQ + lane;
+            if (row < n_rows)
             {
-                float wx = sqrtf(U2 - dyz2) * 1.00001f + 1e-6f;
-                int cx0 = min(max((int)floorf((lx - wx) * inv_h), 0), g.nx - 1);
-                int cx1 = min(max((int)floorf((lx + wx) * inv_h), 0), g.nx - 1);
-                int c0 = (cz * g.ny + cy) * g.nx;
-                int b = __ldg(g.start + c0 + cx0), e = __ldg(g.start + c0 + cx1 + 1);
-                for (int k = b; k < e; ++k)
+                int cz = cz0 + row / ny_rows, cy = cy0 + row % ny_rows;
+                // edge cells also hold points clamped into them: their slab extends to infinity
+                float zlo = cz == 0 ? -FG_INF : (float)cz * h, zhi = cz == g.nz - 1 ? FG_INF : (float)(cz + 1) * h;
+                float ylo = cy == 0 ? -FG_INF : (float)cy * h, yhi = cy == g.ny - 1 ? FG_INF : (float)(cy + 1) * h;
+                float dz = fmaxf(fmaxf(zlo - lz, lz - zhi), 0.0f);
+                float dy = fmaxf(fmaxf(ylo - ly, ly - yhi), 0.0f);
+                float dyz2 = dz * dz + dy * dy;
+                if (dyz2 <= U2)
+                {
+                    float wx = sqrtf(U2 - dyz2) * 1.00001f + 1e-6f;
+                    int cx0 = min(max((int)floorf((lx - wx) * inv_h), 0), g.nx - 1);
+                    int cx1 = min(max((int)floorf((lx + wx) * inv_h), 0), g.nx - 1);
+                    int c0 = (cz * g.ny + cy) * g.nx;
+                    rb[r] = __ldg(g.start + c0 + cx0); re[r] = __ldg(g.start + c0 + cx1 + 1);
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < NN_RPL; ++r)
+        {
+            {
+                for (int k = rb[r]; k < re[r]; ++k)
                 {
                     float4 m = __ldg(g.pts + k);
                     float d = fg_sq3(__fsub_rn(qx, m.x), __fsub_rn(qy, m.y), __fsub_rn(qz, m.z));
@@ -311,7 +367,7 @@ k_nn_grid(CellGrid g, LutDev L, float res, const float4* __restrict__ data, cons
                             float s = __fsqrt_rn(d);
                             best = s; best_idx = idx;
                             thr_lo = fg_sqrt_preimage_lo(s); thr_hi = fg_sqrt_preimage_hi(s);
-                            U2 = fminf(U2, thr_hi * 1.00002f + 1e-12f);
+                            U2 = fminf(U2, fg_shrink(thr_hi, margin));
                         }
                         else if (d <= thr_hi && idx < best_idx) best_idx = idx;
                     }
@@ -319,17 +375,15 @@ k_nn_grid(CellGrid g, LutDev L, float res, const float4* __restrict__ data, cons
                     {
                         // squared compare that also keeps the runner-up distance (decides below whether the
                         // rooted rule could pick another index)
-                        if (d < best) { second = best; best = d; best_idx = idx; U2 = fminf(U2, d * 1.00002f + 1e-12f); }
-                        else if (d == best) best_idx = min(best_idx, idx);
+                        if (d < best) { second = best; best = d; best_idx = idx; U2 = fminf(U2, fg_shrink(d, margin)); }
+                        else if (d == best) { best_idx = min(best_idx, idx); tie = true; }
                         else second = fminf(second, d);
                     }
                     else
                     {
-                        if (d < best || (d == best && idx < best_idx))
-                        {
-                            best = d; best_idx = idx;
-                            U2 = fminf(U2, d * 1.00002f + 1e-12f);
-                        }
+                        if (d < best) { second = best; best = d; best_idx = idx; U2 = fminf(U2, fg_shrink(d, margin)); }
+                        else if (d == best) { best_idx = min(best_idx, idx); tie = true; }
+                        else second = fminf(second, d);
                     }
                 }
             }
@@ -346,6 +400,19 @@ k_nn_grid(CellGrid g, LutDev L, float res, const float4* __restrict__ data, cons
         unsigned long long other = __shfl_xor_sync(team_mask, key, o, NN_LPQ);
         key = other < key ? other : key;
     }
+    if (memo && (!ROOTED || !exact) && key != 0xffffffffffffffffull)
+    {
+        // Clearance: every point other than the winner is either a candidate this scan has seen (runner-up distance
+        // `other`, equal to the winner's on a tie) or lies outside the final ball (all pruning is conservative by
+        // ~1e-5, taken as 1e-4 here).  Half the gap, less a slack far above the rounding of the distance formula.
+        const unsigned int win_idx = (unsigned int)(key & 0xffffffffull);
+        const float wd2 = __uint_as_float((unsigned int)(key >> 32));
+        float other = ((unsigned int)best_idx != win_idx || tie) ? best : second;
+#pragma unroll
+        for (int o = NN_LPQ / 2; o > 0; o >>= 1) other = fminf(other, __shfl_xor_sync(team_mask, other, o, NN_LPQ));
+        const float ds = fminf(sqrtf(other), sqrtf(U2) * 0.9999f);
+        rho = 0.5f * (ds - sqrtf(wd2)) - (1e-5f * ds + 1e-7f);
+    }
     if (ROOTED && NN_FAST_ROOTED && !exact)
     {
         if (key == 0xffffffffffffffffull) break;
@@ -361,7 +428,11 @@ k_nn_grid(CellGrid g, LutDev L, float res, const float4* __restrict__ data, cons
         }
     }
     }   // exact
-    if (lane == 0) keys[i] = key;
+    if (lane == 0)
+    {
+        keys[i] = key;
+        if (memo) memo[i] = make_float4(qx, qy, qz, rho);
+    }
 }
 
 // keys -> (idx, d2 of the winner recomputed with the canonical formula)
@@ -719,11 +790,12 @@ static int ensure_icp_capacity(fgoicp_ctx* c, int n)
     if (n <= c->icp_capacity) return FGOICP_OK;
     // size for a whole batch at once when that is cheap (25 bytes per instance and data point): the capacity then
     // never changes during a search (no cudaFree / cudaMalloc between levels)
-    if ((size_t)ICP_MAX_BATCH * c->ns * 25 <= ((size_t)256 << 20)) n = std::max(n, ICP_MAX_BATCH);
+    if ((size_t)ICP_MAX_BATCH * c->ns * 41 <= ((size_t)512 << 20)) n = std::max(n, ICP_MAX_BATCH);
     FG_CUDA(cudaStreamSynchronize(c->stream));
-    cudaFree(c->d_work); cudaFree(c->d_nnkey); cudaFree(c->d_icp); cudaFree(c->d_inl); cudaFree(c->d_icp_part);
-    c->d_work = nullptr; c->d_nnkey = nullptr; c->d_icp = nullptr; c->d_inl = nullptr; c->d_icp_part = nullptr; c->icp_capacity = 0;
+    cudaFree(c->d_work); cudaFree(c->d_nnkey); cudaFree(c->d_icp); cudaFree(c->d_inl); cudaFree(c->d_icp_part); cudaFree(c->d_nnmemo);
+    c->d_work = nullptr; c->d_nnkey = nullptr; c->d_icp = nullptr; c->d_inl = nullptr; c->d_icp_part = nullptr; c->d_nnmemo = nullptr; c->icp_capacity = 0;
     FG_CUDA(cudaMalloc(&c->d_work, sizeof(float4) * c->ns * n));
+    FG_CUDA(cudaMalloc(&c->d_nnmemo, sizeof(float4) * c->ns * n));
     FG_CUDA(cudaMalloc(&c->d_nnkey, sizeof(unsigned long long) * c->ns * n));
     FG_CUDA(cudaMalloc(&c->d_icp, (size_t)ICP_INST_BYTES * n + 256));
     FG_CUDA(cudaMalloc(&c->d_inl, c->ns * (size_t)n));
@@ -757,11 +829,16 @@ static int enqueue_nn(fgoicp_ctx* c, int n_inst, int src_sel, int pose_sel, int 
         const int qpb = NNG_WARPS * 32 / NN_LPQ;            // queries per block
         // inside the ICP loop the key buffer carries the previous pass's winners (all-ones before the first pass)
         const float4* warm = (check_done && !getenv("FGOICP_NN_NO_WARM")) ? c->d_model : nullptr;
+        // winner memo (ICP loop only): scans reach `margin` beyond the winner so that the proven clearance covers the
+        // rounding-level offset between the two searches of an iteration and the small moves of late iterations
+        static const float margin_cfg = getenv("FGOICP_NN_MARGIN") ? (float)atof(getenv("FGOICP_NN_MARGIN")) : FG_NN_MARGIN;
+        float4* memo = (warm && margin_cfg > 0.0f) ? c->d_nnmemo : nullptr;
+        const float margin = memo ? margin_cfg : 0.0f;
         dim3 grid((unsigned)((c->ns + qpb - 1) / qpb), (unsigned)n_inst);
         if (rooted)
-            k_nn_grid<1><<<grid, NNG_WARPS * 32, 0, c->stream>>>(g, c->lut, c->res, c->d_data, c->d_work, (int)c->ns, inst, src_sel, pose_sel, c->d_nnkey, check_done, warm);
+            k_nn_grid<1><<<grid, NNG_WARPS * 32, 0, c->stream>>>(g, c->lut, c->res, c->d_data, c->d_work, (int)c->ns, inst, src_sel, pose_sel, c->d_nnkey, check_done, warm, memo, margin);
         else
-            k_nn_grid<0><<<grid, NNG_WARPS * 32, 0, c->stream>>>(g, c->lut, c->res, c->d_data, c->d_work, (int)c->ns, inst, src_sel, pose_sel, c->d_nnkey, check_done, warm);
+            k_nn_grid<0><<<grid, NNG_WARPS * 32, 0, c->stream>>>(g, c->lut, c->res, c->d_data, c->d_work, (int)c->ns, inst, src_sel, pose_sel, c->d_nnkey, check_done, warm, memo, margin);
         FG_CUDA(cudaGetLastError());
         return FGOICP_OK;
     }
@@ -839,7 +916,7 @@ static int icp_slots(const fgoicp_ctx* c)
 {
     int s = ICP_MAX_BATCH;
     if (const char* e = getenv("FGOICP_ICP_SLOTS")) s = std::min(256, std::max(1, atoi(e)));
-    while (s > 1 && (size_t)s * c->ns * 25 > ((size_t)1 << 30)) s /= 2;         // 25 bytes per slot and data point
+    while (s > 1 && (size_t)s * c->ns * 41 > ((size_t)1 << 30)) s /= 2;         // 41 bytes per slot and data point
     return s;
 }
 

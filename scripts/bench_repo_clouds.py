@@ -67,7 +67,7 @@ def ours(pair, res, mse, reps=3):
         ang, terr = pose_err(R, t, Rt, tt)
         runs.append(dict(run_ms=st["run_ms"], ctor_ms=st["ctor_ms"], lut_build_ms=st["lut_build_ms"], sse=float(g.best_sse),
                          mse=float(g.best_sse) / len(data), bound_evals=int(st["bound_evals"]), rot_cubes=int(st["rot_cubes"]),
-                         icp_runs=int(st["icp_runs"]), ms_bnb_ub=st["ms_bnb_ub"], ms_icp=st["ms_icp"], ms_bnb_lb=st["ms_bnb_lb"],
+                         icp_runs=int(st["icp_runs"]), icp_iters=int(st["icp_iters"]), ms_bnb_ub=st["ms_bnb_ub"], ms_icp=st["ms_icp"], ms_bnb_lb=st["ms_bnb_lb"],
                          rot_err_deg=ang, t_err=terr, R=np.asarray(R).tolist(), t=np.asarray(t).tolist(),
                          grid_dims=list(info.dims), packed_bytes=int(info.packed_bytes)))
         g.close()
@@ -141,6 +141,8 @@ def main():
     ap.add_argument("--child", nargs=4)
     ap.add_argument("--cap", type=float, default=35.0, help="wall-clock cap per baseline run, seconds")
     ap.add_argument("--no-baselines", action="store_true")
+    ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--out", default="repo_clouds_r01.json")
     ap.add_argument("--only", default=None, help="substring filter on the case name")
     args = ap.parse_args()
     if args.child:
@@ -154,22 +156,22 @@ def main():
     gw.close()
     rows = []
     for name, pair, res, mse, with_base in CASES:
-        if args.only and args.only not in name:
+        if args.only and not any(tok in name for tok in args.only.split(",")):
             continue
         model, data, _, _ = load_pair(pair)
-        row = dict(case=name, nt=len(model), ns=len(data), lut_resolution=res, mse_threshold=mse, ours=ours(pair, res, mse))
+        row = dict(case=name, nt=len(model), ns=len(data), lut_resolution=res, mse_threshold=mse, ours=ours(pair, res, mse, args.reps))
         if with_base and not args.no_baselines:
             row["reference"] = baseline("reference", pair, res, mse, args.cap)
             row["cpu_port"] = baseline("cpu_port", pair, res, mse, args.cap)
         rows.append(row)
         o = row["ours"]
-        print("%-32s nt %6d ns %5d | ours run %8.1f ms ctor %7.1f ms mse %.3e evals %.2e | ref %s | cpu %s"
-              % (name, row["nt"], row["ns"], o["run_ms"], o["ctor_ms"], o["mse"], o["bound_evals"],
+        print("%-32s nt %6d ns %5d | ours run %8.1f ms (icp %7.1f ms, %d runs, %d iters) ctor %7.1f ms mse %.3e evals %.2e | ref %s | cpu %s"
+              % (name, row["nt"], row["ns"], o["run_ms"], o["ms_icp"], o["icp_runs"], o["icp_iters"], o["ctor_ms"], o["mse"], o["bound_evals"],
                  json.dumps({k: v for k, v in row.get("reference", {}).items() if k in ("run_ms", "run_ms_at_least", "sse", "error")}),
                  json.dumps({k: v for k, v in row.get("cpu_port", {}).items() if k in ("run_ms", "run_ms_at_least", "sse", "error")})),
               flush=True)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    with open(os.path.join(ROOT, "gpurun_out", "repo_clouds_r01.json"), "w") as f:
+    with open(os.path.join(ROOT, "gpurun_out", args.out), "w") as f:
         json.dump(rows, f, indent=1)
 
 

@@ -383,3 +383,24 @@ def test_icp_batch_equals_single_refinements(small_problem, gpu_ctx, monkeypatch
     assert np.all(it == 0) and np.array_equal(R, np.array(seeds_R[:5]).reshape(5, 9)) and np.all(e == np.float32(1e10))
     e0 = gpu_ctx.icp_batch(np.zeros((0, 9), np.float32), np.zeros((0, 3), np.float32), 10, 0.005)[0]
     assert len(e0) == 0
+
+
+@pytest.mark.parametrize("which", ["synthetic", "dragon"])
+def test_winner_memo_changes_no_result(which):
+    """The winner memo of the ICP searches (skip the scan when the point moved less than the clearance the last scan
+    proved) must not change a single bit: refinements with the memo off (margin 0), at the default margin and at a
+    large one give identical SSE, poses and iteration counts."""
+    import json
+    import os
+    import subprocess
+    import sys
+    probe = os.path.join(os.path.dirname(os.path.abspath(__file__)), "icp_probe.py")
+    outs = {}
+    for margin in ("0", "2.5e-4", "4e-3"):
+        env = dict(os.environ, FGOICP_NN_MARGIN=margin)
+        r = subprocess.run([sys.executable, probe, which], capture_output=True, text=True, env=env, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs[margin] = json.loads([l for l in r.stdout.splitlines() if l.startswith("PROBE ")][-1][6:])
+    assert outs["0"] == outs["2.5e-4"] == outs["4e-3"]
+    its = outs["0"]["1e-05"]["it"]
+    assert max(its) > 30                                  # long runs were exercised

@@ -217,6 +217,12 @@ __device__ __forceinline__ float fg_shrink(float d2, float margin)
 #ifndef NN_RPL
 #define NN_RPL 1            // rows per lane and pass of the cell-grid search; measured on the dragon pair (W3, ICP ms): 1 -> 3688, 4 -> 3873, 8 -> 4101
 #endif
+#ifndef NN_INCR_ROWS
+#define NN_INCR_ROWS 0      // 1 (needs NN_RPL == 1): row -> (cz, cy) carried incrementally instead of divided per row (experiment)
+#endif
+#if NN_INCR_ROWS && NN_RPL != 1
+#error "NN_INCR_ROWS needs NN_RPL == 1"
+#endif
 #ifndef NN_FAST_ROOTED
 #define NN_FAST_ROOTED 1      // 0: always the exact rooted scan (measured: ICP 86 -> 71 ms on W5 with 1)
 #endif
@@ -322,6 +328,9 @@ k_nn_grid(CellGrid g, LutDev L, float res, const float4* __restrict__ data, cons
     const int cy1 = min(max((int)floorf((ly + U) * inv_h), 0), g.ny - 1);
     const int ny_rows = cy1 - cy0 + 1;
     const int n_rows = ny_rows * (cz1 - cz0 + 1);
+#if NN_INCR_ROWS
+    int rz = lane / ny_rows, ry = lane % ny_rows;
+#endif
     // NN_RPL rows per lane and pass: the two cell-range lookups of all of them are in flight together.  Measured
     // neutral to slightly negative (see NN_RPL above): the row lookups are not what far queries wait for.
     for (int row0 = 0; row0 < n_rows; row0 += NN_LPQ * NN_RPL)
@@ -334,7 +343,12 @@ k_nn_grid(CellGrid g, LutDev L, float res, const float4* __restrict__ data, cons
             const int row = row0 + r * NN_LPQ + lane;
             if (row < n_rows)
             {
+#if NN_INCR_ROWS
+                // (cz, cy) of this lane's row carried from pass to pass instead of a division per row
+                const int cz = cz0 + rz, cy = cy0 + ry;
+#else
                 int cz = cz0 + row / ny_rows, cy = cy0 + row % ny_rows;
+#endif
                 // edge cells also hold points clamped into them: their slab extends to infinity
                 float zlo = cz == 0 ? -FG_INF : (float)cz * h, zhi = cz == g.nz - 1 ? FG_INF : (float)(cz + 1) * h;
                 float ylo = cy == 0 ? -FG_INF : (float)cy * h, yhi = cy == g.ny - 1 ? FG_INF : (float)(cy + 1) * h;
@@ -391,6 +405,10 @@ k_nn_grid(CellGrid g, LutDev L, float res, const float4* __restrict__ data, cons
         // share the tightest radius before the next pass
 #pragma unroll
         for (int o = NN_LPQ / 2; o > 0; o >>= 1) U2 = fminf(U2, __shfl_xor_sync(team_mask, U2, o, NN_LPQ));
+#if NN_INCR_ROWS
+        ry += NN_LPQ;
+        while (ry >= ny_rows) { ry -= ny_rows; ++rz; }
+#endif
     }
     key = 0xffffffffffffffffull;
     if (best_idx != 0x7fffffff) key = ((unsigned long long)__float_as_uint(best) << 32) | (unsigned int)best_idx;

@@ -141,6 +141,7 @@ def main():
     ap.add_argument("--child", nargs=4)
     ap.add_argument("--cap", type=float, default=35.0, help="wall-clock cap per baseline run, seconds")
     ap.add_argument("--no-baselines", action="store_true")
+    ap.add_argument("--skip", default=None, help="comma-separated substrings of case names to leave out")
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--out", default="repo_clouds_r01.json")
     ap.add_argument("--only", default=None, help="substring filter on the case name")
@@ -157,6 +158,8 @@ def main():
     rows = []
     for name, pair, res, mse, with_base in CASES:
         if args.only and not any(tok in name for tok in args.only.split(",")):
+            continue
+        if args.skip and any(tok in name for tok in args.skip.split(",")):
             continue
         model, data, _, _ = load_pair(pair)
         row = dict(case=name, nt=len(model), ns=len(data), lut_resolution=res, mse_threshold=mse, ours=ours(pair, res, mse, args.reps))

@@ -365,15 +365,46 @@ k_nn_grid(CellGrid g, LutDev L, float res, const float4* __restrict__ data, cons
                 }
             }
         }
+        // Candidates of the team's rows, dealt evenly over its lanes.  A far query grazes the surface: the cells its
+        // ball cuts hold hundreds of points, nearly all just outside the ball and owned by a handful of rows; walking
+        // each row's range in its own lane left 4-9 of 32 lanes active (ncu: profiles/nn_grid_w3_r01.md).  Here the
+        // ranges are concatenated (prefix sum over the lanes) and flat position t belongs to the first lane whose
+        // inclusive prefix exceeds t, found by a five-step binary search over shuffles.  Which lane sees which
+        // candidate does not matter: winners merge as a lexicographic minimum over (value, index).
 #pragma unroll
         for (int r = 0; r < NN_RPL; ++r)
         {
+            const int cnt = re[r] - rb[r];
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < NN_LPQ; o <<= 1)
             {
-                for (int k = rb[r]; k < re[r]; ++k)
+                const int v = __shfl_up_sync(team_mask, incl, o, NN_LPQ);
+                if (lane >= o) incl += v;
+            }
+            const int total = __shfl_sync(team_mask, incl, NN_LPQ - 1, NN_LPQ);
+            const int excl = incl - cnt;
+            for (int t0 = 0; t0 < total; t0 += NN_LPQ)
+            {
+                const int tt = t0 + lane;
+                int owner = 0;
+#pragma unroll
+                for (int step = NN_LPQ / 2; step > 0; step >>= 1)
                 {
-                    float4 m = __ldg(g.pts + k);
-                    float d = fg_sq3(__fsub_rn(qx, m.x), __fsub_rn(qy, m.y), __fsub_rn(qz, m.z));
-                    int idx = __float_as_int(m.w);
+                    const int v = __shfl_sync(team_mask, incl, owner + step - 1, NN_LPQ);
+                    if (v <= tt) owner += step;
+                }
+                const int ob = __shfl_sync(team_mask, rb[r], owner, NN_LPQ);
+                const int oe = __shfl_sync(team_mask, excl, owner, NN_LPQ);
+                if (tt < total)
+                {
+                    const float4 m = __ldg(g.pts + ob + (tt - oe));
+                    const float d = fg_sq3(__fsub_rn(qx, m.x), __fsub_rn(qy, m.y), __fsub_rn(qz, m.z));
+                    // outside the current ball: cannot win, and the clearance of the winner memo never looks beyond
+                    // the ball (every radius the ball shrinks to stays above the distances that matter below)
+                    if (d <= U2)
+                    {
+                    const int idx = __float_as_int(m.w);
                     if (ROOTED && !(NN_FAST_ROOTED && !exact))
                     {
                         if (d < thr_lo)
@@ -385,19 +416,14 @@ k_nn_grid(CellGrid g, LutDev L, float res, const float4* __restrict__ data, cons
                         }
                         else if (d <= thr_hi && idx < best_idx) best_idx = idx;
                     }
-                    else if (ROOTED)
+                    else
                     {
-                        // squared compare that also keeps the runner-up distance (decides below whether the
-                        // rooted rule could pick another index)
+                        // squared compare that also keeps the runner-up distance (rooted fast path: decides below
+                        // whether the rooted rule could pick another index; both: clearance of the winner memo)
                         if (d < best) { second = best; best = d; best_idx = idx; U2 = fminf(U2, fg_shrink(d, margin)); }
                         else if (d == best) { best_idx = min(best_idx, idx); tie = true; }
                         else second = fminf(second, d);
                     }
-                    else
-                    {
-                        if (d < best) { second = best; best = d; best_idx = idx; U2 = fminf(U2, fg_shrink(d, margin)); }
-                        else if (d == best) { best_idx = min(best_idx, idx); tie = true; }
-                        else second = fminf(second, d);
                     }
                 }
             }

@@ -30,6 +30,19 @@ def test_library_exports_every_declared_symbol():
     assert b"sm_100a" in L.fgoicp_version()
 
 
+def test_header_is_plain_c_and_struct_layouts_match_the_binding(tmp_path):
+    """include/fgoicp_c.h compiles as strict C99, and the ctypes mirrors in capi.py have the compiler's layout."""
+    import subprocess
+    exe = str(tmp_path / "abi_sizes")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I" + os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "cpp", "abi_sizes.c"), "-o", exe], check=True)
+    out = dict((l.split()[0], [int(x) for x in l.split()[1:]]) for l in subprocess.run([exe], capture_output=True, text=True).stdout.splitlines())
+    I, S, N = capi.Info, capi.LevelStats, capi.Normalisation
+    assert out["fgoicp_info"] == [ctypes.sizeof(I), I.dims.offset, I.grid_bytes.offset, I.build_ms.offset]
+    assert out["fgoicp_level_stats"] == [ctypes.sizeof(S), S.n_icp.offset, S.ms_bnb_ub.offset, S.best_icp_index.offset]
+    assert out["fgoicp_normalisation"] == [ctypes.sizeof(N), N.scale.offset, N.bbox_min.offset, N.device_ms.offset]
+
+
 def test_cpp_api_symbols_present():
     out = os.popen("nm -DC %s" % capi.LIB_PATH).read()
     assert "icp::FastGoICP::run()" in out

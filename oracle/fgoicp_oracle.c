@@ -448,8 +448,8 @@ ORC_API void orc_bounds(const float* lut, const int* dims, const float* bbox_min
 /* rooted = 0: compare squared distances, strict <, ascending j (lowest index wins ties)
  * rooted = 1: compare sqrtf(d2) as glm::distance does, strict >, ascending j.
  * queries are transformed by (R, t) first when R != NULL.  idx / d2 may be NULL. */
-ORC_API void orc_nn(const float* model, size_t nt, const float* q_in, size_t n,
-                    const float* R, const float* t, int rooted, int32_t* idx, float* d2out)
+static void orc_nn_brute(const float* model, size_t nt, const float* q_in, size_t n,
+                         const float* R, const float* t, int rooted, int32_t* idx, float* d2out)
 {
     long long i;
 #pragma omp parallel for schedule(static)
@@ -471,6 +471,152 @@ ORC_API void orc_nn(const float* model, size_t nt, const float* q_in, size_t n,
         if (idx) idx[i] = bi;
         if (d2out) d2out[i] = best_d2;
     }
+}
+
+/* The same search through a k-d tree (the CPU baseline's stand-in for the nanoflann ICP BASELINE.json names; nanoflann
+ * itself is not in this image).  EXACT, ties included: the winner is the lexicographic minimum of (key, index), which
+ * is what the ascending scans above pick, and a subtree is skipped only when the key of its bounding box -- the same
+ * fp32 formula on the per-axis gaps, monotone in every rounding step -- is strictly above the best key so far. */
+#define ORC_KD_LEAF 12
+typedef struct orc_kdnode
+{
+    float lo[3], hi[3];
+    int left, right;            /* children, -1 for a leaf    */
+    int begin, end;             /* leaf: range of perm / pts  */
+} orc_kdnode;
+typedef struct orc_kdtree
+{
+    orc_kdnode* nodes;
+    int n_nodes;
+    int32_t* perm;              /* original index of slot p   */
+    float* pts;                 /* xyz in slot order          */
+    size_t nt;
+    uint64_t hash;              /* of the model bytes (cache) */
+} orc_kdtree;
+
+static int g_nn_mode = 1;       /* 0: brute force, 1: k-d tree for nt >= 64 */
+static orc_kdtree g_kd = { NULL, 0, NULL, NULL, 0, 0 };
+
+ORC_API void orc_set_nn_mode(int mode) { g_nn_mode = mode; }
+
+static int orc_kd_build_rec(orc_kdtree* T, const float* model, int begin, int end)
+{
+    int id = T->n_nodes++, a, p, axis = 0;
+    orc_kdnode* nd = &T->nodes[id];
+    for (a = 0; a < 3; ++a) { nd->lo[a] = FLT_MAX; nd->hi[a] = -FLT_MAX; }
+    for (p = begin; p < end; ++p)
+        for (a = 0; a < 3; ++a)
+        {
+            float v = model[3 * (size_t)T->perm[p] + a];
+            if (v < nd->lo[a]) nd->lo[a] = v;
+            if (v > nd->hi[a]) nd->hi[a] = v;
+        }
+    nd->begin = begin; nd->end = end; nd->left = nd->right = -1;
+    if (end - begin <= ORC_KD_LEAF) return id;
+    for (a = 1; a < 3; ++a) if (nd->hi[a] - nd->lo[a] > nd->hi[axis] - nd->lo[axis]) axis = a;
+    if (!(nd->hi[axis] > nd->lo[axis])) return id;                    /* all points coincide: one leaf */
+    {
+        /* quickselect of the median along `axis` */
+        int mid = begin + (end - begin) / 2, lo = begin, hi = end - 1;
+        while (lo < hi)
+        {
+            float pivot = model[3 * (size_t)T->perm[(lo + hi) / 2] + axis];
+            int i = lo, j = hi;
+            while (i <= j)
+            {
+                while (model[3 * (size_t)T->perm[i] + axis] < pivot) ++i;
+                while (model[3 * (size_t)T->perm[j] + axis] > pivot) --j;
+                if (i <= j) { int32_t tmp = T->perm[i]; T->perm[i] = T->perm[j]; T->perm[j] = tmp; ++i; --j; }
+            }
+            if (mid <= j) hi = j; else if (mid >= i) lo = i; else break;
+        }
+        {
+            int l = orc_kd_build_rec(T, model, begin, mid);
+            int r = orc_kd_build_rec(T, model, mid, end);
+            T->nodes[id].left = l; T->nodes[id].right = r;            /* T->nodes never moves: sized up front */
+        }
+    }
+    return id;
+}
+
+static const orc_kdtree* orc_kd_get(const float* model, size_t nt)
+{
+    uint64_t h = 1469598103934665603ull;
+    const uint32_t* w = (const uint32_t*)model;
+    size_t i;
+    for (i = 0; i < 3 * nt; ++i) { h ^= w[i]; h *= 1099511628211ull; }
+    if (g_kd.nodes && g_kd.nt == nt && g_kd.hash == h) return &g_kd;
+    free(g_kd.nodes); free(g_kd.perm); free(g_kd.pts);
+    g_kd.nodes = (orc_kdnode*)malloc(sizeof(orc_kdnode) * (2 * nt + 1));
+    g_kd.perm = (int32_t*)malloc(sizeof(int32_t) * nt);
+    g_kd.pts = (float*)malloc(sizeof(float) * 3 * nt);
+    g_kd.n_nodes = 0; g_kd.nt = nt; g_kd.hash = h;
+    for (i = 0; i < nt; ++i) g_kd.perm[i] = (int32_t)i;
+    orc_kd_build_rec(&g_kd, model, 0, (int)nt);
+    for (i = 0; i < nt; ++i) memcpy(g_kd.pts + 3 * i, model + 3 * (size_t)g_kd.perm[i], 3 * sizeof(float));
+    return &g_kd;
+}
+
+static inline float orc_kd_box_d2(const orc_kdnode* nd, const float* q)
+{
+    float g[3];
+    int a;
+    for (a = 0; a < 3; ++a)
+        g[a] = q[a] < nd->lo[a] ? nd->lo[a] - q[a] : (q[a] > nd->hi[a] ? q[a] - nd->hi[a] : 0.0f);
+    return orc_sq3(g[0], g[1], g[2]);
+}
+
+static void orc_nn_kd(const orc_kdtree* T, const float* q_in, size_t n,
+                      const float* R, const float* t, int rooted, int32_t* idx, float* d2out)
+{
+    long long i;
+#pragma omp parallel for schedule(dynamic, 64)
+    for (i = 0; i < (long long)n; ++i)
+    {
+        float q[3];
+        float best = ORC_INF, best_d2 = ORC_INF;
+        int32_t bi = -1;
+        int stack[128], sp = 0;
+        if (R) orc_xform(R, t, q_in + 3 * i, q);
+        else { q[0] = q_in[3 * i]; q[1] = q_in[3 * i + 1]; q[2] = q_in[3 * i + 2]; }
+        stack[sp++] = 0;
+        while (sp > 0)
+        {
+            const orc_kdnode* nd = &T->nodes[stack[--sp]];
+            float lb = orc_kd_box_d2(nd, q);
+            if ((rooted ? sqrtf(lb) : lb) > best) continue;             /* equal keys may still hold a lower index */
+            if (nd->left < 0)
+            {
+                int p;
+                for (p = nd->begin; p < nd->end; ++p)
+                {
+                    float dx = q[0] - T->pts[3 * p], dy = q[1] - T->pts[3 * p + 1], dz = q[2] - T->pts[3 * p + 2];
+                    float dd = orc_sq3(dx, dy, dz);
+                    float key = rooted ? sqrtf(dd) : dd;
+                    int32_t j = T->perm[p];
+                    /* the brute-force scan starts from ORC_INF with a strict compare: keys >= ORC_INF never win */
+                    if (key < best || (key == best && bi >= 0 && j < bi)) { best = key; best_d2 = dd; bi = j; }
+                }
+            }
+            else
+            {
+                float dl = orc_kd_box_d2(&T->nodes[nd->left], q), dr = orc_kd_box_d2(&T->nodes[nd->right], q);
+                if (dl <= dr) { stack[sp++] = nd->right; stack[sp++] = nd->left; }     /* nearer child on top */
+                else { stack[sp++] = nd->left; stack[sp++] = nd->right; }
+            }
+        }
+        if (idx) idx[i] = bi;
+        if (d2out) d2out[i] = best_d2;
+    }
+}
+
+ORC_API void orc_nn(const float* model, size_t nt, const float* q_in, size_t n,
+                    const float* R, const float* t, int rooted, int32_t* idx, float* d2out)
+{
+    if (g_nn_mode == 1 && nt >= 64 && nt < ((size_t)1 << 30))
+        orc_nn_kd(orc_kd_get(model, nt), q_in, n, R, t, rooted, idx, d2out);
+    else
+        orc_nn_brute(model, nt, q_in, n, R, t, rooted, idx, d2out);
 }
 
 /* Registration::compute_sse_error(R, t), registration.cu:62-86 */

@@ -29,6 +29,7 @@ def lib():
     L.orc_set_sin_table.argtypes = [_f32p, _f32p, C.c_int]
     L.orc_num_threads.restype = C.c_int
     L.orc_set_num_threads.argtypes = [C.c_int]
+    L.orc_set_nn_mode.argtypes = [C.c_int]
     L.orc_rotation.argtypes = [C.c_float, C.c_float, C.c_float, _f32p]
     L.orc_rotation.restype = C.c_float
     L.orc_overlaps_so3.argtypes = [C.c_float] * 4
@@ -188,6 +189,11 @@ def bounds(lut, dims, bbox_min, res, data, R, rot_span, fix_rot, tcubes):
     lib().orc_bounds(_f32(lut), np.ascontiguousarray(dims, np.int32), _f32(bbox_min), res, data,
                      len(data), _f32(R), rot_span, int(bool(fix_rot)), tc, T, lb, ub)
     return lb, ub
+
+
+def set_nn_mode(mode):
+    """0: brute-force scans (the reference's kernels, literally); 1 (default): exact k-d tree, same winners."""
+    lib().orc_set_nn_mode(int(mode))
 
 
 def nn(model, q, R=None, t=None, rooted=False):

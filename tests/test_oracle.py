@@ -192,3 +192,37 @@ def test_bnb_r3_finds_translation(small_problem):
     assert np.all(np.abs(bt - t_n) <= 0.0625 + 1e-6)      # within the leaf cube
     assert evals == nb * len(pp["data"]) or evals <= nb * 32 * len(pp["data"])
     assert ub < 40 * thr
+
+
+def test_kdtree_search_equals_the_brute_force_scans():
+    """The k-d tree behind the oracle's NN (the CPU baseline's stand-in for a nanoflann ICP) returns the SAME index and
+    the same distance bits as the literal restatement of the reference's scans (registration.cu:160-172,
+    icp3d.cu:11-28), under both tie rules: random clouds, every point triplicated, queries on model points, clustered
+    points, degenerate (flat / collinear / identical) clouds."""
+    rng = np.random.default_rng(77)
+    base = rng.uniform(-1, 1, (3000, 3)).astype(np.float32)
+    clouds = {
+        "random": base,
+        "triplicated": np.concatenate([base[:900]] * 3)[rng.permutation(2700)],
+        "clustered": (base[:40, None, :] + rng.normal(scale=1e-4, size=(40, 60, 3))).reshape(-1, 3).astype(np.float32),
+        "flat": np.concatenate([base[:1500, :2], np.zeros((1500, 1), np.float32)], axis=1),
+        "collinear": np.outer(np.linspace(-1, 1, 500), [1, 2, -1]).astype(np.float32),
+        "identical": np.tile(base[:1], (200, 1)),
+        "quantised": np.round(base * 8) / 8,                       # many exactly equal distances
+    }
+    try:
+        for name, model in clouds.items():
+            model = np.ascontiguousarray(model, np.float32)
+            q = np.concatenate([rng.uniform(-1.3, 1.3, (600, 3)), model[::7][:200], np.round(rng.uniform(-1, 1, (200, 3)) * 8) / 8]).astype(np.float32)
+            R, _ = O.rotation(0.2, -0.1, 0.3)
+            t = np.array([0.05, -0.02, 0.1], np.float32)
+            for rooted in (False, True):
+                for pose in ((None, None), (R, t)):
+                    O.set_nn_mode(0)
+                    i0, d0 = O.nn(model, q, pose[0], pose[1], rooted=rooted)
+                    O.set_nn_mode(1)
+                    i1, d1 = O.nn(model, q, pose[0], pose[1], rooted=rooted)
+                    assert np.array_equal(i0, i1), (name, rooted)
+                    assert np.array_equal(d0, d1), (name, rooted)
+    finally:
+        O.set_nn_mode(1)

@@ -157,8 +157,14 @@ def cpu_baseline_sample(pp, seconds=12.0):
         e, _, _, it = O.icp(pp["model"], pp["data"], 100, 0.05, np.eye(3, dtype=np.float32).ravel(), np.zeros(3, np.float32))
         out["first_icp_ms"] = (time.perf_counter() - t1) * 1e3
         out["first_icp"] = "k-d tree ICP of the oracle, %d iterations, sse %.6g, same host threads" % (it, e)
-    except Exception as ex:  # never let the extra measurement cost the bench line
-        out["first_icp_error"] = str(ex)[:200]
+        # and the constructor's grid build on the host (k-d tree build of the oracle), compared cell for cell with the
+        # grid the GPU built for this run
+        t1 = time.perf_counter()
+        cpu_lut, cpu_dims = O.lut_build(pp["model"], pp["bbox_min"], pp["bbox_max"], RES)
+        out["lut_build_ms"] = (time.perf_counter() - t1) * 1e3
+        out["lut_equals_gpu_grid"] = bool(np.array_equal(cpu_dims, dims) and np.array_equal(cpu_lut, lut))
+    except Exception as ex:  # never let the extra measurements cost the bench line
+        out["extra_error"] = str(ex)[:200]
     return out
 
 

@@ -264,8 +264,8 @@ ORC_API void orc_lut_dims(const float* bbox_min, const float* bbox_max, float re
 
 /* buildLUTKernel (registration.cu:258-278) with the host-side point shift (:289-296).
  * SASS: dx = FFMA(float(x), res, -P.x) -- the node coordinate is never rounded on its own. */
-ORC_API void orc_lut_build(const float* model, size_t nt, const float* bbox_min, float res,
-                           const int* dims, float* out)
+static void orc_lut_build_brute(const float* model, size_t nt, const float* bbox_min, float res,
+                                const int* dims, float* out)
 {
     float* P = (float*)malloc(sizeof(float) * 3 * (nt ? nt : 1));
     size_t j;
@@ -608,6 +608,95 @@ static void orc_nn_kd(const orc_kdtree* T, const float* q_in, size_t n,
         if (idx) idx[i] = bi;
         if (d2out) d2out[i] = best_d2;
     }
+}
+
+/* The grid build through the same tree (over the SHIFTED points P = model - bbox_min, registration.cu:289-296): each
+ * node's value is the plain minimum of the reference's per-pair expression, so only values matter (no tie rule).
+ * A subtree is skipped when its box cannot beat the best value: per axis, with c = x * res exact, every point p of
+ * the box has |fl(c - p)| >= |fl(c - lo)| when c <= lo and >= |fl(c - hi)| when c >= hi (one rounding, monotone),
+ * and the sign of fl(c - lo) / fl(c - hi) is the sign of the exact difference. */
+static inline float orc_kd_box_d2_node(const orc_kdnode* nd, const float* f, float res)
+{
+    float g[3];
+    int a;
+    for (a = 0; a < 3; ++a)
+    {
+        float glo = fmaf(f[a], res, -nd->lo[a]);
+        if (glo <= 0.0f) g[a] = -glo;
+        else
+        {
+            float ghi = fmaf(f[a], res, -nd->hi[a]);
+            g[a] = ghi >= 0.0f ? ghi : 0.0f;
+        }
+    }
+    return orc_sq3(g[0], g[1], g[2]);
+}
+
+static int g_lut_mode = 1;      /* 0: brute force over all points per node, 1: k-d tree */
+ORC_API void orc_set_lut_mode(int mode) { g_lut_mode = mode; }
+
+ORC_API void orc_lut_build(const float* model, size_t nt, const float* bbox_min, float res,
+                           const int* dims, float* out)
+{
+    orc_kdtree T = { NULL, 0, NULL, NULL, 0, 0 };
+    float* P;
+    size_t j;
+    long long rows = (long long)dims[1] * dims[2], row;
+    if (g_lut_mode != 1 || nt < 64 || nt >= ((size_t)1 << 30)) { orc_lut_build_brute(model, nt, bbox_min, res, dims, out); return; }
+    P = (float*)malloc(sizeof(float) * 3 * nt);
+    for (j = 0; j < nt; ++j)
+    {
+        P[3 * j + 0] = model[3 * j + 0] + (-bbox_min[0]);
+        P[3 * j + 1] = model[3 * j + 1] + (-bbox_min[1]);
+        P[3 * j + 2] = model[3 * j + 2] + (-bbox_min[2]);
+    }
+    T.nodes = (orc_kdnode*)malloc(sizeof(orc_kdnode) * (2 * nt + 1));
+    T.perm = (int32_t*)malloc(sizeof(int32_t) * nt);
+    T.pts = (float*)malloc(sizeof(float) * 3 * nt);
+    T.nt = nt;
+    for (j = 0; j < nt; ++j) T.perm[j] = (int32_t)j;
+    orc_kd_build_rec(&T, P, 0, (int)nt);
+    for (j = 0; j < nt; ++j) memcpy(T.pts + 3 * j, P + 3 * (size_t)T.perm[j], 3 * sizeof(float));
+#pragma omp parallel for schedule(dynamic, 16)
+    for (row = 0; row < rows; ++row)
+    {
+        int y = (int)(row % dims[1]), z = (int)(row / dims[1]), x;
+        int seed = 0;                                   /* slot of the previous node's winner: a real candidate, so a valid start */
+        for (x = 0; x < dims[0]; ++x)
+        {
+            float f[3] = { (float)x, (float)y, (float)z };
+            float best;
+            int stack[128], sp = 0;
+            {
+                float dx = fmaf(f[0], res, -T.pts[3 * seed]), dy = fmaf(f[1], res, -T.pts[3 * seed + 1]), dz = fmaf(f[2], res, -T.pts[3 * seed + 2]);
+                best = orc_sq3(dx, dy, dz);
+            }
+            stack[sp++] = 0;
+            while (sp > 0)
+            {
+                const orc_kdnode* nd = &T.nodes[stack[--sp]];
+                if (orc_kd_box_d2_node(nd, f, res) > best) continue;
+                if (nd->left < 0)
+                {
+                    int p;
+                    for (p = nd->begin; p < nd->end; ++p)
+                    {
+                        float dx = fmaf(f[0], res, -T.pts[3 * p]), dy = fmaf(f[1], res, -T.pts[3 * p + 1]), dz = fmaf(f[2], res, -T.pts[3 * p + 2]);
+                        float d = orc_sq3(dx, dy, dz);
+                        if (d < best) { best = d; seed = p; }
+                    }
+                }
+                else
+                {
+                    float dl = orc_kd_box_d2_node(&T.nodes[nd->left], f, res), dr = orc_kd_box_d2_node(&T.nodes[nd->right], f, res);
+                    if (dl <= dr) { stack[sp++] = nd->right; stack[sp++] = nd->left; }
+                    else { stack[sp++] = nd->left; stack[sp++] = nd->right; }
+                }
+            }
+            out[((size_t)z * dims[1] + y) * dims[0] + x] = best;
+        }
+    }
+    free(T.nodes); free(T.perm); free(T.pts); free(P);
 }
 
 ORC_API void orc_nn(const float* model, size_t nt, const float* q_in, size_t n,

@@ -30,6 +30,7 @@ def lib():
     L.orc_num_threads.restype = C.c_int
     L.orc_set_num_threads.argtypes = [C.c_int]
     L.orc_set_nn_mode.argtypes = [C.c_int]
+    L.orc_set_lut_mode.argtypes = [C.c_int]
     L.orc_rotation.argtypes = [C.c_float, C.c_float, C.c_float, _f32p]
     L.orc_rotation.restype = C.c_float
     L.orc_overlaps_so3.argtypes = [C.c_float] * 4
@@ -194,6 +195,11 @@ def bounds(lut, dims, bbox_min, res, data, R, rot_span, fix_rot, tcubes):
 def set_nn_mode(mode):
     """0: brute-force scans (the reference's kernels, literally); 1 (default): exact k-d tree, same winners."""
     lib().orc_set_nn_mode(int(mode))
+
+
+def set_lut_mode(mode):
+    """0: every grid node scans every model point (the reference's kernel, literally); 1 (default): k-d tree, same values."""
+    lib().orc_set_lut_mode(int(mode))
 
 
 def nn(model, q, R=None, t=None, rooted=False):

@@ -226,3 +226,25 @@ def test_kdtree_search_equals_the_brute_force_scans():
                     assert np.array_equal(d0, d1), (name, rooted)
     finally:
         O.set_nn_mode(1)
+
+
+def test_kdtree_grid_build_equals_the_brute_force_build():
+    """The oracle's fast grid build (k-d tree over the shifted points) writes the same bits as the literal restatement of
+    buildLUTKernel (registration.cu:258-278: every node scans every point), including off-centre boxes, coarse and fine
+    resolutions, and degenerate clouds."""
+    rng = np.random.default_rng(12)
+    base = rng.normal(size=(2500, 3)).astype(np.float32) * np.array([0.4, 0.25, 0.1], np.float32) + np.float32(0.05)
+    cases = [(base, 0.05), (base, 0.011),
+             (np.concatenate([base[:600, :2], np.full((600, 1), 0.3, np.float32)], axis=1), 0.02),
+             ((np.round(base[:800] * 16) / 16).astype(np.float32), 0.03)]
+    try:
+        for model, res in cases:
+            model = np.ascontiguousarray(model, np.float32)
+            mn, mx = model.min(0) - np.float32(0.013), model.max(0) + np.float32(0.021)
+            O.set_lut_mode(0)
+            a, da = O.lut_build(model, mn, mx, res)
+            O.set_lut_mode(1)
+            b, db = O.lut_build(model, mn, mx, res)
+            assert np.array_equal(da, db) and np.array_equal(a, b)
+    finally:
+        O.set_lut_mode(1)

@@ -162,7 +162,7 @@ def cpu_baseline_sample(pp, seconds=12.0):
         t1 = time.perf_counter()
         cpu_lut, cpu_dims = O.lut_build(pp["model"], pp["bbox_min"], pp["bbox_max"], RES)
         out["lut_build_ms"] = (time.perf_counter() - t1) * 1e3
-        out["lut_equals_gpu_grid"] = bool(np.array_equal(cpu_dims, dims) and np.array_equal(cpu_lut, lut))
+        out["lut_equals_gpu_grid"] = bool(np.array_equal(np.ravel(cpu_dims), np.ravel(dims)) and np.array_equal(np.ravel(cpu_lut), np.ravel(lut)))
     except Exception as ex:  # never let the extra measurements cost the bench line
         out["extra_error"] = str(ex)[:200]
     return out

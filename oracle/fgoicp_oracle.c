@@ -17,7 +17,11 @@
  *       here with explicit fmaf() and -ffp-contract=off;
  *   (3) on a GPU box, tests also compare the CUDA path AND this oracle against oracle/_ref live (real tex3D,
  *       real kernels);
- *   (4) independent cross-checks in tests (scipy cKDTree, numpy SVD/Kabsch, numpy trilinear).
+ *   (4) independent cross-checks in tests (scipy cKDTree, numpy SVD/Kabsch, numpy trilinear);
+ *   (5) the nearest-neighbour search and the grid build exist twice here -- the literal scans of the reference's
+ *       kernels and an exact k-d tree (default, so that the oracle answers at full size) -- and are tested to agree
+ *       bit for bit (tests/test_oracle.py); driven through the level-synchronous driver the oracle reproduces the
+ *       CUDA path's whole search at full size bit for bit (tests/test_fullsize_parity.py).
  * The trimming switch (orc_set_trim_k) is an EXTENSION with no reference behaviour: it is pinned by a numpy
  * restatement only (tests/test_trimming.py) and is off by default.
  *

@@ -392,6 +392,9 @@ static int build_cell_grid(fgoicp_ctx* c, const float4* d_P)
     float max_ext = std::max(ext[0], std::max(ext[1], ext[2]));
     float area = ext[0] * ext[1] + ext[1] * ext[2] + ext[0] * ext[2];     // half the bounding-box surface
     float h = std::sqrt(4.0f * area / (float)nt);
+    // FGOICP_NN_CELL_SCALE (experiment knob, default 1): smaller cells mean fewer candidates per far query of the NN
+    // search and more (cheap) rows; any size gives the same exact results
+    if (const char* e = getenv("FGOICP_NN_CELL_SCALE")) { float f = (float)atof(e); if (f >= 0.125f && f <= 8.0f) h *= f; }
     h = std::max(h, std::max(max_ext / 256.0f, 2.0f * c->res));
     c->cell_h = h; c->cell_inv_h = 1.0f / h;
     c->cnx = std::max(1, (int)std::ceil(ext[0] / h)); c->cny = std::max(1, (int)std::ceil(ext[1] / h)); c->cnz = std::max(1, (int)std::ceil(ext[2] / h));

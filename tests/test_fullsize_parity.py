@@ -54,3 +54,36 @@ def test_cuda_path_reproduces_the_recorded_w5_result_bit_for_bit():
     R, t = g.run()
     _check(g, R, t, z, "w5")
     g.close()
+
+
+def _sharded_worker(rank, world, port, out_path):
+    import torch
+    import torch.distributed as dist
+    from oracle import oracle as O
+    from oracle_context import OracleContext
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    O.set_num_threads(4)
+    z = np.load(GOLD)
+    g = driver.FastGoICP(z["model"], z["data"], 0.005, 1e-3, ctx_factory=OracleContext)
+    R, t = g.run()
+    if rank == 0:
+        torch.save(dict(R=np.asarray(R, np.float32), t=np.asarray(t, np.float32), sse=np.float32(g.best_sse),
+                        local_evals=g.stats["bound_evals"]), out_path)
+    g.close()
+    dist.destroy_process_group()
+
+
+def test_frontier_sharded_over_two_ranks_reproduces_the_same_bits(tmp_path):
+    """SURVEY.md 8e at full size: the rotation frontier dealt over 2 ranks (gloo), best upper bound MIN-reduced per wave --
+    same SSE and pose as one rank and as the GPU, with each rank doing only its share of the evaluations."""
+    import torch
+    import torch.multiprocessing as mp
+    z = np.load(GOLD)
+    out = str(tmp_path / "sharded.pt")
+    mp.spawn(_sharded_worker, args=(2, 29650 + os.getpid() % 300, out), nprocs=2, join=True)
+    res = torch.load(out, weights_only=False)
+    assert res["sse"] == z["gpu_sse_mse1e-3"]
+    assert np.array_equal(res["R"], z["gpu_R_mse1e-3"]) and np.array_equal(res["t"], z["gpu_t_mse1e-3"])
+    assert 0 < res["local_evals"] < int(z["gpu_counts_mse1e-3"][0])

@@ -1,7 +1,7 @@
 // Test harness for the drop-in C++ class icp::FastGoICP (reference fgoicp/fgoicp.hpp:10-108), used the way the
 // reference's src/main.cpp:46-53 uses it: construct with (target, source, lut_resolution, mse_threshold), run(),
 // read the error.  Reads two raw float32 xyz files, prints one line of hex floats so the Python test can compare
-// bit patterns:   R[9 column-major] t[3] sse scale ctor_ms run_ms
+// bit patterns:   R[9 column-major] t[3] sse scale ctor_ms run_ms bound_evals rot_cubes icp_runs
 //
 //   fgoicp_harness <model.f32> <data.f32> <lut_resolution> <mse_threshold>
 //
@@ -38,8 +38,10 @@ int main(int argc, char** argv)
         for (int c = 0; c < 3; ++c)
             for (int r = 0; r < 3; ++r) std::printf(" %a", static_cast<double>(R[c][r]));
         for (int a = 0; a < 3; ++a) std::printf(" %a", static_cast<double>(t[a]));
-        std::printf(" %a %a %a %a\n", static_cast<double>(fgoicp.get_best_error()), static_cast<double>(fgoicp.scaling()),
+        std::printf(" %a %a %a %a", static_cast<double>(fgoicp.get_best_error()), static_cast<double>(fgoicp.scaling()),
                     static_cast<double>(fgoicp.stats().ctor_ms), static_cast<double>(fgoicp.stats().run_ms));
+        std::printf(" %a %a %a\n", static_cast<double>(fgoicp.stats().bound_evals), static_cast<double>(fgoicp.stats().rot_cubes),
+                    static_cast<double>(fgoicp.stats().icp_runs));
         return 0;
     }
     catch (const std::exception& e)

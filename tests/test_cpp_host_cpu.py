@@ -1,0 +1,77 @@
+"""The drop-in C++ class icp::FastGoICP (include/fgoicp/fgoicp.hpp, csrc/fgoicp_host.cpp) WITHOUT a GPU: the same host
+driver source, linked against an oracle-backed stand-in of the C ABI (tests/cpp/oracle_abi.c, test infrastructure), must
+make the same decisions as the Python mirror of the driver over the oracle -- and, on the reference repository's bunny
+pair at full size, land on the very bits the CUDA path returned on the B200 (tests/golden/bunny_full.npz)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from fast_go_icp_b200 import build_harness, driver, workloads
+from oracle import oracle as O
+from oracle_context import OracleContext
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "bunny_full.npz")
+
+
+def _run_cpp(tmp_path, model, data, res, mse, **env):
+    exe = build_harness.build_cpu()
+    np.ascontiguousarray(model, np.float32).tofile(tmp_path / "model.f32")
+    np.ascontiguousarray(data, np.float32).tofile(tmp_path / "data.f32")
+    e = dict(os.environ)
+    e.update({k: str(v) for k, v in env.items()})
+    out = subprocess.run([exe, str(tmp_path / "model.f32"), str(tmp_path / "data.f32"), repr(res), repr(mse)],
+                         capture_output=True, text=True, env=e, timeout=900)
+    assert out.returncode == 0, out.stderr
+    v = np.array([float.fromhex(x) for x in [l for l in out.stdout.splitlines() if l.startswith("RESULT")][-1].split()[1:]])
+    return dict(R=v[:9].astype(np.float32).reshape(3, 3).T, t=v[9:12].astype(np.float32), sse=np.float32(v[12]),
+                scale=np.float32(v[13]), evals=int(v[16]), cubes=int(v[17]), icps=int(v[18]))
+
+
+@pytest.fixture(scope="module")
+def problem():
+    return workloads.synthetic_pair(nt=1500, ns=200, sigma=0.005, seed=12, max_angle=1.2)
+
+
+def test_cpp_level_schedule_equals_python_driver(tmp_path, problem):
+    w = problem
+    cpp = _run_cpp(tmp_path, w["model"], w["data"], 0.03, 1e-4)
+    g = driver.FastGoICP(w["model"], w["data"], 0.03, 1e-4, ctx_factory=OracleContext)
+    R, t = g.run()
+    assert cpp["sse"] == np.float32(g.best_sse) and cpp["scale"] == np.float32(g.pp["scale"])
+    assert np.array_equal(cpp["R"], np.asarray(R, np.float32)) and np.array_equal(cpp["t"], np.asarray(t, np.float32))
+    assert [cpp["evals"], cpp["cubes"], cpp["icps"]] == [g.stats["bound_evals"], g.stats["rot_cubes"], g.stats["icp_runs"]]
+    g.close()
+    ang = np.degrees(np.arccos(np.clip((np.trace(cpp["R"] @ w["R_true"].T) - 1) / 2, -1, 1)))
+    assert ang < 2.0 and np.linalg.norm(cpp["t"] - w["t_true"]) < 0.03
+
+
+def test_cpp_reference_schedule_agrees_with_the_oracle_run(tmp_path, problem):
+    """FGOICP_SCHEDULE=bestfirst is the reference's own order (fgoicp.cpp:32-100), which the oracle's orc_run restates:
+    same registration (the heaps may order exact ties differently, so the comparison is the stated tolerance, not bits)."""
+    w = problem
+    cpp = _run_cpp(tmp_path, w["model"], w["data"], 0.03, 1e-4, FGOICP_SCHEDULE="bestfirst")
+    pp = O.preprocess(w["model"], w["data"])
+    lut, dims = O.lut_build(pp["model"], pp["bbox_min"], pp["bbox_max"], 0.03)
+    e, R, t, st = O.run(pp["model"], pp["data"], lut, dims, pp["bbox_min"], 0.03, 1e-4)
+    assert abs(float(cpp["sse"]) - float(e)) <= 1e-6 * float(e)
+    t_orig = O.restore_translation(R, t, pp["scale"], pp["offset_pcs"], pp["offset_pct"])
+    assert np.allclose(cpp["R"], np.asarray(R, np.float32).reshape(3, 3).T, atol=1e-6) and np.allclose(cpp["t"], t_orig, atol=1e-5)
+
+
+def test_cpp_class_on_the_full_bunny_pair_lands_on_the_gpu_bits(tmp_path):
+    z = np.load(GOLD)
+    cpp = _run_cpp(tmp_path, z["model"], z["data"], 0.005, 1e-3)
+    assert cpp["sse"] == z["gpu_sse_mse1e-3"]
+    assert np.array_equal(cpp["R"], z["gpu_R_mse1e-3"]) and np.array_equal(cpp["t"], z["gpu_t_mse1e-3"])
+    assert [cpp["evals"], cpp["cubes"], cpp["icps"]] == [int(c) for c in z["gpu_counts_mse1e-3"]]
+
+
+def test_cpp_class_reports_a_missing_gpu_for_device_preprocessing(tmp_path, problem):
+    exe = build_harness.build_cpu()
+    problem["model"].astype(np.float32).tofile(tmp_path / "m.f32")
+    problem["data"].astype(np.float32).tofile(tmp_path / "d.f32")
+    out = subprocess.run([exe, str(tmp_path / "m.f32"), str(tmp_path / "d.f32"), "0.03", "1e-4"], capture_output=True, text=True,
+                         env=dict(os.environ, FGOICP_DEVICE_PREPROCESS="1"), timeout=120)
+    assert out.returncode == 1 and "no CUDA device" in out.stderr

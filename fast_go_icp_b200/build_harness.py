@@ -25,21 +25,3 @@ def build(force: bool = False):
 if __name__ == "__main__":
     print(build(force=True))
 
-
-def build_cpu(force: bool = False):
-    """TEST INFRASTRUCTURE: the same harness and the same C++ host driver (csrc/fgoicp_host.cpp), linked against
-    tests/cpp/oracle_abi.c -- an oracle-backed stand-in for the C ABI -- instead of the CUDA library, so that the drop-in
-    class can be exercised without a GPU (tests/test_cpp_host_cpu.py).  Output: build/fgoicp_harness_cpu."""
-    out = os.path.join(ROOT, "build", "fgoicp_harness_cpu")
-    host = os.path.join(HERE, "csrc", "fgoicp_host.cpp")
-    abi = os.path.join(ROOT, "tests", "cpp", "oracle_abi.c")
-    oracle_dir = os.path.join(ROOT, "oracle")
-    deps = [SRC, host, abi, os.path.join(oracle_dir, "libfgoicp_oracle.so"), os.path.join(ROOT, "include", "fgoicp", "fgoicp.hpp")]
-    os.makedirs(os.path.dirname(out), exist_ok=True)
-    if not force and os.path.exists(out) and os.path.getmtime(out) >= max(os.path.getmtime(d) for d in deps):
-        return out
-    obj = os.path.join(ROOT, "build", "oracle_abi.o")
-    subprocess.run(["gcc", "-std=c11", "-O2", "-Wall", "-Wextra", "-I" + os.path.join(ROOT, "include"), "-c", abi, "-o", obj], check=True)
-    subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-I" + os.path.join(ROOT, "include"), SRC, host, obj, "-o", out,
-                    "-L" + oracle_dir, "-lfgoicp_oracle", "-Wl,-rpath," + oracle_dir, "-Wl,-rpath,$ORIGIN/../oracle", "-lpthread"], check=True)
-    return out

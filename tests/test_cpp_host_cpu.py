@@ -8,7 +8,8 @@ import subprocess
 import numpy as np
 import pytest
 
-from fast_go_icp_b200 import build_harness, driver, workloads
+import cpu_harness
+from fast_go_icp_b200 import driver, workloads
 from oracle import oracle as O
 from oracle_context import OracleContext
 
@@ -16,7 +17,7 @@ GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "bunny
 
 
 def _run_cpp(tmp_path, model, data, res, mse, **env):
-    exe = build_harness.build_cpu()
+    exe = cpu_harness.build_cpu()
     np.ascontiguousarray(model, np.float32).tofile(tmp_path / "model.f32")
     np.ascontiguousarray(data, np.float32).tofile(tmp_path / "data.f32")
     e = dict(os.environ)
@@ -69,7 +70,7 @@ def test_cpp_class_on_the_full_bunny_pair_lands_on_the_gpu_bits(tmp_path):
 
 
 def test_cpp_class_reports_a_missing_gpu_for_device_preprocessing(tmp_path, problem):
-    exe = build_harness.build_cpu()
+    exe = cpu_harness.build_cpu()
     problem["model"].astype(np.float32).tofile(tmp_path / "m.f32")
     problem["data"].astype(np.float32).tofile(tmp_path / "d.f32")
     out = subprocess.run([exe, str(tmp_path / "m.f32"), str(tmp_path / "d.f32"), "0.03", "1e-4"], capture_output=True, text=True,

@@ -14,6 +14,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <queue>
+#include <thread>
 
 namespace icp
 {
@@ -74,6 +75,20 @@ namespace icp
         if (const char* s = std::getenv("FGOICP_SKIP_DEAD_LB")) options_.skip_dead_lb = std::atoi(s) != 0;
         if (const char* s = std::getenv("FGOICP_TRIM_FRACTION")) options_.trim_fraction = static_cast<float>(std::atof(s));
         if (const char* s = std::getenv("FGOICP_DEVICE_PREPROCESS")) options_.device_preprocess = std::atoi(s) != 0;
+        if (const char* s = std::getenv("FGOICP_DEVICES"))
+        {
+            options_.devices.clear();
+            for (const char* p = s; *p;)
+            {
+                char* end = nullptr;
+                long d = std::strtol(p, &end, 10);
+                if (end == p) break;
+                options_.devices.push_back(static_cast<int>(d));
+                p = (*end == ',') ? end + 1 : end;
+            }
+        }
+        if (options_.devices.empty()) options_.devices.push_back(options_.device);
+        options_.device = options_.devices.front();
         preprocess_clouds();
         init(_lut_resolution);
     }
@@ -108,11 +123,30 @@ namespace icp
         static_assert(sizeof(glm::vec3) == 3 * sizeof(float), "glm::vec3 must be three packed floats");
         unsigned flags = FGOICP_BUILD_PACKED;
         if (options_.sampler == FGOICP_SAMPLER_TEX) flags |= FGOICP_BUILD_TEX;
-        check(fgoicp_ctx_create(reinterpret_cast<const float*>(pct.data()), nt,
-                                reinterpret_cast<const float*>(pcs.data()), ns,
-                                bmin, bmax, lut_resolution, options_.device, flags, &ctx_),
-              "fgoicp_ctx_create");
-        if (options_.sampler >= 0) check(fgoicp_set_sampler(ctx_, options_.sampler), "fgoicp_set_sampler");
+        // one context per device (clouds and grids are replicated); built concurrently, one host thread each
+        const size_t K = options_.devices.size();
+        ctxs_.assign(K, nullptr);
+        {
+            std::vector<std::string> errors(K);
+            auto make = [&](size_t k)
+            {
+                int rc = fgoicp_ctx_create(reinterpret_cast<const float*>(pct.data()), nt,
+                                           reinterpret_cast<const float*>(pcs.data()), ns,
+                                           bmin, bmax, lut_resolution, options_.devices[k], flags, &ctxs_[k]);
+                if (rc == FGOICP_OK && options_.sampler >= 0) rc = fgoicp_set_sampler(ctxs_[k], options_.sampler);
+                if (rc != FGOICP_OK) errors[k] = std::string("fgoicp_ctx_create: ") + fgoicp_last_error();   // message is per thread
+            };
+            if (K == 1) make(0);
+            else
+            {
+                std::vector<std::thread> th;
+                for (size_t k = 0; k < K; ++k) th.emplace_back(make, k);
+                for (auto& t : th) t.join();
+            }
+            ctx_ = ctxs_[0];
+            for (size_t k = 0; k < K; ++k)
+                if (!errors[k].empty()) throw ApiError(errors[k]);
+        }
         fgoicp_info info;
         check(fgoicp_ctx_info(ctx_, &info), "fgoicp_ctx_info");
         if (info.dims[0] >= 1024 || info.dims[1] >= 1024 || info.dims[2] >= 1024)
@@ -124,7 +158,7 @@ namespace icp
             // trimmed registration (extension; the reference only parses `trim`): sums over the n_inliers smallest
             // residuals, threshold scaled accordingly (Go-ICP: SSEThresh = MSEThresh * inlierNum)
             std::uint64_t k = ns;
-            check(fgoicp_set_trim(ctx_, options_.trim_fraction, &k), "fgoicp_set_trim");
+            for (fgoicp_ctx* c : ctxs_) check(fgoicp_set_trim(c, options_.trim_fraction, &k), "fgoicp_set_trim");
             n_inliers = static_cast<size_t>(k);
             sse_threshold = static_cast<float>(n_inliers) * mse_threshold;
         }
@@ -133,7 +167,123 @@ namespace icp
 
     FastGoICP::~FastGoICP()
     {
-        fgoicp_ctx_destroy(ctx_);
+        for (fgoicp_ctx* c : ctxs_) fgoicp_ctx_destroy(c);
+    }
+
+    // One wave of the fixed-rotation phase (inner searches + ICP on promising cubes) over all devices.  The cubes are
+    // dealt round-robin; every device works against the same wave-start best_sse, so which cube is refined and what
+    // every search returns do not depend on the number of devices.  The new incumbent is the MIN over
+    // (sse, index of the cube within the wave) -- the cube a single device's ascending scan would have picked.
+    void FastGoICP::level_ub(const float* cubes, int m, float* ub, float* bt, float& level_best, float* bR, float* bT,
+                             fgoicp_level_stats& st)
+    {
+        const int K = static_cast<int>(ctxs_.size());
+        if (K == 1 || m < 2)
+        {
+            check(fgoicp_so3_level_ub(ctx_, cubes, m, best_sse, sse_threshold, ub, bt, &level_best, bR, bT, &st), "fgoicp_so3_level_ub");
+            return;
+        }
+        struct Shard
+        {
+            std::vector<float> cubes, ub, bt;
+            float best, R[9], t[3];
+            fgoicp_level_stats st;
+            std::string error;
+        };
+        std::vector<Shard> sh(K);
+        const float start_best = best_sse;
+        for (int k = 0; k < K; ++k)
+        {
+            const int mk = (m - k + K - 1) / K;
+            sh[k].cubes.resize(4 * static_cast<size_t>(mk)); sh[k].ub.resize(mk); sh[k].bt.resize(3 * static_cast<size_t>(mk));
+            for (int j = 0; j < mk; ++j) std::memcpy(&sh[k].cubes[4 * j], cubes + 4 * (k + j * K), 4 * sizeof(float));
+            sh[k].best = start_best;
+            std::memcpy(sh[k].R, bR, sizeof(sh[k].R)); std::memcpy(sh[k].t, bT, sizeof(sh[k].t));
+            std::memset(&sh[k].st, 0, sizeof(sh[k].st)); sh[k].st.best_icp_index = -1;
+        }
+        auto work = [&](int k)
+        {
+            Shard& s = sh[k];
+            const int mk = static_cast<int>(s.ub.size());
+            if (mk == 0) return;
+            int rc = fgoicp_so3_level_ub(ctxs_[k], s.cubes.data(), mk, start_best, sse_threshold, s.ub.data(), s.bt.data(),
+                                         &s.best, s.R, s.t, &s.st);
+            if (rc != FGOICP_OK) s.error = std::string("fgoicp_so3_level_ub: ") + fgoicp_last_error();
+        };
+        {
+            std::vector<std::thread> th;
+            for (int k = 1; k < K; ++k) th.emplace_back(work, k);
+            work(0);
+            for (auto& t : th) t.join();
+        }
+        std::memset(&st, 0, sizeof(st)); st.best_icp_index = -1;
+        int winner = -1, winner_index = 0;
+        for (int k = 0; k < K; ++k)
+        {
+            Shard& s = sh[k];
+            if (!s.error.empty()) throw ApiError(s.error);
+            const int mk = static_cast<int>(s.ub.size());
+            for (int j = 0; j < mk; ++j)
+            {
+                ub[k + j * K] = s.ub[j];
+                std::memcpy(bt + 3 * (k + j * K), &s.bt[3 * j], 3 * sizeof(float));
+            }
+            st.evals += s.st.evals; st.n_icp += s.st.n_icp; st.icp_iters += s.st.icp_iters;
+            st.ms_bnb_ub = std::max(st.ms_bnb_ub, s.st.ms_bnb_ub); st.ms_icp = std::max(st.ms_icp, s.st.ms_icp);
+            if (s.st.best_icp_index >= 0 && s.best < start_best)
+            {
+                const int gi = k + s.st.best_icp_index * K;
+                if (winner < 0 || s.best < sh[winner].best || (s.best == sh[winner].best && gi < winner_index)) { winner = k; winner_index = gi; }
+            }
+        }
+        if (winner >= 0)
+        {
+            level_best = sh[winner].best;
+            std::memcpy(bR, sh[winner].R, sizeof(sh[winner].R)); std::memcpy(bT, sh[winner].t, sizeof(sh[winner].t));
+            st.best_icp_index = winner_index;
+        }
+    }
+
+    // Rotation-uncertainty searches of a level over all devices (independent per cube).
+    void FastGoICP::level_lb(const float* cubes, int n, float* lb, fgoicp_level_stats& st)
+    {
+        const int K = static_cast<int>(ctxs_.size());
+        if (K == 1 || n < 2)
+        {
+            check(fgoicp_so3_level_lb(ctx_, cubes, n, best_sse, sse_threshold, lb, &st), "fgoicp_so3_level_lb");
+            return;
+        }
+        std::vector<std::vector<float>> sc(K), sl(K);
+        std::vector<fgoicp_level_stats> ss(K);
+        std::vector<std::string> errors(K);
+        for (int k = 0; k < K; ++k)
+        {
+            const int nk = (n - k + K - 1) / K;
+            sc[k].resize(4 * static_cast<size_t>(nk)); sl[k].resize(nk);
+            for (int j = 0; j < nk; ++j) std::memcpy(&sc[k][4 * j], cubes + 4 * (k + j * K), 4 * sizeof(float));
+            std::memset(&ss[k], 0, sizeof(ss[k]));
+        }
+        auto work = [&](int k)
+        {
+            const int nk = static_cast<int>(sl[k].size());
+            if (nk == 0) return;
+            int rc = fgoicp_so3_level_lb(ctxs_[k], sc[k].data(), nk, best_sse, sse_threshold, sl[k].data(), &ss[k]);
+            if (rc != FGOICP_OK) errors[k] = std::string("fgoicp_so3_level_lb: ") + fgoicp_last_error();
+        };
+        {
+            std::vector<std::thread> th;
+            for (int k = 1; k < K; ++k) th.emplace_back(work, k);
+            work(0);
+            for (auto& t : th) t.join();
+        }
+        std::memset(&st, 0, sizeof(st));
+        for (int k = 0; k < K; ++k)
+        {
+            if (!errors[k].empty()) throw ApiError(errors[k]);
+            for (size_t j = 0; j < sl[k].size(); ++j) lb[k + static_cast<int>(j) * K] = sl[k][j];
+            st.evals += ss[k].evals;
+            st.ms_bnb_lb = std::max(st.ms_bnb_lb, ss[k].ms_bnb_lb);
+        }
     }
 
     float FastGoICP::icp(int max_iter, float thr, const glm::mat3& R0, const glm::vec3& t0, glm::mat3& R, glm::vec3& t)
@@ -244,8 +394,7 @@ namespace icp
                 to_array(best_rotation, bR);
                 float level_best = best_sse;
                 fgoicp_level_stats st{};
-                check(fgoicp_so3_level_ub(ctx_, wc.data(), m, best_sse, sse_threshold, wub.data(), wbt.data(),
-                                          &level_best, bR, bT, &st), "fgoicp_so3_level_ub");
+                level_ub(wc.data(), m, wub.data(), wbt.data(), level_best, bR, bT, st);
                 for (int k = 0; k < m; ++k)
                 {
                     ub[wave[k]] = wub[k];
@@ -269,8 +418,7 @@ namespace icp
                 std::fill(lb.begin(), lb.end(), 0.0f);
             }
             else
-                check(fgoicp_so3_level_lb(ctx_, cubes.data(), n, best_sse, sse_threshold, lb.data(), &st_lb),
-                      "fgoicp_so3_level_lb");
+                level_lb(cubes.data(), n, lb.data(), st_lb);
             for (int i = 0; i < n; ++i)
             {
                 if (lb[i] >= best_sse) continue;

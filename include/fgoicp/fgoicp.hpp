@@ -14,6 +14,7 @@
 #include <mutex>
 
 struct fgoicp_ctx;
+struct fgoicp_level_stats;
 
 namespace icp
 {
@@ -31,6 +32,7 @@ namespace icp
         {
             Schedule schedule = Schedule::Level;
             int device = 0;
+            std::vector<int> devices;  // more than one entry: one context per device, every wave of a level sharded over them (env FGOICP_DEVICES=0,1,...)
             int sampler = -1;        // FGOICP_SAMPLER_*, -1 = library default
             int wave1 = 32;          // first-wave size of a level (then x4, x16, rest): early ICPs tighten best_sse; 0: no split
             bool skip_dead_lb = true; // skip the leaf level's rotation-uncertainty searches (they cannot change any output)
@@ -118,7 +120,8 @@ namespace icp
 
         Options options_;
         Stats stats_;
-        fgoicp_ctx* ctx_ = nullptr;
+        fgoicp_ctx* ctx_ = nullptr;            // context of the first device (ICPs of run(), best-first schedule)
+        std::vector<fgoicp_ctx*> ctxs_;        // one per device; ctxs_[0] == ctx_
 
         void init(float lut_resolution);
         void preprocess_clouds();
@@ -132,6 +135,8 @@ namespace icp
 
         float icp(int max_iter, float thr, const glm::mat3& R0, const glm::vec3& t0, glm::mat3& R, glm::vec3& t);
         void search_level_synchronous();
+        void level_ub(const float* cubes, int m, float* ub, float* bt, float& level_best, float* bR, float* bT, fgoicp_level_stats& st);
+        void level_lb(const float* cubes, int n, float* lb, fgoicp_level_stats& st);
         void search_best_first();
     };
 }

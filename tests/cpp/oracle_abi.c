@@ -6,9 +6,15 @@
  * Linked ONLY into build/fgoicp_harness_cpu by tests/test_cpp_host_cpu.py; never part of libfgoicp_b200.so. */
 #include <fgoicp_c.h>
 
+#include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+
+/* the oracle keeps process-wide state (k-d tree cache, trim switch): calls from the host driver's per-device threads
+ * are serialised here -- the stand-in checks the driver's sharding logic, not concurrency of the oracle */
+static pthread_mutex_t g_lock = PTHREAD_MUTEX_INITIALIZER;
+static int g_contexts_created = 0;
 
 /* oracle exports (oracle/fgoicp_oracle.c) */
 void orc_lut_dims(const float* bbox_min, const float* bbox_max, float res, int* dims);
@@ -39,12 +45,15 @@ int fgoicp_ctx_create(const float* model_xyz, size_t nt, const float* data_xyz, 
 {
     fgoicp_ctx* c;
     size_t cells;
-    (void)device; (void)flags;
+    (void)flags;
     if (!out || !model_xyz || !data_xyz || nt == 0 || ns == 0 || !(lut_resolution > 0.0f))
     {
         snprintf(g_err, sizeof(g_err), "bad argument");
         return FGOICP_ERR_ARG;
     }
+    pthread_mutex_lock(&g_lock);
+    ++g_contexts_created;
+    if (getenv("ORACLE_ABI_TRACE")) fprintf(stderr, "oracle_abi: context %d on device %d\n", g_contexts_created, device);
     c = (fgoicp_ctx*)calloc(1, sizeof(*c));
     c->nt = nt; c->ns = ns; c->res = lut_resolution;
     c->model = (float*)malloc(sizeof(float) * 3 * nt); memcpy(c->model, model_xyz, sizeof(float) * 3 * nt);
@@ -55,6 +64,7 @@ int fgoicp_ctx_create(const float* model_xyz, size_t nt, const float* data_xyz, 
     c->lut = (float*)malloc(sizeof(float) * cells);
     orc_lut_build(c->model, nt, bbox_min, lut_resolution, c->dims, c->lut);
     *out = c;
+    pthread_mutex_unlock(&g_lock);
     return FGOICP_OK;
 }
 
@@ -97,7 +107,10 @@ int fgoicp_icp(fgoicp_ctx* c, const float R0[9], const float t0[3], int max_iter
 {
     float Ro[9], to[3];
     int it = 0;
-    float e = orc_icp(c->model, c->nt, c->data, c->ns, max_iter, thr, R0, t0, Ro, to, &it);
+    float e;
+    pthread_mutex_lock(&g_lock);
+    e = orc_icp(c->model, c->nt, c->data, c->ns, max_iter, thr, R0, t0, Ro, to, &it);
+    pthread_mutex_unlock(&g_lock);
     if (sse) *sse = e;
     if (R) memcpy(R, Ro, sizeof(Ro));
     if (t) memcpy(t, to, sizeof(to));
@@ -105,8 +118,8 @@ int fgoicp_icp(fgoicp_ctx* c, const float R0[9], const float t0[3], int max_iter
     return FGOICP_OK;
 }
 
-int fgoicp_bnb_r3(fgoicp_ctx* c, const float rot_xyz_span[4], int fix_rot, float best_sse, float sse_threshold,
-                  float* best_ub, float best_t[3], uint64_t* evals)
+static int bnb_r3_unlocked(fgoicp_ctx* c, const float rot_xyz_span[4], int fix_rot, float best_sse, float sse_threshold,
+                           float* best_ub, float best_t[3], uint64_t* evals)
 {
     uint64_t ev = 0;
     uint32_t nb = 0;
@@ -119,6 +132,16 @@ int fgoicp_bnb_r3(fgoicp_ctx* c, const float rot_xyz_span[4], int fix_rot, float
     return FGOICP_OK;
 }
 
+int fgoicp_bnb_r3(fgoicp_ctx* c, const float rot_xyz_span[4], int fix_rot, float best_sse, float sse_threshold,
+                  float* best_ub, float best_t[3], uint64_t* evals)
+{
+    int rc;
+    pthread_mutex_lock(&g_lock);
+    rc = bnb_r3_unlocked(c, rot_xyz_span, fix_rot, best_sse, sse_threshold, best_ub, best_t, evals);
+    pthread_mutex_unlock(&g_lock);
+    return rc;
+}
+
 /* csrc/bnb.cu fgoicp_so3_level_ub: fixed-rotation searches of every cube against the level-start best_sse, then ICP on
  * the cubes with ub < 1.8 * best_sse (double compare), winners taken in ascending cube order */
 int fgoicp_so3_level_ub(fgoicp_ctx* c, const float* cubes, int n, float best_sse, float sse_threshold, float* ub, float* bt,
@@ -126,10 +149,11 @@ int fgoicp_so3_level_ub(fgoicp_ctx* c, const float* cubes, int n, float best_sse
 {
     int i;
     if (stats) { memset(stats, 0, sizeof(*stats)); stats->best_icp_index = -1; }
+    pthread_mutex_lock(&g_lock);
     for (i = 0; i < n; ++i)
     {
         uint64_t ev = 0;
-        fgoicp_bnb_r3(c, cubes + 4 * i, 1, best_sse, sse_threshold, &ub[i], bt + 3 * i, &ev);
+        bnb_r3_unlocked(c, cubes + 4 * i, 1, best_sse, sse_threshold, &ub[i], bt + 3 * i, &ev);
         if (stats) stats->evals += ev;
     }
     for (i = 0; i < n; ++i)
@@ -147,6 +171,7 @@ int fgoicp_so3_level_ub(fgoicp_ctx* c, const float* cubes, int n, float best_sse
             if (stats) stats->best_icp_index = i;
         }
     }
+    pthread_mutex_unlock(&g_lock);
     return FGOICP_OK;
 }
 
@@ -155,12 +180,14 @@ int fgoicp_so3_level_lb(fgoicp_ctx* c, const float* cubes, int n, float best_sse
 {
     int i;
     if (stats) memset(stats, 0, sizeof(*stats));
+    pthread_mutex_lock(&g_lock);
     for (i = 0; i < n; ++i)
     {
         uint64_t ev = 0;
         float dummy[3];
-        fgoicp_bnb_r3(c, cubes + 4 * i, 0, best_sse, sse_threshold, &lb[i], dummy, &ev);
+        bnb_r3_unlocked(c, cubes + 4 * i, 0, best_sse, sse_threshold, &lb[i], dummy, &ev);
         if (stats) stats->evals += ev;
     }
+    pthread_mutex_unlock(&g_lock);
     return FGOICP_OK;
 }

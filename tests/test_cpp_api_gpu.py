@@ -53,6 +53,17 @@ def test_cpp_class_device_preprocess_is_bit_identical(tmp_path, problem):
     assert np.array_equal(a["R"], b["R"]) and np.array_equal(a["t"], b["t"]) and a["sse"] == b["sse"] and a["scale"] == b["scale"]
 
 
+def test_cpp_class_frontier_sharded_over_two_gpus(tmp_path, problem):
+    """FGOICP_DEVICES=0,1: one context per GPU inside the C++ class, waves dealt over them by host threads (the sharding
+    logic itself is tested on the CPU in tests/test_cpp_host_cpu.py).  Needs two GPUs."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    a = _run_harness(tmp_path, problem, 0.02, 1e-4)
+    b = _run_harness(tmp_path, problem, 0.02, 1e-4, FGOICP_DEVICES="0,1")
+    assert np.array_equal(a["R"], b["R"]) and np.array_equal(a["t"], b["t"]) and a["sse"] == b["sse"]
+
+
 def test_cpp_class_reference_schedule(tmp_path, problem):
     """FGOICP_SCHEDULE=bestfirst: the reference's own visiting order (fgoicp.cpp:32-100), one cube at a time.  It stops
     as soon as best_sse - lb <= sse_threshold, so it agrees with the level schedule within that threshold."""

@@ -48,6 +48,24 @@ def test_cpp_level_schedule_equals_python_driver(tmp_path, problem):
     assert ang < 2.0 and np.linalg.norm(cpp["t"] - w["t_true"]) < 0.03
 
 
+@pytest.mark.parametrize("devices", ["0,1", "0,1,2,3,4"])
+def test_cpp_frontier_sharded_over_devices_changes_no_bit(tmp_path, problem, devices):
+    """FGOICP_DEVICES: one context per device, every wave of a level dealt round-robin over them by host threads, the new
+    incumbent taken as the MIN over (sse, cube index).  Same pose, SSE and total counts as one device (the stand-in's
+    "devices" are all the CPU oracle: this checks the sharding and merging logic of the host driver)."""
+    w = problem
+    one = _run_cpp(tmp_path, w["model"], w["data"], 0.03, 1e-4)
+    exe = cpu_harness.build_cpu()
+    e = dict(os.environ, FGOICP_DEVICES=devices, ORACLE_ABI_TRACE="1")
+    out = subprocess.run([exe, str(tmp_path / "model.f32"), str(tmp_path / "data.f32"), "0.03", "0.0001"], capture_output=True, text=True,
+                         env=e, timeout=900)
+    assert out.returncode == 0, out.stderr
+    assert out.stderr.count("oracle_abi: context") == len(devices.split(","))
+    many = _run_cpp(tmp_path, w["model"], w["data"], 0.03, 1e-4, FGOICP_DEVICES=devices)
+    assert many["sse"] == one["sse"] and np.array_equal(many["R"], one["R"]) and np.array_equal(many["t"], one["t"])
+    assert [many["evals"], many["cubes"], many["icps"]] == [one["evals"], one["cubes"], one["icps"]]
+
+
 def test_cpp_reference_schedule_agrees_with_the_oracle_run(tmp_path, problem):
     """FGOICP_SCHEDULE=bestfirst is the reference's own order (fgoicp.cpp:32-100), which the oracle's orc_run restates:
     same registration (the heaps may order exact ties differently, so the comparison is the stated tolerance, not bits)."""

@@ -26,3 +26,16 @@ for tag, case in (("mse1e-3", "W1 bunny res 0.005"), ("mse1e-5", "W1 bunny res 0
 path = os.path.join(ROOT, "tests", "golden", "bunny_full.npz")
 np.savez_compressed(path, **out)
 print("wrote", path, os.path.getsize(path), "bytes", {k: (v.shape if hasattr(v, "shape") else v) for k, v in out.items()})
+
+# W3: the two dragon range scans at full size (75,305 / 10,000 points) -- the ICP-heavy case (2,498 refinements, 46,588
+# ICP iterations; the CPU oracle reproduces the mse 1e-3 result bit for bit in 343 s, profiles/fullsize_parity_r01.log)
+out = dict(model=z["dragon_model"], data=z["dragon_data"])
+for tag, case in (("mse1e-3", "W3 dragon"), ("mse1e-4", "W3 dragon mse 1e-4")):
+    o = [r for r in rows if r["case"] == case][0]["ours"]
+    out["gpu_R_" + tag] = np.asarray(o["R"], np.float32)
+    out["gpu_t_" + tag] = np.asarray(o["t"], np.float32)
+    out["gpu_sse_" + tag] = np.float32(o["sse"])
+    out["gpu_counts_" + tag] = np.array([o["bound_evals"], o["rot_cubes"], o["icp_runs"]], np.int64)
+path = os.path.join(ROOT, "tests", "golden", "dragon_full.npz")
+np.savez_compressed(path, **out)
+print("wrote", path, os.path.getsize(path), "bytes")

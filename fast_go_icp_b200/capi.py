@@ -19,7 +19,7 @@ BUILD_DEFAULT = BUILD_PACKED | BUILD_TEX
 
 EXPORTS = [
     "fgoicp_last_error", "fgoicp_version", "fgoicp_ctx_create", "fgoicp_ctx_destroy", "fgoicp_ctx_info",
-    "fgoicp_set_sampler", "fgoicp_set_trim", "fgoicp_set_stream", "fgoicp_set_nn_mode", "fgoicp_set_phased", "fgoicp_set_bnb_mode", "fgoicp_gather_probe", "fgoicp_lut_download", "fgoicp_lut_sample", "fgoicp_rot_sin",
+    "fgoicp_set_sampler", "fgoicp_set_trim", "fgoicp_set_stream", "fgoicp_set_nn_mode", "fgoicp_set_phased", "fgoicp_set_bnb_mode", "fgoicp_set_icp_mode", "fgoicp_gather_probe", "fgoicp_lut_download", "fgoicp_lut_sample", "fgoicp_rot_sin",
     "fgoicp_bounds_batch", "fgoicp_bounds_multi", "fgoicp_bounds_multi_dev", "fgoicp_sse", "fgoicp_nn",
     "fgoicp_icp", "fgoicp_bnb_r3", "fgoicp_bnb_r3_batch", "fgoicp_so3_level_ub", "fgoicp_so3_level_lb",
     "fgoicp_preprocess", "fgoicp_preprocess_dev", "fgoicp_icp_batch",
@@ -75,6 +75,7 @@ def lib():
     L.fgoicp_set_nn_mode.argtypes = [vp, C.c_int]
     L.fgoicp_set_phased.argtypes = [vp, C.c_int]
     L.fgoicp_set_bnb_mode.argtypes = [vp, C.c_int]
+    L.fgoicp_set_icp_mode.argtypes = [vp, C.c_int]
     L.fgoicp_set_trim.argtypes = [vp, C.c_float, C.POINTER(C.c_uint64)]
     L.fgoicp_gather_probe.argtypes = [vp, C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_float)]
     L.fgoicp_lut_download.argtypes = [vp, _f32p, C.c_size_t]
@@ -178,6 +179,10 @@ class Context:
     def set_bnb_mode(self, mode):
         """0: automatic, 1: persistent per-cube searches, 2: round-synchronous searches (same results)."""
         _check(lib().fgoicp_set_bnb_mode(self._h, int(mode)), "fgoicp_set_bnb_mode")
+
+    def set_icp_mode(self, mode):
+        """0: persistent loop kernel (default), 1: one launch per stage and iteration (same results)."""
+        _check(lib().fgoicp_set_icp_mode(self._h, int(mode)), "fgoicp_set_icp_mode")
 
     def set_phased(self, on):
         _check(lib().fgoicp_set_phased(self._h, int(bool(on))), "fgoicp_set_phased")

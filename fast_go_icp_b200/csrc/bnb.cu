@@ -588,6 +588,7 @@ static int bnb_rounds(fgoicp_ctx* c, const float4* d_rot, int Rn, int fix_rot, f
     const bool log_rounds = getenv("FGOICP_BNBR_LOG") != nullptr;
     auto t_prev = std::chrono::steady_clock::now();
     // a search pops at most 4681 cubes, at least one per round
+    bool drained = false;
     for (int round = 0; round < 4700; ++round)
     {
         FG_CUDA(cudaMemsetAsync(d_ctl, 0, 8, c->stream));
@@ -603,7 +604,7 @@ static int bnb_rounds(fgoicp_ctx* c, const float4* d_rot, int Rn, int fix_rot, f
                     std::chrono::duration<double, std::micro>(now - t_prev).count());
             t_prev = now;
         }
-        if (active == 0) break;
+        if (active == 0) { drained = true; break; }
         bool phased = can_phase && pairs >= min_pairs;
         if (phased)
         {
@@ -628,6 +629,8 @@ static int bnb_rounds(fgoicp_ctx* c, const float4* d_rot, int Rn, int fix_rot, f
             if (rc) return rc;
         }
     }
+    // never hand unfinished bounds to the pruning logic above
+    if (!drained) { fg::set_error("inner search did not terminate (round cap reached with live searches)"); return FGOICP_ERR_STATE; }
     k_bnbr_export<<<(Rn + 127) / 128, 128, 0, c->stream>>>(d_meta, Rn, d_out);
     FG_CUDA(cudaGetLastError());
     return FGOICP_OK;

@@ -105,6 +105,7 @@ struct fgoicp_ctx
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    size_t restore_l2_fetch = 0;   // previous cudaLimitMaxL2FetchGranularity when FGOICP_L2_FETCH changed it (0: untouched)
 
     size_t nt = 0, ns = 0;
     float4* d_model = nullptr;     // (x, y, z, index-as-bits)   [nt]
@@ -158,6 +159,9 @@ struct fgoicp_ctx
     float4* d_nnmemo = nullptr;               // winner memo of the ICP searches: scan position + proven clearance [icp_capacity][ns]
     void* d_icp_jobs = nullptr;               // job queue of a batch of refinements: counters, seed poses, results (nn_icp.cu)
     size_t icp_jobs_bytes = 0;
+    void* d_icp_loop = nullptr;               // persistent ICP loop kernel: control block, reduction partials, miss list (nn_icp.cu)
+    int icp_mode = 0;                         // 0: persistent loop kernel (default), 1: launch chain (test hook, trimmed runs)
+    int icp_loop_grid = 0;                    // co-resident blocks of k_icp_loop on this device (0: not yet queried)
 };
 
 namespace fg

@@ -495,6 +495,8 @@ static int build_texture(fgoicp_ctx* c)
     return FGOICP_OK;
 }
 
+int fg_icp_prealloc(fgoicp_ctx* c);
+
 extern "C" const char* fgoicp_last_error(void) { return fg::g_last_error.c_str(); }
 extern "C" const char* fgoicp_version(void) { return "fgoicp-b200 0.1 (sm_100a)"; }
 
@@ -520,25 +522,32 @@ extern "C" int fgoicp_ctx_create(const float* model_xyz, size_t nt, const float*
     FG_ARG(device >= 0 && device < ndev, "device index out of range");
     FG_CUDA(cudaSetDevice(device));
 
-    // The bound kernels gather one random 32-byte sector per evaluation from a grid far larger than L2.
-    // With the default L2 fetch granularity every such miss pulls ~3 sectors from HBM (measured with ncu:
-    // 95 B of DRAM traffic per 32 B requested), i.e. two thirds of the HBM bandwidth is wasted.  Ask for
-    // sector-granular fills.  (A hint; FGOICP_L2_FETCH=64|128 restores coarser fills for experiments.)
+    // L2 fetch granularity is DEVICE-WIDE state shared with everything else in the process, so the library leaves it
+    // alone by default (measured on B200: 32-byte fills change nothing for the 32-byte cell gathers -- an L2 miss
+    // still moves a 64-byte DRAM atom).  FGOICP_L2_FETCH=32|64|128 sets it for experiments; the previous value is
+    // restored by fgoicp_ctx_destroy.
+    size_t prev_gran = 0;
+    if (const char* eg = getenv("FGOICP_L2_FETCH"))
     {
-        size_t gran = 32;
-        if (const char* e = getenv("FGOICP_L2_FETCH")) gran = (size_t)atoi(e);
-        if (gran == 32 || gran == 64 || gran == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
+        size_t gran = (size_t)atoi(eg);
+        if ((gran == 32 || gran == 64 || gran == 128) && cudaDeviceGetLimit(&prev_gran, cudaLimitMaxL2FetchGranularity) == cudaSuccess)
+            cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
+        else prev_gran = 0;
     }
 
     fgoicp_ctx* c = new fgoicp_ctx();
     c->device = device;
+    c->restore_l2_fetch = prev_gran;
+    // from here on every failure goes through fgoicp_ctx_destroy (no leaked context, streams or events)
+#define FG_TRY0(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { int code__ = fg::cuda_fail(e__, #call, __FILE__, __LINE__); fgoicp_ctx_destroy(c); return code__; } } while (0)
     cudaDeviceProp prop;
-    FG_CUDA(cudaGetDeviceProperties(&prop, device));
+    FG_TRY0(cudaGetDeviceProperties(&prop, device));
     c->sm_count = prop.multiProcessorCount;
-    FG_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    FG_TRY0(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
-    FG_CUDA(cudaEventCreate(&c->ev0));
-    FG_CUDA(cudaEventCreate(&c->ev1));
+    FG_TRY0(cudaEventCreate(&c->ev0));
+    FG_TRY0(cudaEventCreate(&c->ev1));
+#undef FG_TRY0
     c->nt = nt; c->ns = ns; c->res = lut_resolution;
     for (int a = 0; a < 3; ++a) { c->bbox_min[a] = bbox_min[a]; c->bbox_max[a] = bbox_max[a]; }
 
@@ -654,6 +663,12 @@ extern "C" int fgoicp_ctx_create(const float* model_xyz, size_t nt, const float*
     d_P = nullptr;
 #undef FG_TRY
     c->sampler = c->d_packed ? FGOICP_SAMPLER_PACKED : FGOICP_SAMPLER_GRID;
+    if (const char* e = getenv("FGOICP_ICP_MODE")) c->icp_mode = atoi(e) == 1 ? 1 : 0;
+    // buffers of the refinements and of the level driver: allocated here, never inside run()
+    rc = fg_icp_prealloc(c);
+    if (rc) { fgoicp_ctx_destroy(c); return rc; }
+    rc = fg::ensure_scratch(c, (size_t)8 << 20);
+    if (rc) { fgoicp_ctx_destroy(c); return rc; }
     // phase-ordered evaluation is the default for the flat bound entry points (bit-identical results, ~1.6x);
     // FGOICP_PHASED=0 selects the plain kernel
     c->phased = c->d_packed != nullptr;
@@ -670,12 +685,13 @@ extern "C" int fgoicp_ctx_destroy(fgoicp_ctx* c)
     if (c->lut.tex) cudaDestroyTextureObject(c->lut.tex);
     if (c->arr) cudaFreeArray(c->arr);
     cudaFree(c->d_model); cudaFree(c->d_data); cudaFree(c->d_data_orig); cudaFree(c->d_grid); cudaFree(c->d_packed);
-    cudaFree(c->d_scratch); cudaFree(c->d_work); cudaFree(c->d_nnkey); cudaFree(c->d_icp); cudaFree(c->d_inl); cudaFree(c->d_icp_part); cudaFree(c->d_icp_jobs); cudaFree(c->d_nnmemo);
+    cudaFree(c->d_scratch); cudaFree(c->d_work); cudaFree(c->d_nnkey); cudaFree(c->d_icp); cudaFree(c->d_inl); cudaFree(c->d_icp_part); cudaFree(c->d_icp_jobs); cudaFree(c->d_nnmemo); cudaFree(c->d_icp_loop);
     cudaFree(c->d_cell_start); cudaFree(c->d_cell_P); cudaFree(c->d_cell_M); cudaFree(c->d_phase); cudaFree(c->d_rounds);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    if (c->restore_l2_fetch) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, c->restore_l2_fetch);
     delete c;
     return FGOICP_OK;
 }

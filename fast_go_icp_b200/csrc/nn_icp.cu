@@ -19,6 +19,8 @@
 #include "svd3_device.cuh"
 #include "trim.cuh"
 
+#include <cooperative_groups.h>
+
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -226,59 +228,19 @@ __device__ __forceinline__ float fg_shrink(float d2, float margin)
 #ifndef NN_FAST_ROOTED
 #define NN_FAST_ROOTED 1      // 0: always the exact rooted scan (measured: ICP 86 -> 71 ms on W5 with 1)
 #endif
+// The exact search of ONE query by one team of NN_LPQ lanes (a whole warp by default): steps 1-3 above.  `prev` is the
+// warm start -- the winner of the previous pass of the ICP loop (0xffffffff: none), taken at a position a rounding error
+// (squared pass -> next rooted pass) or one ICP increment (rooted -> squared pass) away: its distance is an upper bound on
+// the nearest distance, usually the nearest distance itself, and shrinks the ball from "node distance + 2 x offset to the
+// node" to just that.  Only the radius changes: the scan still visits every point inside it, so the result (tie rule
+// included) is the same.  Returns the packed winner (value bits << 32 | index), all ones if the cloud is empty;
+// `rho` receives the proven clearance of the winner (winner memo) when want_rho is set.  Shared by k_nn_grid and by the
+// persistent ICP loop kernel, so both produce the same bits by construction.
 template <int ROOTED>
-__global__ void __launch_bounds__(NNG_WARPS * 32)
-k_nn_grid(CellGrid g, LutDev L, float res, const float4* __restrict__ data, const float4* __restrict__ work_base,
-          int ns, char* inst_base, int src_sel, int pose_sel, unsigned long long* __restrict__ keys_base, int check_done,
-          const float4* __restrict__ model_by_index, float4* __restrict__ memo_base, float margin)
+__device__ __forceinline__ unsigned long long fg_nn_scan(const CellGrid& g, const LutDev& L, float res, float qx, float qy, float qz,
+                                                         unsigned int prev, const float4* __restrict__ model_by_index, float margin,
+                                                         bool want_rho, int lane, unsigned int team_mask, float& rho)
 {
-    IcpInst* inst = fg_inst(inst_base, blockIdx.y);
-    if (check_done && inst->st.done) return;
-    const float4* src = src_sel == SRC_DATA ? data : work_base + (size_t)blockIdx.y * ns;
-    const float* pose = fg_pose(inst, pose_sel);
-    unsigned long long* keys = keys_base + (size_t)blockIdx.y * ns;
-    float4* memo = memo_base ? memo_base + (size_t)blockIdx.y * ns : nullptr;
-    // NN_LPQ lanes per query (a whole warp by default; smaller teams put more queries in flight but were measured
-    // slower: the rows of a query are better spread over 32 lanes).  Teams of one warp never talk to each other:
-    // every shuffle is confined to the team's lanes.
-    const int lane = threadIdx.x & (NN_LPQ - 1);
-    const unsigned int team_mask = NN_LPQ == 32 ? 0xffffffffu : (((1u << NN_LPQ) - 1u) << ((threadIdx.x & 31) & ~(NN_LPQ - 1)));
-    const int i = (blockIdx.x * NNG_WARPS * 32 + threadIdx.x) / NN_LPQ;
-    if (i >= ns) return;
-    float4 p = src[i];
-    float qx = p.x, qy = p.y, qz = p.z;
-    if (pose)
-    {
-        float R[9];
-#pragma unroll
-        for (int k = 0; k < 9; ++k) R[k] = pose[k];
-        float3 rp = fg_rotate(R, p.x, p.y, p.z);
-        qx = __fadd_rn(rp.x, pose[9]); qy = __fadd_rn(rp.y, pose[10]); qz = __fadd_rn(rp.z, pose[11]);
-    }
-    // Winner memo (ICP loop).  The last full scan of this point, done at position memo.xyz, proved a clearance
-    // memo.w: the winner stays the unique nearest point (by a margin far above fp32 rounding, so under both tie
-    // rules) for every query within that distance of the scan position.  The two searches of an ICP iteration --
-    // composed pose on the original point (icp3d.cu:103) and the incrementally moved working copy (icp3d.cu:146) --
-    // sit a rounding error apart, and late iterations move points by less than the gap to the runner-up: such
-    // queries need one distance evaluation instead of a scan.  Only provably unchanged winners take this path.
-    if (memo && model_by_index)
-    {
-        const float4 mm = memo[i];
-        const unsigned int prev = (unsigned int)(keys[i] & 0xffffffffull);
-        if (prev != 0xffffffffu && mm.w > 0.0f)
-        {
-            const float ex = qx - mm.x, ey = qy - mm.y, ez = qz - mm.z;
-            const float moved = sqrtf(ex * ex + ey * ey + ez * ez) * 1.0001f + 1e-9f;
-            if (moved < mm.w)
-            {
-                const float4 m = __ldg(model_by_index + prev);
-                float d = fg_sq3(__fsub_rn(qx, m.x), __fsub_rn(qy, m.y), __fsub_rn(qz, m.z));
-                if (ROOTED) d = __fsqrt_rn(d);
-                if (lane == 0) keys[i] = ((unsigned long long)__float_as_uint(d) << 32) | prev;
-                return;
-            }
-        }
-    }
     // LUT-space position (binning frame) and the nearest grid node
     float lx = qx + L.ox, ly = qy + L.oy, lz = qz + L.oz;
     int nx = min(max(__float2int_rn(lx * L.scale), 0), L.dx - 1);
@@ -287,14 +249,9 @@ k_nn_grid(CellGrid g, LutDev L, float res, const float4* __restrict__ data, cons
     float Tn = __ldg(L.grid + ((size_t)nz * L.dy + ny) * L.dx + nx);
     float ex = lx - (float)nx * res, ey = ly - (float)ny * res, ez = lz - (float)nz * res;
     float U = (sqrtf(Tn) + sqrtf(ex * ex + ey * ey + ez * ez)) * 1.0001f + 1e-6f;
-    // Warm start (ICP loop): keys[i] still holds this point's winner of the previous pass, taken at a position a
-    // rounding error (squared pass -> next rooted pass) or one ICP increment (rooted -> squared pass) away.  Its
-    // distance is an upper bound on the nearest distance, usually the nearest distance itself, and shrinks the
-    // ball from "node distance + 2 x offset to the node" to just that.  Only the radius changes: the scan still
-    // visits every point inside it, so the result (tie rule included) is the same.
+    // warm start: see above
     if (model_by_index)
     {
-        unsigned int prev = (unsigned int)(keys[i] & 0xffffffffull);
         if (prev != 0xffffffffu)
         {
             float4 m = __ldg(model_by_index + prev);
@@ -310,7 +267,7 @@ k_nn_grid(CellGrid g, LutDev L, float res, const float4* __restrict__ data, cons
     // tracks the runner-up distance; only if that falls in the window is the query redone with the exact rule.
     const float U2_0 = U2;
     unsigned long long key = 0xffffffffffffffffull;
-    float rho = 0.0f;                                              // proven clearance of the winner (winner memo)
+    rho = 0.0f;                                                    // proven clearance of the winner (winner memo)
 #pragma unroll 1
     for (int exact = (ROOTED && NN_FAST_ROOTED) ? 0 : 1; exact < 2; ++exact)
     {
@@ -444,7 +401,7 @@ k_nn_grid(CellGrid g, LutDev L, float res, const float4* __restrict__ data, cons
         unsigned long long other = __shfl_xor_sync(team_mask, key, o, NN_LPQ);
         key = other < key ? other : key;
     }
-    if (memo && (!ROOTED || !exact) && key != 0xffffffffffffffffull)
+    if (want_rho && (!ROOTED || !exact) && key != 0xffffffffffffffffull)
     {
         // Clearance: every point other than the winner is either a candidate this scan has seen (runner-up distance
         // `other`, equal to the winner's on a tie) or lies outside the final ball (all pruning is conservative by
@@ -472,6 +429,65 @@ k_nn_grid(CellGrid g, LutDev L, float res, const float4* __restrict__ data, cons
         }
     }
     }   // exact
+    return key;
+}
+
+template <int ROOTED>
+__global__ void __launch_bounds__(NNG_WARPS * 32)
+k_nn_grid(CellGrid g, LutDev L, float res, const float4* __restrict__ data, const float4* __restrict__ work_base,
+          int ns, char* inst_base, int src_sel, int pose_sel, unsigned long long* __restrict__ keys_base, int check_done,
+          const float4* __restrict__ model_by_index, float4* __restrict__ memo_base, float margin)
+{
+    IcpInst* inst = fg_inst(inst_base, blockIdx.y);
+    if (check_done && inst->st.done) return;
+    const float4* src = src_sel == SRC_DATA ? data : work_base + (size_t)blockIdx.y * ns;
+    const float* pose = fg_pose(inst, pose_sel);
+    unsigned long long* keys = keys_base + (size_t)blockIdx.y * ns;
+    float4* memo = memo_base ? memo_base + (size_t)blockIdx.y * ns : nullptr;
+    // NN_LPQ lanes per query (a whole warp by default; smaller teams put more queries in flight but were measured
+    // slower: the rows of a query are better spread over 32 lanes).  Teams of one warp never talk to each other:
+    // every shuffle is confined to the team's lanes.
+    const int lane = threadIdx.x & (NN_LPQ - 1);
+    const unsigned int team_mask = NN_LPQ == 32 ? 0xffffffffu : (((1u << NN_LPQ) - 1u) << ((threadIdx.x & 31) & ~(NN_LPQ - 1)));
+    const int i = (blockIdx.x * NNG_WARPS * 32 + threadIdx.x) / NN_LPQ;
+    if (i >= ns) return;
+    float4 p = src[i];
+    float qx = p.x, qy = p.y, qz = p.z;
+    if (pose)
+    {
+        float R[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) R[k] = pose[k];
+        float3 rp = fg_rotate(R, p.x, p.y, p.z);
+        qx = __fadd_rn(rp.x, pose[9]); qy = __fadd_rn(rp.y, pose[10]); qz = __fadd_rn(rp.z, pose[11]);
+    }
+    // Winner memo (ICP loop).  The last full scan of this point, done at position memo.xyz, proved a clearance
+    // memo.w: the winner stays the unique nearest point (by a margin far above fp32 rounding, so under both tie
+    // rules) for every query within that distance of the scan position.  The two searches of an ICP iteration --
+    // composed pose on the original point (icp3d.cu:103) and the incrementally moved working copy (icp3d.cu:146) --
+    // sit a rounding error apart, and late iterations move points by less than the gap to the runner-up: such
+    // queries need one distance evaluation instead of a scan.  Only provably unchanged winners take this path.
+    if (memo && model_by_index)
+    {
+        const float4 mm = memo[i];
+        const unsigned int prev = (unsigned int)(keys[i] & 0xffffffffull);
+        if (prev != 0xffffffffu && mm.w > 0.0f)
+        {
+            const float ex = qx - mm.x, ey = qy - mm.y, ez = qz - mm.z;
+            const float moved = sqrtf(ex * ex + ey * ey + ez * ez) * 1.0001f + 1e-9f;
+            if (moved < mm.w)
+            {
+                const float4 m = __ldg(model_by_index + prev);
+                float d = fg_sq3(__fsub_rn(qx, m.x), __fsub_rn(qy, m.y), __fsub_rn(qz, m.z));
+                if (ROOTED) d = __fsqrt_rn(d);
+                if (lane == 0) keys[i] = ((unsigned long long)__float_as_uint(d) << 32) | prev;
+                return;
+            }
+        }
+    }
+    const unsigned int prev = model_by_index ? (unsigned int)(keys[i] & 0xffffffffull) : 0xffffffffu;
+    float rho;
+    const unsigned long long key = fg_nn_scan<ROOTED>(g, L, res, qx, qy, qz, prev, model_by_index, margin, memo != nullptr, lane, team_mask, rho);
     if (lane == 0)
     {
         keys[i] = key;
@@ -681,10 +697,9 @@ __global__ void k_icp_prepare(const float4* __restrict__ data, float4* work_base
 
 // End of every loop body: loop head of the next iteration; a slot whose refinement has ended publishes the result
 // and takes the next pending job.
-__global__ void k_icp_next(char* inst_base, const float* __restrict__ jobs, IcpResult* __restrict__ results,
-                           IcpQueue* q, int max_iter, float thr)
+__device__ __forceinline__ void fg_icp_next_job(IcpInst* in, const float* __restrict__ jobs, IcpResult* __restrict__ results,
+                                                IcpQueue* q, int max_iter, float thr)
 {
-    IcpInst* in = fg_inst(inst_base, blockIdx.x);
     IcpState* st = &in->st;
     in->fresh = 0;
     if (!st->done) fg_icp_loop_head(st);
@@ -701,6 +716,12 @@ __global__ void k_icp_next(char* inst_base, const float* __restrict__ jobs, IcpR
         fg_icp_seed(in, jobs + 12 * j, j, max_iter, thr);
         fg_icp_loop_head(st);                                    // loop head of iteration 1 (ends at once if max_iter == 0)
     }
+}
+
+__global__ void k_icp_next(char* inst_base, const float* __restrict__ jobs, IcpResult* __restrict__ results,
+                           IcpQueue* q, int max_iter, float thr)
+{
+    fg_icp_next_job(fg_inst(inst_base, blockIdx.x), jobs, results, q, max_iter, thr);
 }
 
 // ---- Procrustes step over ICP_NB blocks per instance ------------------------------------------------------
@@ -768,6 +789,34 @@ k_icp_centroids(const float4* __restrict__ work_base, const unsigned long long* 
     }
 }
 
+// closest rotation of the summed cross-covariance, increment and composed pose (icp3d.cu:164-172, 101-102);
+// one thread per instance
+__device__ __noinline__ void fg_icp_pose_update(IcpState* st, const double* sums9)
+{
+    const float ab[3] = { st->abar[0], st->abar[1], st->abar[2] };
+    const float bb[3] = { st->bbar[0], st->bbar[1], st->bbar[2] };
+    float ABt[9], Rd[9], td[3], Rn[9], tn[3];
+    for (int k = 0; k < 9; ++k) ABt[k] = (float)sums9[k];
+    fg_closest_rotation(ABt, Rd);
+    // host-side glm arithmetic in the reference: unfused, left to right
+    for (int r = 0; r < 3; ++r)
+    {
+        float ra = __fadd_rn(__fadd_rn(__fmul_rn(Rd[r], ab[0]), __fmul_rn(Rd[3 + r], ab[1])), __fmul_rn(Rd[6 + r], ab[2]));
+        td[r] = __fsub_rn(bb[r], ra);                                                   // icp3d.cu:169
+    }
+    for (int c = 0; c < 3; ++c)
+        for (int r = 0; r < 3; ++r)
+            Rn[c * 3 + r] = __fadd_rn(__fadd_rn(__fmul_rn(Rd[r], st->R[c * 3]), __fmul_rn(Rd[3 + r], st->R[c * 3 + 1])),
+                                      __fmul_rn(Rd[6 + r], st->R[c * 3 + 2]));          // R = R_ * R  (icp3d.cu:101)
+    for (int r = 0; r < 3; ++r)
+    {
+        float rt = __fadd_rn(__fadd_rn(__fmul_rn(Rd[r], st->t[0]), __fmul_rn(Rd[3 + r], st->t[1])), __fmul_rn(Rd[6 + r], st->t[2]));
+        tn[r] = __fadd_rn(rt, td[r]);                                                   // t = R_ * t + t_  (icp3d.cu:102)
+    }
+    for (int k = 0; k < 9; ++k) { st->Rd[k] = Rd[k]; st->R[k] = Rn[k]; }
+    for (int k = 0; k < 3; ++k) { st->td[k] = td[k]; st->t[k] = tn[k]; }
+}
+
 // cross-covariance of the centred clouds, closest rotation, pose update (icp3d.cu:158-172, 101-102)
 __global__ void __launch_bounds__(ICP_BT)
 k_icp_procrustes(const float4* __restrict__ work_base, const unsigned long long* __restrict__ keys_base,
@@ -801,43 +850,371 @@ k_icp_procrustes(const float4* __restrict__ work_base, const unsigned long long*
                 v[c * 3 + r] += (double)__fmul_rn(a[r], b[c]);
     }
     if (!fg_grid_sum<9>(v, part_base + (size_t)inst * ICP_NB * ICP_PART, counters + 2 * inst + 1, s_out)) return;
-    if (threadIdx.x == 0)
+    if (threadIdx.x == 0) fg_icp_pose_update(st, s_out);
+}
+
+// ---- the whole ICP loop in ONE persistent cooperative kernel ---------------------------------------------------
+// The launch chain above costs nine launches per iteration, each a whole-GPU ramp-up for a few microseconds of work,
+// plus a host poll every eight iterations; a search on partial-overlap scans runs ~46,000 such iterations (W3), and on
+// W5 the refinements of the two coarse levels are pure latency.  k_icp_loop keeps every block of the GPU resident for
+// the whole batch and walks the same stages separated by grid-wide barriers (cooperative launch):
+//   S1  thread per (slot, point): fresh slots get W = pose0 * data; the winner memo is tested by ONE THREAD per query
+//       (the chain spent a whole warp on it); queries it cannot answer go to a miss list          (icp3d.cu:85, 146)
+//   S2  warp per miss, dealt dynamically: the exact rooted search (fg_nn_scan, the same code as k_nn_grid)
+//   S3  centroids: fp64 partial sums per (slot, 512-point chunk)                                   (icp3d.cu:150-156)
+//   S4  cross-covariance partials; every block folds the centroid partials itself, in chunk order  (icp3d.cu:158-163)
+//   S5  one thread per slot: fold, closest rotation (fp64 Jacobi SVD), pose update                 (icp3d.cu:164-172, 101-102)
+//   S6  W = Rd * W + td, query = R * data + t, memo test for the squared search                    (icp3d.cu:100, 103)
+//   S7  warp per miss: exact squared search
+//   S8  SSE partials per (slot, chunk);  S9  one thread per slot: fold, loop head, publish / next job (icp3d.cu:94-98)
+// The chunk partition depends on ns alone and partials are folded in chunk order, so results do not depend on the
+// grid size, the slot a refinement ran in or what its neighbours did; per-point values come from the same device
+// functions as the chain, and every sum is fp64 of fp32 terms rounded once.
+// The host launches it once per batch and synchronises once: no polls, no allocation, ~9 barriers per iteration.
+namespace cgrp = cooperative_groups;
+
+#define ICPL_THREADS 512
+#define ICPL_CHUNK   512                // points per reduction item
+#define ICPL_PART    32                 // doubles per (slot, chunk): [0,6) centroids, [8,17) cross-covariance, [24] SSE
+
+struct IcpLoopCtl
+{
+    unsigned int n_miss_a, next_a;      // rooted search: misses appended / handed out
+    unsigned int n_miss_b, next_b;      // squared search
+    int error;                          // 1: iteration guard hit
+    unsigned int iterations;            // loop trips (diagnostics)
+    unsigned int scans_a, scans_b;      // full scans run (diagnostics: the rest were memo hits)
+};
+
+struct IcpLoopArgs
+{
+    CellGrid g; LutDev L; float res;
+    const float4* data; const float4* model; float4* work; unsigned long long* keys; float4* memo;
+    char* inst; int ns, S;
+    const float* jobs; IcpResult* results; IcpQueue* q; int max_iter; float thr;
+    double* part; unsigned int* miss; IcpLoopCtl* ctl;
+    float margin; long long guard_max;
+};
+
+// winner memo, one thread per query (see k_nn_grid): true = the previous winner provably still wins, key rewritten
+template <int ROOTED>
+__device__ __forceinline__ bool fg_memo_hit(float qx, float qy, float qz, const float4 mm, unsigned long long old_key,
+                                            const float4* __restrict__ model, unsigned long long& new_key)
+{
+    const unsigned int prev = (unsigned int)(old_key & 0xffffffffull);
+    if (prev == 0xffffffffu || !(mm.w > 0.0f)) return false;
+    const float ex = qx - mm.x, ey = qy - mm.y, ez = qz - mm.z;
+    const float moved = sqrtf(ex * ex + ey * ey + ez * ez) * 1.0001f + 1e-9f;
+    if (!(moved < mm.w)) return false;
+    const float4 m = __ldg(model + prev);
+    float d = fg_sq3(__fsub_rn(qx, m.x), __fsub_rn(qy, m.y), __fsub_rn(qz, m.z));
+    if (ROOTED) d = __fsqrt_rn(d);
+    new_key = ((unsigned long long)__float_as_uint(d) << 32) | prev;
+    return true;
+}
+
+// append the items of the warp's lanes whose `miss` is set to the list (one atomic per warp)
+__device__ __forceinline__ void fg_miss_append(bool miss, unsigned int item, unsigned int* counter, unsigned int* list, int lane)
+{
+    const unsigned int m = __ballot_sync(0xffffffffu, miss);
+    if (m == 0) return;
+    unsigned int base = 0;
+    if (lane == __ffs(m) - 1) base = atomicAdd(counter, (unsigned int)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+    if (miss) list[base + __popc(m & ((1u << lane) - 1u))] = item;
+}
+
+__global__ void __launch_bounds__(ICPL_THREADS, 2)
+k_icp_loop(IcpLoopArgs a)
+{
+    cgrp::grid_group grid = cgrp::this_grid();
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int gthreads = (int)gridDim.x * ICPL_THREADS, gtid = (int)blockIdx.x * ICPL_THREADS + tid;
+    const int gwarps = gthreads >> 5;
+    const int ns = a.ns, S = a.S;
+    const int NC = (ns + ICPL_CHUNK - 1) / ICPL_CHUNK;
+    const int items = S * ns;
+    __shared__ double s_out[16];
+    __shared__ float s_ab[6];
+
+    // first jobs of the batch: slot k runs job k (k_icp_assign)
+    if (gtid < S)
     {
-        float ABt[9], Rd[9], td[3], Rn[9], tn[3];
-        for (int k = 0; k < 9; ++k) ABt[k] = (float)s_out[k];
-        fg_closest_rotation(ABt, Rd);
-        // host-side glm arithmetic in the reference: unfused, left to right
-        for (int r = 0; r < 3; ++r)
+        IcpInst* in = fg_inst(a.inst, gtid);
+        fg_icp_seed(in, a.jobs + 12 * gtid, gtid, a.max_iter, a.thr);
+        fg_icp_loop_head(&in->st);                               // loop head of iteration 1
+    }
+
+    for (long long it = 0;; ++it)
+    {
+        grid.sync();                                             // slot states of the prologue / of S9 are visible
         {
-            float ra = __fadd_rn(__fadd_rn(__fmul_rn(Rd[r], ab[0]), __fmul_rn(Rd[3 + r], ab[1])), __fmul_rn(Rd[6 + r], ab[2]));
-            td[r] = __fsub_rn(bb[r], ra);                                                   // icp3d.cu:169
+            const volatile IcpQueue* vq = a.q;
+            if (vq->finished >= vq->n_jobs) break;               // uniform: nobody writes the queue before the next S9
         }
-        for (int c = 0; c < 3; ++c)
-            for (int r = 0; r < 3; ++r)
-                Rn[c * 3 + r] = __fadd_rn(__fadd_rn(__fmul_rn(Rd[r], st->R[c * 3]), __fmul_rn(Rd[3 + r], st->R[c * 3 + 1])),
-                                          __fmul_rn(Rd[6 + r], st->R[c * 3 + 2]));          // R = R_ * R  (icp3d.cu:101)
-        for (int r = 0; r < 3; ++r)
+        if (it >= a.guard_max) { if (gtid == 0) a.ctl->error = 1; break; }
+
+        // ---- S1: working copies of fresh slots, memo test of the rooted search
+        for (int base = gtid - lane; base < items; base += gthreads)
         {
-            float rt = __fadd_rn(__fadd_rn(__fmul_rn(Rd[r], st->t[0]), __fmul_rn(Rd[3 + r], st->t[1])), __fmul_rn(Rd[6 + r], st->t[2]));
-            tn[r] = __fadd_rn(rt, td[r]);                                                   // t = R_ * t + t_  (icp3d.cu:102)
+            const int item = base + lane;
+            bool miss = false;
+            if (item < items)
+            {
+                const int slot = item / ns, i = item - slot * ns;
+                IcpInst* in = fg_inst(a.inst, slot);
+                if (!in->st.done)
+                {
+                    const size_t o = (size_t)slot * ns + i;
+                    if (in->fresh)
+                    {
+                        const float* pose = in->pose0;
+                        float R[9];
+#pragma unroll
+                        for (int k = 0; k < 9; ++k) R[k] = pose[k];
+                        const float4 p = a.data[i];
+                        const float3 rp = fg_rotate(R, p.x, p.y, p.z);
+                        a.work[o] = make_float4(__fadd_rn(rp.x, pose[9]), __fadd_rn(rp.y, pose[10]), __fadd_rn(rp.z, pose[11]), p.w);
+                        a.keys[o] = 0xffffffffffffffffull;
+                        miss = true;
+                    }
+                    else
+                    {
+                        const float4 w = __ldcg(a.work + o);
+                        unsigned long long nk;
+                        if (a.margin > 0.0f && fg_memo_hit<1>(w.x, w.y, w.z, __ldcg(a.memo + o), __ldcg(a.keys + o), a.model, nk)) a.keys[o] = nk;
+                        else miss = true;
+                    }
+                }
+            }
+            fg_miss_append(miss, (unsigned int)item, &a.ctl->n_miss_a, a.miss, lane);
         }
-        for (int k = 0; k < 9; ++k) { st->Rd[k] = Rd[k]; st->R[k] = Rn[k]; }
-        for (int k = 0; k < 3; ++k) { st->td[k] = td[k]; st->t[k] = tn[k]; }
+        grid.sync();
+
+        // ---- S2: exact rooted search of the misses, one warp per query, dealt dynamically in small runs
+        {
+            const unsigned int n_miss = *(volatile unsigned int*)&a.ctl->n_miss_a;
+            const unsigned int run = min(8u, max(1u, n_miss / (unsigned int)(4 * gwarps)));
+            while (true)
+            {
+                unsigned int m0 = 0;
+                if (lane == 0) m0 = atomicAdd(&a.ctl->next_a, run);
+                m0 = __shfl_sync(0xffffffffu, m0, 0);
+                if (m0 >= n_miss) break;
+                const unsigned int m1 = min(n_miss, m0 + run);
+                for (unsigned int m = m0; m < m1; ++m)
+                {
+                    const unsigned int item = __ldcg(a.miss + m);
+                    const size_t o = (size_t)item;
+                    const float4 w = __ldcg(a.work + o);
+                    const unsigned int prev = (unsigned int)(__ldcg(a.keys + o) & 0xffffffffull);
+                    float rho;
+                    const unsigned long long key = fg_nn_scan<1>(a.g, a.L, a.res, w.x, w.y, w.z, prev, a.model, a.margin, a.margin > 0.0f,
+                                                                 lane, 0xffffffffu, rho);
+                    if (lane == 0)
+                    {
+                        a.keys[o] = key;
+                        if (a.margin > 0.0f) a.memo[o] = make_float4(w.x, w.y, w.z, rho);
+                    }
+                }
+            }
+            if (gtid == 0) { a.ctl->n_miss_b = 0; a.ctl->next_b = 0; a.ctl->scans_a += n_miss; }   // the squared search's list is idle here
+        }
+        grid.sync();
+
+        // ---- S3: centroid partials of the working cloud and of its correspondences (icp3d.cu:150-156)
+        for (int it2 = blockIdx.x; it2 < S * NC; it2 += gridDim.x)
+        {
+            const int slot = it2 / NC, c = it2 - slot * NC;
+            if (fg_inst(a.inst, slot)->st.done) continue;
+            const int i = c * ICPL_CHUNK + tid;
+            double v[6] = { 0, 0, 0, 0, 0, 0 };
+            if (tid < ICPL_CHUNK && i < ns)
+            {
+                const size_t o = (size_t)slot * ns + i;
+                const float4 w4 = __ldcg(a.work + o);
+                const float4 m4 = __ldg(a.model + (unsigned int)(__ldcg(a.keys + o) & 0xffffffffull));
+                v[0] = (double)w4.x; v[1] = (double)w4.y; v[2] = (double)w4.z;
+                v[3] = (double)m4.x; v[4] = (double)m4.y; v[5] = (double)m4.z;
+            }
+            fg_block_sum<6>(v, s_out);
+            if (tid < 6) a.part[(size_t)it2 * ICPL_PART + tid] = s_out[tid];
+            __syncthreads();
+        }
+        grid.sync();
+
+        // ---- S4: cross-covariance partials of the centred clouds (icp3d.cu:158-163)
+        for (int it2 = blockIdx.x; it2 < S * NC; it2 += gridDim.x)
+        {
+            const int slot = it2 / NC, c = it2 - slot * NC;
+            IcpState* st = &fg_inst(a.inst, slot)->st;
+            if (st->done) continue;
+            if (tid < 6)
+            {
+                double acc = 0.0;
+                for (int q = 0; q < NC; ++q) acc += __ldcg(a.part + ((size_t)slot * NC + q) * ICPL_PART + tid);     // chunk order
+                s_ab[tid] = __fdiv_rn((float)acc, (float)ns);
+            }
+            __syncthreads();
+            const float ab[3] = { s_ab[0], s_ab[1], s_ab[2] }, bb[3] = { s_ab[3], s_ab[4], s_ab[5] };
+            if (c == 0 && tid < 3) { st->abar[tid] = ab[tid]; st->bbar[tid] = bb[tid]; }
+            const int i = c * ICPL_CHUNK + tid;
+            double v[9] = { 0, 0, 0, 0, 0, 0, 0, 0, 0 };
+            if (tid < ICPL_CHUNK && i < ns)
+            {
+                const size_t o = (size_t)slot * ns + i;
+                const float4 w4 = __ldcg(a.work + o);
+                const float4 m4 = __ldg(a.model + (unsigned int)(__ldcg(a.keys + o) & 0xffffffffull));
+                const float av[3] = { __fsub_rn(w4.x, ab[0]), __fsub_rn(w4.y, ab[1]), __fsub_rn(w4.z, ab[2]) };   // icp3d.cu:43
+                const float bv[3] = { __fsub_rn(m4.x, bb[0]), __fsub_rn(m4.y, bb[1]), __fsub_rn(m4.z, bb[2]) };
+                // glm::outerProduct(a, b)[c][r] = a[r] * b[c]   (icp3d.cu:51)
+#pragma unroll
+                for (int cc = 0; cc < 3; ++cc)
+#pragma unroll
+                    for (int r = 0; r < 3; ++r)
+                        v[cc * 3 + r] = (double)__fmul_rn(av[r], bv[cc]);
+            }
+            fg_block_sum<9>(v, s_out);
+            if (tid < 9) a.part[(size_t)it2 * ICPL_PART + 8 + tid] = s_out[tid];
+            __syncthreads();
+        }
+        grid.sync();
+
+        // ---- S5: closest rotation and pose update, one thread per slot (icp3d.cu:164-172, 101-102)
+        for (int slot = blockIdx.x; slot < S; slot += gridDim.x)
+        {
+            IcpState* st = &fg_inst(a.inst, slot)->st;
+            if (st->done) continue;
+            if (tid < 9)
+            {
+                double acc = 0.0;
+                for (int q = 0; q < NC; ++q) acc += __ldcg(a.part + ((size_t)slot * NC + q) * ICPL_PART + 8 + tid);
+                s_out[tid] = acc;
+            }
+            __syncthreads();
+            if (tid == 0) fg_icp_pose_update(st, s_out);
+            __syncthreads();
+        }
+        grid.sync();
+
+        // ---- S6: W = Rd * W + td (icp3d.cu:100); query of the SSE search = R * data + t (icp3d.cu:103); memo test
+        for (int base = gtid - lane; base < items; base += gthreads)
+        {
+            const int item = base + lane;
+            bool miss = false;
+            if (item < items)
+            {
+                const int slot = item / ns, i = item - slot * ns;
+                IcpInst* in = fg_inst(a.inst, slot);
+                if (!in->st.done)
+                {
+                    const size_t o = (size_t)slot * ns + i;
+                    const IcpState* st = &in->st;
+                    float Rd[9], R[9];
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) { Rd[k] = st->Rd[k]; R[k] = st->R[k]; }
+                    const float4 w = __ldcg(a.work + o);
+                    const float3 rw = fg_rotate(Rd, w.x, w.y, w.z);
+                    a.work[o] = make_float4(__fadd_rn(rw.x, st->td[0]), __fadd_rn(rw.y, st->td[1]), __fadd_rn(rw.z, st->td[2]), w.w);
+                    const float4 p = a.data[i];
+                    const float3 rp = fg_rotate(R, p.x, p.y, p.z);
+                    const float qx = __fadd_rn(rp.x, st->t[0]), qy = __fadd_rn(rp.y, st->t[1]), qz = __fadd_rn(rp.z, st->t[2]);
+                    unsigned long long nk;
+                    if (a.margin > 0.0f && fg_memo_hit<0>(qx, qy, qz, __ldcg(a.memo + o), __ldcg(a.keys + o), a.model, nk)) a.keys[o] = nk;
+                    else miss = true;
+                }
+            }
+            fg_miss_append(miss, (unsigned int)item, &a.ctl->n_miss_b, a.miss, lane);
+        }
+        grid.sync();
+
+        // ---- S7: exact squared search of the misses
+        {
+            const unsigned int n_miss = *(volatile unsigned int*)&a.ctl->n_miss_b;
+            const unsigned int run = min(8u, max(1u, n_miss / (unsigned int)(4 * gwarps)));
+            while (true)
+            {
+                unsigned int m0 = 0;
+                if (lane == 0) m0 = atomicAdd(&a.ctl->next_b, run);
+                m0 = __shfl_sync(0xffffffffu, m0, 0);
+                if (m0 >= n_miss) break;
+                const unsigned int m1 = min(n_miss, m0 + run);
+                for (unsigned int m = m0; m < m1; ++m)
+                {
+                    const unsigned int item = __ldcg(a.miss + m);
+                    const int slot = (int)(item / (unsigned int)ns), i = (int)(item - (unsigned int)slot * (unsigned int)ns);
+                    const size_t o = (size_t)item;
+                    const IcpState* st = &fg_inst(a.inst, slot)->st;
+                    float R[9];
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) R[k] = st->R[k];
+                    const float4 p = a.data[i];
+                    const float3 rp = fg_rotate(R, p.x, p.y, p.z);
+                    const float qx = __fadd_rn(rp.x, st->t[0]), qy = __fadd_rn(rp.y, st->t[1]), qz = __fadd_rn(rp.z, st->t[2]);
+                    const unsigned int prev = (unsigned int)(__ldcg(a.keys + o) & 0xffffffffull);
+                    float rho;
+                    const unsigned long long key = fg_nn_scan<0>(a.g, a.L, a.res, qx, qy, qz, prev, a.model, a.margin, a.margin > 0.0f,
+                                                                 lane, 0xffffffffu, rho);
+                    if (lane == 0)
+                    {
+                        a.keys[o] = key;
+                        if (a.margin > 0.0f) a.memo[o] = make_float4(qx, qy, qz, rho);
+                    }
+                }
+            }
+            if (gtid == 0) { a.ctl->n_miss_a = 0; a.ctl->next_a = 0; a.ctl->scans_b += n_miss; a.ctl->iterations += 1; }
+        }
+        grid.sync();
+
+        // ---- S8: SSE partials (keys carry d2 bits in the high word)
+        for (int it2 = blockIdx.x; it2 < S * NC; it2 += gridDim.x)
+        {
+            const int slot = it2 / NC, c = it2 - slot * NC;
+            if (fg_inst(a.inst, slot)->st.done) continue;
+            const int i = c * ICPL_CHUNK + tid;
+            double v[1] = { 0.0 };
+            if (tid < ICPL_CHUNK && i < ns) v[0] = (double)__uint_as_float((unsigned int)(__ldcg(a.keys + (size_t)slot * ns + i) >> 32));
+            fg_block_sum<1>(v, s_out);
+            if (tid == 0) a.part[(size_t)it2 * ICPL_PART + 24] = s_out[0];
+            __syncthreads();
+        }
+        grid.sync();
+
+        // ---- S9: SSE, loop head of the next iteration, publish / next job (k_sse_reduce + k_icp_next)
+        for (int slot = blockIdx.x * ICPL_THREADS + tid; slot < S; slot += gthreads)
+        {
+            IcpInst* in = fg_inst(a.inst, slot);
+            IcpState* st = &in->st;
+            if (!st->done)
+            {
+                double acc = 0.0;
+                for (int q = 0; q < NC; ++q) acc += __ldcg(a.part + ((size_t)slot * NC + q) * ICPL_PART + 24);
+                st->sse = (float)acc;
+            }
+            fg_icp_next_job(in, a.jobs, a.results, a.q, a.max_iter, a.thr);
+        }
     }
 }
 
 // ---------------------------------------------------------------------------------------------
 
+static size_t icp_loop_part_bytes(const fgoicp_ctx* c, int n)
+{
+    const size_t nc = (c->ns + ICPL_CHUNK - 1) / ICPL_CHUNK;
+    return sizeof(double) * ICPL_PART * nc * (size_t)n;
+}
+static size_t icp_loop_bytes(const fgoicp_ctx* c, int n) { return 256 + icp_loop_part_bytes(c, n) + sizeof(unsigned int) * c->ns * (size_t)n; }
+
 // per-context ICP buffers sized for `n` concurrent instances
-static int ensure_icp_capacity(fgoicp_ctx* c, int n)
+int fg_ensure_icp_capacity(fgoicp_ctx* c, int n)
 {
     if (n <= c->icp_capacity) return FGOICP_OK;
     // size for a whole batch at once when that is cheap (25 bytes per instance and data point): the capacity then
     // never changes during a search (no cudaFree / cudaMalloc between levels)
     if ((size_t)ICP_MAX_BATCH * c->ns * 41 <= ((size_t)512 << 20)) n = std::max(n, ICP_MAX_BATCH);
     FG_CUDA(cudaStreamSynchronize(c->stream));
-    cudaFree(c->d_work); cudaFree(c->d_nnkey); cudaFree(c->d_icp); cudaFree(c->d_inl); cudaFree(c->d_icp_part); cudaFree(c->d_nnmemo);
-    c->d_work = nullptr; c->d_nnkey = nullptr; c->d_icp = nullptr; c->d_inl = nullptr; c->d_icp_part = nullptr; c->d_nnmemo = nullptr; c->icp_capacity = 0;
+    cudaFree(c->d_work); cudaFree(c->d_nnkey); cudaFree(c->d_icp); cudaFree(c->d_inl); cudaFree(c->d_icp_part); cudaFree(c->d_nnmemo); cudaFree(c->d_icp_loop);
+    c->d_work = nullptr; c->d_nnkey = nullptr; c->d_icp = nullptr; c->d_inl = nullptr; c->d_icp_part = nullptr; c->d_nnmemo = nullptr; c->d_icp_loop = nullptr; c->icp_capacity = 0;
     FG_CUDA(cudaMalloc(&c->d_work, sizeof(float4) * c->ns * n));
     FG_CUDA(cudaMalloc(&c->d_nnmemo, sizeof(float4) * c->ns * n));
     FG_CUDA(cudaMalloc(&c->d_nnkey, sizeof(unsigned long long) * c->ns * n));
@@ -847,6 +1224,8 @@ static int ensure_icp_capacity(fgoicp_ctx* c, int n)
     size_t part_bytes = sizeof(double) * ICP_NB * ICP_PART * (size_t)n;
     FG_CUDA(cudaMalloc(&c->d_icp_part, part_bytes + sizeof(unsigned int) * 2 * (size_t)n));
     FG_CUDA(cudaMemsetAsync((char*)c->d_icp_part + part_bytes, 0, sizeof(unsigned int) * 2 * (size_t)n, c->stream));
+    // persistent loop kernel: control block | partial sums [n][chunks][ICPL_PART] | miss list [n][ns]
+    FG_CUDA(cudaMalloc(&c->d_icp_loop, icp_loop_bytes(c, n)));
     c->icp_capacity = n;
     return FGOICP_OK;
 }
@@ -900,7 +1279,7 @@ static int enqueue_nn(fgoicp_ctx* c, int n_inst, int src_sel, int pose_sel, int 
 // seed poses of n instances -> pose0 slots (through pinned staging)
 static int upload_seeds(fgoicp_ctx* c, const float* R0s, const float* t0s, int n)
 {
-    int rc = ensure_icp_capacity(c, n);
+    int rc = fg_ensure_icp_capacity(c, n);
     if (rc) return rc;
     rc = fg::ensure_pinned(c, (size_t)n * (sizeof(IcpInst) + 64) + 4096);
     if (rc) return rc;
@@ -964,7 +1343,7 @@ static int icp_slots(const fgoicp_ctx* c)
     return s;
 }
 
-static int ensure_icp_jobs(fgoicp_ctx* c, int n)
+int fg_ensure_icp_jobs(fgoicp_ctx* c, int n)
 {
     size_t need = sizeof(IcpQueue) + (size_t)n * (12 * sizeof(float) + sizeof(IcpResult));
     if (need <= c->icp_jobs_bytes) return FGOICP_OK;
@@ -985,9 +1364,9 @@ int fg_icp_run_batch(fgoicp_ctx* c, const float* R0s, const float* t0s, int n, i
     FG_RANGE("fgoicp icp batch");
     if (n <= 0) return FGOICP_OK;
     const int S = std::min(n, icp_slots(c));
-    int rc = ensure_icp_capacity(c, S);
+    int rc = fg_ensure_icp_capacity(c, S);
     if (rc) return rc;
-    rc = ensure_icp_jobs(c, n);
+    rc = fg_ensure_icp_jobs(c, n);
     if (rc) return rc;
     rc = fg::ensure_pinned(c, (size_t)n * (12 * sizeof(float) + sizeof(IcpResult)) + 8192);
     if (rc) return rc;
@@ -1008,14 +1387,59 @@ int fg_icp_run_batch(fgoicp_ctx* c, const float* R0s, const float* t0s, int n, i
 
     char* inst = (char*)c->d_icp;
     const int ns = (int)c->ns;
+    const long long guard_max = ((long long)(n + S - 1) / S + 1) * ((long long)max_iter + 2) + 8;
+    bool all_done = false, results_on_host = false;
+    const bool trimmed = c->trim_k > 0 && c->trim_k < c->ns;
+    if (c->icp_mode == 0 && !trimmed && c->nn_mode == 0)
+    {
+        // ---- persistent loop kernel: one cooperative launch, one synchronisation for the whole batch
+        if (c->icp_loop_grid == 0)
+        {
+            int occ = 0;
+            FG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_icp_loop, ICPL_THREADS, 0));
+            if (occ < 1) { fg::set_error("k_icp_loop does not fit on this device"); return FGOICP_ERR_STATE; }
+            c->icp_loop_grid = c->sm_count * std::min(occ, 2);
+            if (const char* e = getenv("FGOICP_ICP_GRID")) c->icp_loop_grid = std::max(1, std::min(c->icp_loop_grid, atoi(e)));
+        }
+        static const float margin_cfg = getenv("FGOICP_NN_MARGIN") ? (float)atof(getenv("FGOICP_NN_MARGIN")) : FG_NN_MARGIN;
+        IcpLoopArgs a;
+        a.g.start = c->d_cell_start; a.g.pts = c->d_cell_M;
+        a.g.nx = c->cnx; a.g.ny = c->cny; a.g.nz = c->cnz; a.g.h = c->cell_h; a.g.inv_h = c->cell_inv_h;
+        a.L = c->lut; a.res = c->res;
+        a.data = c->d_data; a.model = c->d_model; a.work = c->d_work; a.keys = c->d_nnkey; a.memo = c->d_nnmemo;
+        a.inst = inst; a.ns = ns; a.S = S;
+        a.jobs = d_seeds; a.results = d_res; a.q = d_q; a.max_iter = max_iter; a.thr = thr;
+        a.ctl = (IcpLoopCtl*)c->d_icp_loop;
+        a.part = (double*)((char*)c->d_icp_loop + 256);
+        a.miss = (unsigned int*)((char*)c->d_icp_loop + 256 + icp_loop_part_bytes(c, c->icp_capacity));
+        a.margin = getenv("FGOICP_NN_NO_WARM") ? 0.0f : std::max(0.0f, margin_cfg);
+        a.guard_max = guard_max;
+        FG_CUDA(cudaMemsetAsync(a.ctl, 0, sizeof(IcpLoopCtl), c->stream));
+        // no more blocks than there is work for: a barrier costs time per participating block
+        // (enough warps that a first pass -- every query a full scan -- hands each warp about four of them)
+        const long long want = ((long long)S * ns + 63) / 64;
+        const int grid = (int)std::max<long long>(1, std::min<long long>(c->icp_loop_grid, want));
+        void* params[] = { &a };
+        FG_CUDA(cudaLaunchCooperativeKernel((const void*)k_icp_loop, dim3((unsigned)grid), dim3(ICPL_THREADS), params, 0, c->stream));
+        IcpLoopCtl* hctl = (IcpLoopCtl*)((char*)c->h_pinned + 2048);
+        FG_CUDA(cudaMemcpyAsync(hq, d_q, sizeof(IcpQueue), cudaMemcpyDeviceToHost, c->stream));
+        FG_CUDA(cudaMemcpyAsync(hctl, a.ctl, sizeof(IcpLoopCtl), cudaMemcpyDeviceToHost, c->stream));
+        FG_CUDA(cudaMemcpyAsync((char*)c->h_pinned + 4096, d_res, sizeof(IcpResult) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+        FG_CUDA(cudaStreamSynchronize(c->stream));
+        all_done = hq->finished >= n && hctl->error == 0;
+        results_on_host = all_done;
+        if (getenv("FGOICP_ICP_LOG"))
+            fprintf(stderr, "[icp loop] jobs %d slots %d grid %d loop trips %u full scans: rooted %u squared %u\n", n, S, grid,
+                    hctl->iterations, hctl->scans_a, hctl->scans_b);
+    }
+    else
+    {
     dim3 pgrid((unsigned)((ns + 255) / 256), (unsigned)S);
     k_icp_assign<<<S, 1, 0, c->stream>>>(inst, d_seeds, max_iter, thr);
     FG_CUDA(cudaGetLastError());
     // iterations enqueued between polls of the queue (finished slots with no job left cost only empty launches)
     const int burst = 8;
-    const long long guard_max = ((long long)(n + S - 1) / S + 1) * ((long long)max_iter + 2) + burst;
-    bool all_done = false;
-    for (long long guard = 0; guard <= guard_max && !all_done; guard += burst)
+    for (long long guard = 0; guard <= guard_max + burst && !all_done; guard += burst)
     {
         for (int b = 0; b < burst; ++b)
         {
@@ -1047,10 +1471,14 @@ int fg_icp_run_batch(fgoicp_ctx* c, const float* R0s, const float* t0s, int n, i
         FG_CUDA(cudaStreamSynchronize(c->stream));
         all_done = hq->finished >= n;
     }
+    }
     if (!all_done) { fg::set_error("ICP loop did not terminate"); return FGOICP_ERR_STATE; }
     IcpResult* hres = (IcpResult*)((char*)c->h_pinned + 4096);
-    FG_CUDA(cudaMemcpyAsync(hres, d_res, sizeof(IcpResult) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
-    FG_CUDA(cudaStreamSynchronize(c->stream));
+    if (!results_on_host)
+    {
+        FG_CUDA(cudaMemcpyAsync(hres, d_res, sizeof(IcpResult) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+        FG_CUDA(cudaStreamSynchronize(c->stream));
+    }
     for (int k = 0; k < n; ++k)
     {
         if (sse) sse[k] = hres[k].sse;
@@ -1058,6 +1486,25 @@ int fg_icp_run_batch(fgoicp_ctx* c, const float* R0s, const float* t0s, int n, i
         if (t) memcpy(t + 3 * (size_t)k, hres[k].t, 3 * sizeof(float));
         if (iters) iters[k] = hres[k].iters;
     }
+    return FGOICP_OK;
+}
+
+// Everything run() needs for its refinements, allocated once at context creation so that the timed search allocates
+// nothing (first-ICP latency used to grow with the number of processes contending in the allocator).
+int fg_icp_prealloc(fgoicp_ctx* c)
+{
+    int rc = fg_ensure_icp_capacity(c, icp_slots(c));
+    if (rc) return rc;
+    rc = fg_ensure_icp_jobs(c, 4096);
+    if (rc) return rc;
+    return fg::ensure_pinned(c, (size_t)4096 * (12 * sizeof(float) + sizeof(IcpResult)) + 8192);
+}
+
+extern "C" int fgoicp_set_icp_mode(fgoicp_ctx* c, int mode)
+{
+    FG_ARG(c, "NULL context");
+    FG_ARG(mode == 0 || mode == 1, "icp mode must be 0 (persistent loop kernel) or 1 (launch chain)");
+    c->icp_mode = mode;
     return FGOICP_OK;
 }
 

@@ -185,6 +185,7 @@ class FastGoICP:
         self.schedule = schedule
         self.wave1 = int(wave1)      # size of the first wave of a level (0: whole level at once)
         self.skip_dead_lb = bool(skip_dead_lb)
+        self.trace = None            # best-first schedule: set to [] to record (cube, ub, icp sse, best sse) per refinement
         self.best_sse = M_INF
         self.best_R = np.array([1, 0, 0, 0, 1, 0, 0, 0, 1], F)
         self.best_t = np.zeros(3, F)
@@ -265,6 +266,8 @@ class FastGoICP:
                     s["icp_iters"] += it
                     if e < self.best_sse:                                   # fgoicp.cpp:79-84
                         self.best_sse, self.best_R, self.best_t = F(e), R, t
+                    if self.trace is not None:                              # what the reference logs at fgoicp.cpp:85
+                        self.trace.append((float(cx), float(cy), float(cz), float(span), float(ub), float(e), float(self.best_sse)))
                 lb, _, ev = self.ctx.bnb_r3(cube, False, self.best_sse, thr)              # fgoicp.cpp:90
                 s["bound_evals"] += int(ev)
                 if lb >= self.best_sse:                                     # fgoicp.cpp:92

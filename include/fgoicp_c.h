@@ -141,6 +141,11 @@ int fgoicp_set_phased(fgoicp_ctx* ctx, int on);
  * thread-block cluster per search), 1 = same, explicitly, 2 = round-synchronous (all searches advance one
  * iteration per round, bounds of each round through the phase-ordered kernel).  Same results either way. */
 int fgoicp_set_bnb_mode(fgoicp_ctx* ctx, int mode);
+/* Driver of the ICP refinements behind fgoicp_icp / fgoicp_icp_batch / fgoicp_so3_level_ub: 0 = one persistent
+ * cooperative kernel per batch (default: the whole loop of icp3d.cu:85-108 on the device, one host synchronisation),
+ * 1 = one launch per stage and iteration with a host poll every 8 iterations (also used by trimmed runs).  Same
+ * results either way. */
+int fgoicp_set_icp_mode(fgoicp_ctx* ctx, int mode);
 /* Measurement hook: useful GB/s of independent random gathers of width_bytes (16/32/64/128) over a
  * buffer of `bytes` bytes -- the gather roofline the bound kernels are compared with. */
 int fgoicp_gather_probe(fgoicp_ctx* ctx, size_t bytes, int width_bytes, int blocks_per_sm, float* out_gbps);

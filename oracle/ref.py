@@ -38,6 +38,9 @@ def lib():
         L.ref_bnb_r3.restype = C.c_float
         L.ref_run.argtypes = [vp, _f32p, _f32p, _f32p, _f32p]
         L.ref_run.restype = C.c_float
+        L.ref_run_trace.argtypes = [vp, _f32p, _f32p, _f32p, C.c_int, C.POINTER(C.c_int)]
+        L.ref_run_trace.restype = C.c_float
+        L.ref_rot_sin.argtypes = [_f32p, C.c_int, _f32p]
         L.ref_sse_threshold.argtypes = [vp]
         L.ref_sse_threshold.restype = C.c_float
         _lib = L
@@ -46,6 +49,15 @@ def lib():
 
 def _f32(a):
     return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def rot_sin(spans):
+    """sin(span * sqrt3 * pi / 2) from a kernel compiled inside the reference build with the reference's constants and
+    flags (registration.cu:41-42): the values its bound kernel uses, obtained without the library under test."""
+    s = _f32(spans).ravel()
+    out = np.zeros(len(s), np.float32)
+    assert lib().ref_rot_sin(s, len(s), out) == 0
+    return out
 
 
 class Reference:
@@ -109,6 +121,13 @@ class Reference:
                         np.zeros(3, np.float32))
         sse = lib().ref_run(self._h, R, t, Rn, tn)
         return sse, R, t, Rn, tn
+
+    def run_trace(self, cap=1 << 16):
+        """run() with the Debug log on: returns (sse, R, t, best error printed after every refinement)."""
+        R, t, tr = np.zeros(9, np.float32), np.zeros(3, np.float32), np.zeros(cap, np.float32)
+        n = C.c_int(0)
+        sse = lib().ref_run_trace(self._h, R, t, tr, cap, C.byref(n))
+        return sse, R, t, tr[:min(n.value, cap)].copy()
 
     def sse_threshold(self):
         return lib().ref_sse_threshold(self._h)

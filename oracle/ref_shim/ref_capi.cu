@@ -46,6 +46,17 @@ namespace
         out[i] = tex3D<float>(tex, x, y, z);
     }
 
+    // sin(half_angle) exactly as kernComputeBounds forms it per thread (reference registration.cu:41-42), with the
+    // reference's own M_SQRT3 / M_PI (fgoicp/common.hpp:17-19) and this build's flags (same libdevice sin, no fast math):
+    // pins the four constants the oracle uses without going through the library under test
+    __global__ void k_ref_rot_sin(const float* spans, int n, float* out)
+    {
+        int i = blockIdx.x * blockDim.x + threadIdx.x;
+        if (i >= n) return;
+        float half_angle = spans[i] * M_SQRT3 * M_PI / 2.0f;
+        out[i] = sin(half_angle);
+    }
+
     // raw texel fetch through the same texture object: unnormalised coordinate i + 0.5 hits texel i exactly
     __global__ void k_ref_texels(cudaTextureObject_t tex, int dx, int dy, int dz, float* out)
     {
@@ -170,6 +181,43 @@ extern "C"
         auto [Rn, tn] = f->get_best_transform();
         from_mat3(Rn, R_norm); t_norm[0] = tn.x; t_norm[1] = tn.y; t_norm[2] = tn.z;
         return f->get_best_error();
+    }
+
+    // run() with the reference's Debug log captured: the sequence of best errors it prints after every refinement
+    // ("New best error: ...", reference fgoicp.cpp:85; 6 significant digits) -- lets a parity report name the first
+    // refinement at which another implementation's search parts ways.  Slower than ref_run (every cudaCheckError logs).
+    float ref_run_trace(void* h, float* R, float* t, float* trace, int cap, int* n_trace)
+    {
+        FastGoICP* f = static_cast<FastGoICP*>(h);
+        std::streambuf* old = std::cout.rdbuf();
+        std::ostringstream sink;
+        std::cout.rdbuf(sink.rdbuf());
+        Logger::set_verbose(true);
+        auto [Ro, to] = f->run();
+        Logger::set_verbose(false);
+        std::cout.rdbuf(old);
+        from_mat3(Ro, R); t[0] = to.x; t[1] = to.y; t[2] = to.z;
+        const std::string log = sink.str();
+        const std::string key = "New best error: ";
+        int n = 0;
+        for (size_t pos = log.find(key); pos != std::string::npos; pos = log.find(key, pos + 1))
+        {
+            if (n < cap) trace[n] = (float)atof(log.c_str() + pos + key.size());
+            ++n;
+        }
+        *n_trace = n;
+        return f->get_best_error();
+    }
+
+    int ref_rot_sin(const float* spans, int n, float* out)
+    {
+        float *ds = nullptr, *dout = nullptr;
+        cudaMalloc(&ds, sizeof(float) * n); cudaMalloc(&dout, sizeof(float) * n);
+        cudaMemcpy(ds, spans, sizeof(float) * n, cudaMemcpyHostToDevice);
+        k_ref_rot_sin<<<(n + 63) / 64, 64>>>(ds, n, dout);
+        cudaError_t e = cudaMemcpy(out, dout, sizeof(float) * n, cudaMemcpyDeviceToHost);
+        cudaFree(ds); cudaFree(dout);
+        return e == cudaSuccess ? 0 : -1;
     }
 
     float ref_sse_threshold(void* h) { return static_cast<FastGoICP*>(h)->sse_threshold; }

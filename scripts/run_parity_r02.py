@@ -1,0 +1,176 @@
+"""run() parity at full size, CUDA path vs the UNMODIFIED reference (oracle/_ref) on the same B200 (VERDICT r01, next #1a).
+
+For every workload of BASELINE.json (W1 bunny, W2 skull, W3 dragon scans, W4 partial overlap, W5 synthetic) at the sizes
+SURVEY.md 8d names:
+  * the CUDA path with schedule="bestfirst" (the reference's visiting order, fgoicp.cpp:32-100) and with the default
+    level-synchronous schedule: SSE, pose, evaluation / cube / refinement counts, wall ms;
+  * the reference's own run() in a subprocess under a wall-clock cap (its time is predicted from the CUDA path's
+    counts first; a threshold whose predicted time exceeds the cap is skipped in favour of the next looser one);
+  * relative SSE difference, rotation angle between the two poses, translation difference, and -- for the cheap pairs --
+    the sequence of best errors after every refinement on both sides with the index of the first difference.
+Writes gpurun_out/run_parity_r02.json (copied to profiles/ afterwards).
+
+    python scripts/run_parity_r02.py [--cap 300] [--only W1,W2]
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "scripts"))
+from bench_repo_clouds import load_pair  # noqa: E402
+
+# name, pair, resolution, thresholds to try (tightest first), trace?
+CASES = [
+    ("W1 bunny", "bunny", 0.005, [1e-3], True),
+    ("W2 skull", "skull", 0.005, [1e-3], True),
+    ("W5 synthetic", "w5", 0.005, [1e-4, 1e-3], False),
+    ("W3 dragon", "dragon", 0.005, [1e-4, 1e-3, 1e-2], False),
+    ("W4 partial overlap", "overlap", 0.005, [1e-4, 1e-3, 1e-2], False),
+]
+
+
+def angle(Ra, Rb):
+    return float(np.degrees(np.arccos(np.clip((np.trace(np.asarray(Ra, np.float64) @ np.asarray(Rb, np.float64).T) - 1) / 2, -1, 1))))
+
+
+def ours(pair, res, mse, schedule, trace=False):
+    from fast_go_icp_b200 import capi, driver
+    model, data, _, _ = load_pair(pair)
+    g = driver.FastGoICP(model, data, res, mse, flags=capi.BUILD_PACKED, schedule=schedule)
+    if trace:
+        g.trace = []
+    R, t = g.run()
+    st = g.stats
+    out = dict(schedule=schedule, run_ms=st["run_ms"], sse=float(g.best_sse), sse_bits=int(np.float32(g.best_sse).view(np.uint32)),
+               R=np.asarray(R, np.float32).tolist(), t=np.asarray(t, np.float32).tolist(), bound_evals=int(st["bound_evals"]),
+               rot_cubes=int(st["rot_cubes"]), icp_runs=int(st["icp_runs"]), icp_iters=int(st["icp_iters"]),
+               initial_icp_sse=st.get("initial_icp_sse"), sse_threshold=float(g.sse_threshold))
+    if trace:
+        out["trace"] = [list(x) for x in g.trace]
+    g.close()
+    return out
+
+
+def ref_child(pair, res, mse, trace):
+    from oracle import ref as REF
+    model, data, _, _ = load_pair(pair)
+    t0 = time.perf_counter()
+    r = REF.Reference(model, data, res, mse)
+    ctor_ms = (time.perf_counter() - t0) * 1e3
+    print(json.dumps(dict(stage="ctor", ctor_ms=ctor_ms)), flush=True)
+    t0 = time.perf_counter()
+    if trace:
+        sse, R, t, tr = r.run_trace()
+    else:
+        sse, R, t, _, _ = r.run()
+        tr = None
+    run_ms = (time.perf_counter() - t0) * 1e3
+    out = dict(stage="run", run_ms=run_ms, sse=float(sse), sse_bits=int(np.float32(sse).view(np.uint32)),
+               R=np.asarray(R, np.float32).reshape(3, 3).T.tolist(), t=np.asarray(t, np.float32).tolist(), traced=bool(trace))
+    if tr is not None:
+        out["trace_best"] = [float(x) for x in tr]
+    print(json.dumps(out), flush=True)
+
+
+def ref_run(pair, res, mse, cap, trace):
+    cmd = [sys.executable, os.path.abspath(__file__), "--child", pair, repr(res), repr(mse), "1" if trace else "0"]
+    t0 = time.perf_counter()
+    out, capped = "", False
+    try:
+        p = subprocess.run(cmd, capture_output=True, text=True, timeout=cap)
+        out = p.stdout
+        if p.returncode != 0:
+            return dict(error=p.stderr[-600:])
+    except subprocess.TimeoutExpired as e:
+        capped = True
+        out = (e.stdout or b"").decode() if isinstance(e.stdout, (bytes, bytearray)) else (e.stdout or "")
+    d = {}
+    for line in out.splitlines():
+        try:
+            d.update(json.loads(line))
+        except ValueError:
+            pass
+    if capped:
+        d["capped_after_s"] = time.perf_counter() - t0
+    return d
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--child", nargs=4)
+    ap.add_argument("--cap", type=float, default=300.0)
+    ap.add_argument("--only", default=None)
+    ap.add_argument("--out", default="run_parity_r02.json")
+    a = ap.parse_args()
+    if a.child:
+        ref_child(a.child[0], float(a.child[1]), float(a.child[2]), a.child[3] == "1")
+        return
+    from fast_go_icp_b200 import capi, driver, workloads
+    from oracle import ref as REF
+    ws = workloads.synthetic_pair(nt=3000, ns=400, seed=3)          # untimed warm-up: loads every kernel of the search
+    gw = driver.FastGoICP(ws["model"], ws["data"], 0.03, 1e-4, flags=capi.BUILD_PACKED)
+    gw.run()
+    gw.close()
+    rows = []
+    path = os.path.join(ROOT, "gpurun_out", a.out)
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    # 1. the CUDA path on every case and threshold (seconds each)
+    for name, pair, res, thresholds, trace in CASES:
+        if a.only and not any(tok in name for tok in a.only.split(",")):
+            continue
+        model, data, _, _ = load_pair(pair)
+        for mse in thresholds:
+            row = dict(case=name, pair=pair, nt=len(model), ns=len(data), lut_resolution=res, mse_threshold=mse, want_trace=trace)
+            row["cuda_bestfirst"] = ours(pair, res, mse, "bestfirst", trace)
+            row["cuda_level"] = ours(pair, res, mse, "level")
+            b = row["cuda_bestfirst"]
+            # the reference spends ~2.2 ms per batch of <= 32 translation cubes (2 cudaMalloc, <= 32 launches, <= 64 blocking
+            # reductions, 2 cudaFree; measured on the bunny pair) and ~(nt * ns / 2.5e11 s + 1 ms) per ICP iteration
+            batches = b["bound_evals"] / len(data) / 22.0
+            row["predicted_reference_s"] = 2.2e-3 * batches + b["icp_iters"] * (len(model) * len(data) / 2.5e11 + 1.5e-3) + 4.0
+            rows.append(row)
+            print("%-20s mse %.0e | bestfirst %8.1f ms sse %.7g cubes %d evals %.2e icps %d | level %8.1f ms sse %.7g | predicted reference %.0f s"
+                  % (name, mse, b["run_ms"], b["sse"], b["rot_cubes"], b["bound_evals"], b["icp_runs"], row["cuda_level"]["run_ms"],
+                     row["cuda_level"]["sse"], row["predicted_reference_s"]), flush=True)
+            json.dump(rows, open(path, "w"), indent=1)
+    # 2. the reference, cheapest predicted first; per case only the tightest threshold that fits the cap
+    done_case = set()
+    for row in sorted(rows, key=lambda r: r["predicted_reference_s"]):
+        if not REF.available():
+            row["reference"] = dict(error="oracle/_ref not built")
+            continue
+        tighter_fit = [r for r in rows if r["case"] == row["case"] and r["mse_threshold"] < row["mse_threshold"]
+                       and r["predicted_reference_s"] <= 0.8 * a.cap]
+        if row["case"] in done_case or tighter_fit or row["predicted_reference_s"] > 0.8 * a.cap:
+            continue
+        done_case.add(row["case"])
+        ref = ref_run(row["pair"], row["lut_resolution"], row["mse_threshold"], a.cap, row["want_trace"])
+        row["reference"] = ref
+        if "sse" in ref:
+            for key in ("cuda_bestfirst", "cuda_level"):
+                o = row[key]
+                row[key + "_vs_reference"] = dict(rel_sse=abs(o["sse"] - ref["sse"]) / ref["sse"], rot_deg=angle(o["R"], ref["R"]),
+                                                  t_diff=float(np.linalg.norm(np.asarray(o["t"]) - np.asarray(ref["t"]))),
+                                                  within_sse_threshold=bool(abs(o["sse"] - ref["sse"]) <= o["sse_threshold"]))
+            if "trace_best" in ref and "trace" in row["cuda_bestfirst"]:
+                mine = [x[6] for x in row["cuda_bestfirst"]["trace"]]
+                theirs = ref["trace_best"]
+                first = next((i for i, (x, y) in enumerate(zip(mine, theirs)) if abs(x - y) > 2e-6 * max(abs(y), 1e-30) + 5e-7), None)
+                row["trace_compare"] = dict(n_cuda=len(mine), n_reference=len(theirs), first_difference=first,
+                                            note="best error after every refinement; the reference prints 6 significant digits")
+        print("%-20s mse %.0e | reference %s | bestfirst vs ref %s | level vs ref %s"
+              % (row["case"], row["mse_threshold"], json.dumps({k: ref.get(k) for k in ("run_ms", "sse", "capped_after_s", "error") if k in ref}),
+                 json.dumps(row.get("cuda_bestfirst_vs_reference")), json.dumps(row.get("cuda_level_vs_reference"))), flush=True)
+        json.dump(rows, open(path, "w"), indent=1)
+    json.dump(rows, open(path, "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()

@@ -385,6 +385,29 @@ def test_icp_batch_equals_single_refinements(small_problem, gpu_ctx, monkeypatch
     assert len(e0) == 0
 
 
+def test_persistent_icp_loop_equals_the_launch_chain(small_problem, gpu_ctx):
+    """The persistent cooperative loop kernel (default) and the one-launch-per-stage chain walk the same ICP
+    (icp3d.cu:85-108): same iteration counts, SSE, poses -- bit for bit -- for easy and hard starts, alone and batched."""
+    rng = np.random.default_rng(77)
+    seeds_R, seeds_t = [], []
+    for k in range(17):
+        v = rng.uniform(-0.45, 0.45, 3) * (0.1 if k % 2 == 0 else 1.0)
+        seeds_R.append(O.rotation(*v.astype(np.float32))[0])
+        seeds_t.append(rng.uniform(-0.2, 0.2, 3).astype(np.float32))
+    out = {}
+    try:
+        for mode in (0, 1):
+            gpu_ctx.set_icp_mode(mode)
+            out[mode] = [gpu_ctx.icp_batch(np.array(seeds_R), np.array(seeds_t), 100, thr) for thr in (0.05, 0.005, 0.0005)]
+            out[mode].append(tuple(np.asarray(x) for x in gpu_ctx.icp(seeds_R[3], seeds_t[3], 100, 0.005)))
+    finally:
+        gpu_ctx.set_icp_mode(0)
+    for a, b in zip(out[0], out[1]):
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
+    assert out[0][1][3].max() > 10
+
+
 @pytest.mark.parametrize("which", ["synthetic", "dragon"])
 def test_winner_memo_changes_no_result(which):
     """The winner memo of the ICP searches (skip the scan when the point moved less than the clearance the last scan

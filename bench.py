@@ -132,24 +132,79 @@ def build_workload(rank):
     return w, rot, tc
 
 
+REPO_CLOUDS = [
+    # name, fixture, lut_resolution, mse_threshold, repetitions  (BASELINE.json configs 1-4 at SURVEY.md 8d's sizes; the
+    # clouds are the reference repository's own files through the seeded loader, committed under tests/golden/)
+    ("W1 bunny (test/bunny.toml: res 0.002, mse 1e-3)", "bunny", 0.002, 1e-3, 3),
+    ("W1 bunny (default res 0.005, mse 1e-3)", "bunny", 0.005, 1e-3, 3),
+    ("W2 skull (test/skull_goicp.toml sizes, mse 1e-3)", "skull", 0.005, 1e-3, 3),
+    ("W3 dragon range scans, mse 1e-4", "dragon", 0.005, 1e-4, 2),
+    ("W4 partial overlap (skull halves), mse 1e-4", "overlap", 0.005, 1e-4, 2),
+]
+
+
+def load_repo_cloud(fixture):
+    z = np.load(os.path.join(ROOT, "tests", "golden", fixture + "_full.npz"))
+    return z["model"], z["data"]
+
+
+def measure_run(model, data, res, mse, reps, device, world=1, barrier=None, **kw):
+    """run() of the Python driver (frontier sharded over the ranks) `reps` times on fresh contexts; returns the run with
+    the median wall time plus all wall times.  Wall clock around run() only (main.cpp:50-55), max over ranks."""
+    from fast_go_icp_b200 import capi, driver
+    import torch
+    runs = []
+    for _ in range(reps):
+        g = driver.FastGoICP(model, data, res, mse, device=device, flags=capi.BUILD_PACKED, **kw)
+        if barrier:
+            barrier()
+        R_out, t_out = g.run()
+        if barrier:
+            barrier()
+        st = g.stats
+        run_ms = st["run_ms"]
+        if world > 1:
+            import torch.distributed as dist
+            tr = torch.tensor([run_ms], device=torch.device("cuda", device))
+            dist.all_reduce(tr, op=dist.ReduceOp.MAX)
+            run_ms = float(tr.item())
+        search_ms = st["ms_bnb_ub"] + st["ms_bnb_lb"]
+        runs.append({"bnb_ms": run_ms, "ctor_ms": st["ctor_ms"], "lut_build_ms": st["lut_build_ms"],
+                     "sse": float(g.best_sse), "best_mse": float(g.best_sse) / g.n_inliers,
+                     "rot_cubes_local": st["rot_cubes"], "bound_evals_local": st["bound_evals"],
+                     "icp_runs_local": st["icp_runs"], "icp_iters_local": st["icp_iters"],
+                     "ms_bnb_ub": st["ms_bnb_ub"], "ms_icp": st["ms_icp"], "ms_bnb_lb": st["ms_bnb_lb"],
+                     "ms_first_icp": st.get("ms_first_icp"), "ms_final_icp": st.get("ms_final_icp"),
+                     "ms_search_wall": st.get("ms_search_wall"),
+                     "in_search_evals_per_s_local": st["bound_evals"] / (search_ms * 1e-3) if search_ms > 0 else None,
+                     "levels": st["level_log"], "_R": np.asarray(R_out), "_t_out": np.asarray(t_out)})
+        g.close()
+    order = sorted(range(reps), key=lambda k: runs[k]["bnb_ms"])
+    med = dict(runs[order[reps // 2]])
+    med["bnb_ms_all_runs"] = [r["bnb_ms"] for r in runs]
+    return med
+
+
 def cpu_baseline_sample(pp, seconds=12.0):
     """Oracle (CPU restatement) bound evaluations per second on a bounded sample of the same workload.
     The dense grid is downloaded from the GPU build (bit-identical to the oracle's own, see tests)."""
     from oracle import oracle as O
     from fast_go_icp_b200 import workloads
     lut, dims = pp["lut"], pp["dims"]
-    rot = workloads.rotation_cube_list(64, seed=99)
-    tc = workloads.translation_cube_list(T_CUBES, level=4, seed=98)
+    # the first cubes of the GPU arm's own list (rank 0), each with its own 32 translation cubes, for the whole time
+    # budget (round 1 stopped after 64 cubes = 0.13 s of work: too short to quote)
+    rot, tcs = workloads.bound_microbench(N_ROT, T_CUBES, seed=7)
     evals, t0 = 0, time.perf_counter()
     k = 0
-    while time.perf_counter() - t0 < seconds and k < len(rot):
-        R, _ = O.rotation(*rot[k, :3])
-        O.bounds(lut, dims, pp["bbox_min"], RES, pp["data"], R, float(rot[k, 3]), False, tc)
+    while time.perf_counter() - t0 < seconds:
+        R, _ = O.rotation(*rot[k % N_ROT, :3])
+        O.bounds(lut, dims, pp["bbox_min"], RES, pp["data"], R, float(rot[k % N_ROT, 3]), False, tcs[k % N_ROT])
         evals += T_CUBES * len(pp["data"])
         k += 1
     dt = time.perf_counter() - t0
     out = {"value": evals / dt, "unit": "evals/s", "cores": O.num_threads(), "kind": "port",
-           "sample": "%d rotation cubes x %d translation cubes x %d points (oracle/fgoicp_oracle.c, OpenMP)" % (k, T_CUBES, len(pp["data"]))}
+           "sample": "first %d rotation cubes of the GPU arm's list x %d translation cubes x %d points, %.1f s "
+                     "(oracle/fgoicp_oracle.c, OpenMP)" % (k, T_CUBES, len(pp["data"]), dt)}
     # the other half of the reference's CPU path BASELINE.json names ("nanoflann ICP"): the first ICP of run()
     # (fgoicp.cpp:12-14) through the oracle's exact k-d tree search (nanoflann is not in this image) -- extra keys only
     try:
@@ -292,8 +347,27 @@ def run_ours(args):
            "h2d_bytes_per_step": int(rot.nbytes + tc.nbytes), "d2h_bytes_per_step": int(lb_h.nbytes + ub_h.nbytes)}
     ctx.close()
 
+    # the same operator at the REFERENCE's call shape (Registration::compute_sse_error: one rotation cube x <= 32
+    # translation cubes per call, host buffers, registration.cu:88-152) over the first cubes of this rank's list: the
+    # figure the reference arm's `e2e` is directly comparable with (bench.py --impl reference walks the same cubes)
+    ref_shape = None
+    if rank == 0:
+        n_s = min(args.ref_rot * 8, N_ROT)
+        ctx2 = capi.Context(pp["model"], pp["data"], pp["bbox_min"], pp["bbox_max"], RES, device=local, flags=capi.BUILD_PACKED)
+        Rs = [driver.rotation_matrix(*rot[k, :3])[0] for k in range(n_s)]
+        for k in range(min(8, n_s)):
+            ctx2.bounds_batch(Rs[k], float(rot[k, 3]), False, tc[k])
+        t0 = time.perf_counter()
+        for k in range(n_s):
+            ctx2.bounds_batch(Rs[k], float(rot[k, 3]), False, tc[k])
+        dt = time.perf_counter() - t0
+        ctx2.close()
+        ref_shape = {"value": n_s * T_CUBES * NS / dt, "unit": "evals/s", "calls": n_s,
+                     "shape": "fgoicp_bounds_batch: 1 rotation cube x %d translation cubes x %d points per call, host buffers, "
+                              "synchronous (the reference's compute_sse_error call shape)" % (T_CUBES, NS)}
+
     # end-to-end Go-ICP search (the second half of the metric): run() wall time, frontier sharded over ranks
-    bnb = None
+    bnb, repo = None, None
     if not args.no_bnb:
         # one small untimed run first: loads every kernel of the search (CUDA loads modules lazily)
         from fast_go_icp_b200 import workloads
@@ -301,39 +375,38 @@ def run_ours(args):
         gw = driver.FastGoICP(ws["model"], ws["data"], 0.03, MSE_THR, device=local, flags=capi.BUILD_PACKED)
         gw.run()
         gw.close()
-        # five runs on fresh contexts; the reported one is the MEDIAN by wall time (all five are listed): run() is a
-        # chain of ~300 host round trips and a single descheduling of the host thread shows up as tens of ms
-        runs = []
-        NRUNS = 5
-        for rep in range(NRUNS):
-            g = driver.FastGoICP(w["model"], w["data"], RES, MSE_THR, device=local, flags=capi.BUILD_PACKED,
-                                 wave1=args.wave1, skip_dead_lb=not args.keep_dead_lb)
-            barrier()
-            R, t = g.run()
-            barrier()
-            st = g.stats
-            run_ms = st["run_ms"]
-            if world > 1:
-                tr = torch.tensor([run_ms], device=dev)
-                dist.all_reduce(tr, op=dist.ReduceOp.MAX)
-                run_ms = float(tr.item())
-            err_R = float(np.degrees(np.arccos(np.clip((np.trace(R @ w["R_true"].T) - 1) / 2, -1, 1))))
-            runs.append({"bnb_ms": run_ms, "ctor_ms": st["ctor_ms"], "lut_build_ms": st["lut_build_ms"],
-                         "best_mse": float(g.best_sse) / NS, "rot_err_deg": err_R,
-                         "t_err": float(np.linalg.norm(t - w["t_true"])), "rot_cubes_local": st["rot_cubes"],
-                         "bound_evals_local": st["bound_evals"], "icp_runs_local": st["icp_runs"],
-                         "ms_bnb_ub": st["ms_bnb_ub"], "ms_icp": st["ms_icp"], "ms_bnb_lb": st["ms_bnb_lb"],
-                         "ms_first_icp": st.get("ms_first_icp"), "ms_final_icp": st.get("ms_final_icp"),
-                         "ms_search_wall": st.get("ms_search_wall"), "levels": st["level_log"]})
-            if rep < NRUNS - 1:
-                g.close()
-        order = sorted(range(NRUNS), key=lambda k: runs[k]["bnb_ms"])
-        bnb = dict(runs[order[NRUNS // 2]])
-        bnb["bnb_ms_all_runs"] = [runs[k]["bnb_ms"] for k in range(NRUNS)]
+        # five runs on fresh contexts; the reported one is the MEDIAN by wall time (all five are listed)
+        bnb = measure_run(w["model"], w["data"], RES, MSE_THR, 5, local, world, barrier, wave1=args.wave1,
+                          skip_dead_lb=not args.keep_dead_lb)
+        Rm, tm = bnb.pop("_R"), bnb.pop("_t_out")
+        bnb["rot_err_deg"] = float(np.degrees(np.arccos(np.clip((np.trace(Rm @ w["R_true"].T) - 1) / 2, -1, 1))))
+        bnb["t_err"] = float(np.linalg.norm(tm - w["t_true"]))
+        if world > 1:
+            ev = torch.tensor([float(bnb["bound_evals_local"]), float(bnb["ms_bnb_ub"] + bnb["ms_bnb_lb"])], device=dev, dtype=torch.float64)
+            tot = ev.clone(); dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+            mx = ev.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            bnb["bound_evals_all_ranks"] = float(tot[0].item())
+            bnb["in_search_evals_per_s"] = float(tot[0].item()) / (float(mx[1].item()) * 1e-3)
+        else:
+            bnb["bound_evals_all_ranks"] = float(bnb["bound_evals_local"])
+            bnb["in_search_evals_per_s"] = bnb["in_search_evals_per_s_local"]
+        # BASELINE.json configs 1-4: the reference repository's own clouds, run() through the same driver
+        if not args.no_repo_clouds:
+            repo = []
+            for name, fixture, res_c, mse_c, reps in REPO_CLOUDS:
+                try:
+                    m_c, d_c = load_repo_cloud(fixture)
+                    r = measure_run(m_c, d_c, res_c, mse_c, reps, local, world, barrier)
+                    r.pop("_R"); r.pop("_t_out"); r.pop("levels")
+                    r.update(case=name, nt=len(m_c), ns=len(d_c), lut_resolution=res_c, mse_threshold=mse_c)
+                    repo.append(r)
+                except Exception as ex:          # a missing fixture must not cost the bench line
+                    repo.append({"case": name, "error": str(ex)[:200]})
         if rank == 0 and world == 1 and not args.no_cpu:
+            g = driver.FastGoICP(w["model"], w["data"], RES, MSE_THR, device=local, flags=capi.BUILD_PACKED)
             lut, dims = g.ctx.lut_download()
             pp["lut"], pp["dims"] = lut, dims
-        g.close()
+            g.close()
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu and "lut" in pp:
@@ -354,8 +427,22 @@ def run_ours(args):
                           "parallelism": "frontier-sharded x%d" % world},
                "e2e": e2e, "gpu_launches": (4 if phased else 2) * args.steps, "clocks": clk, "roofline": roofline,
                "cpu_baseline": cpu, "ctor_ms": ctor_ms, "lut_build_ms": info.build_ms}
+        if ref_shape:
+            out["e2e_reference_call_shape"] = ref_shape
         if bnb:
             out["bnb"] = bnb
+            # the evaluations run() itself spends: inner searches (k_bnb_r3 / round kernels), device time of the search
+            # phases, all ranks; against the same 32 B / evaluation gather roofline
+            a_in = ALGO_BYTES_PER_EVAL * bnb["in_search_evals_per_s"] / 1e9
+            roofline["in_search"] = {"kernel": "inner R^3 searches inside run() on W5 (k_bnb_r3 and the round kernels)",
+                                     "evals_per_s": bnb["in_search_evals_per_s"], "achieved": a_in, "peak": peak * world,
+                                     "unit": "GB/s", "frac": a_in / (peak * world)}
+            out["search_scaling"] = {"scaling": "strong", "n_gpus": world, "bnb_ms": bnb["bnb_ms"],
+                                     "in_search_evals_per_s": bnb["in_search_evals_per_s"],
+                                     "note": "run() on W5 with the per-level rotation frontier sharded over the ranks: total "
+                                             "work fixed as N grows (the headline `value` is the no-prune bound microbench, weak)"}
+        if repo is not None:
+            out["bnb_repo_clouds"] = repo
         emit(out)
     if world > 1:
         dist.destroy_process_group()
@@ -363,10 +450,15 @@ def run_ours(args):
 
 def run_reference(args):
     """Reference arm.  The reference has NO CPU implementation: its bound operator is
-    Registration::compute_sse_error (CUDA).  When oracle/_ref/libfgoicp_ref.so exists (the unmodified
-    reference sources compiled by oracle/build_ref.py) and a GPU is visible, that operator is timed as it
-    ships -- host loop on one CPU thread, kernels on GPU 0.  Otherwise the oracle port is timed on the
-    host cores.  Each step is a bounded sample of the workload."""
+    Registration::compute_sse_error (CUDA) and its search is icp::FastGoICP::run().  When oracle/_ref/libfgoicp_ref.so
+    exists (the unmodified reference sources compiled by oracle/build_ref.py) and a GPU is visible, both are timed as
+    they ship -- host loop on one CPU thread, kernels on GPU 0:
+      * `value` / `e2e`: compute_sse_error over the FIRST `--ref-rot` rotation cubes of the repo arm's own list
+        (workloads.bound_microbench, rank 0's seed), each with its own 32 translation cubes -- a bounded sample of the
+        same workload, the same call shape as the repo arm's `e2e_reference_call_shape`;
+      * `bnb`: run() on the reference repository's bunny pair (BASELINE.json config 1; the repo arm's
+        `bnb_repo_clouds[1]` is the same clouds, resolution and threshold).
+    Otherwise the oracle port is timed on the host cores."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -374,8 +466,8 @@ def run_reference(args):
     from oracle import ref as REF
     w = workloads.synthetic_pair(nt=NT, ns=NS, sigma=0.01, seed=1234)
     n_rot_sample = args.ref_rot
-    rot = workloads.rotation_cube_list(n_rot_sample, seed=7)
-    tc = workloads.translation_cube_list(T_CUBES, level=4, seed=8)
+    rot_all, tc_all = workloads.bound_microbench(N_ROT, T_CUBES, seed=7)
+    rot, tcs = rot_all[:n_rot_sample], tc_all[:n_rot_sample]
     evals_per_step = n_rot_sample * T_CUBES * NS
     kind, cores, sample = None, None, None
     use_ref = False
@@ -385,6 +477,7 @@ def run_reference(args):
             use_ref = torch.cuda.is_available()
         except Exception:
             use_ref = False
+    bnb = None
     if use_ref:
         t0 = time.perf_counter()
         r = REF.Reference(w["model"], w["data"], RES, MSE_THR)
@@ -392,24 +485,23 @@ def run_reference(args):
 
         def step():
             for k in range(n_rot_sample):
-                r.bounds(rot[k], False, tc)
+                r.bounds(rot[k], False, tcs[k])
         kind, cores = "reference", 1
-        sample = ("unmodified reference Registration::compute_sse_error (oracle/_ref, CUDA on GPU 0, 1 host thread): "
-                  "%d rotation cubes x %d translation cubes x %d points per step; reference ctor (LUT build) %.0f ms"
-                  % (n_rot_sample, T_CUBES, NS, ctor_ms))
+        sample = ("unmodified reference Registration::compute_sse_error (oracle/_ref, CUDA on GPU 0, 1 host thread): the first "
+                  "%d rotation cubes of the repo arm's list x %d translation cubes x %d points per step; reference ctor "
+                  "(LUT build) %.0f ms" % (n_rot_sample, T_CUBES, NS, ctor_ms))
     else:
         from oracle import oracle as O
         pp = O.preprocess(w["model"], w["data"])
-        # a coarser grid keeps the CPU brute-force build bounded; the evaluation cost per point is unchanged
-        lut, dims = O.lut_build(pp["model"][::50], pp["bbox_min"], pp["bbox_max"], 0.02)
+        lut, dims = O.lut_build(pp["model"], pp["bbox_min"], pp["bbox_max"], RES)        # k-d tree build, all host threads
 
         def step():
             for k in range(n_rot_sample):
                 R, _ = O.rotation(*rot[k, :3])
-                O.bounds(lut, dims, pp["bbox_min"], 0.02, pp["data"], R, float(rot[k, 3]), False, tc)
+                O.bounds(lut, dims, pp["bbox_min"], RES, pp["data"], R, float(rot[k, 3]), False, tcs[k])
         kind, cores = "port", O.num_threads()
-        sample = ("oracle port (oracle/fgoicp_oracle.c, OpenMP, grid 0.02): %d rotation cubes x %d translation "
-                  "cubes x %d points per step" % (n_rot_sample, T_CUBES, NS))
+        sample = ("oracle port (oracle/fgoicp_oracle.c, OpenMP): the first %d rotation cubes of the repo arm's list x %d "
+                  "translation cubes x %d points per step" % (n_rot_sample, T_CUBES, NS))
     for _ in range(max(args.warmup, 1)):
         step()
     t0 = time.perf_counter()
@@ -417,27 +509,33 @@ def run_reference(args):
         step()
     dt = time.perf_counter() - t0
     v = evals_per_step * args.steps / dt
-    port = None
     if use_ref:
-        # for the record, the CPU restatement (oracle port) on all host threads, same bounded sample (coarser grid so
-        # that the brute-force CPU grid build stays bounded; the per-evaluation cost does not depend on it)
-        from oracle import oracle as O
-        pp = O.preprocess(w["model"], w["data"])
-        lut, dims = O.lut_build(pp["model"][::50], pp["bbox_min"], pp["bbox_max"], 0.02)
-        t1 = time.perf_counter()
-        for k in range(n_rot_sample):
-            R, _ = O.rotation(*rot[k, :3])
-            O.bounds(lut, dims, pp["bbox_min"], 0.02, pp["data"], R, float(rot[k, 3]), False, tc)
-        port = {"value": evals_per_step / (time.perf_counter() - t1), "unit": "evals/s", "cores": O.num_threads(), "kind": "port"}
+        r.close()
+        # the other half of the metric: the reference's own run() (src/main.cpp:46-55) on the bunny pair
+        try:
+            z = np.load(os.path.join(ROOT, "tests", "golden", "bunny_full.npz"))
+            t0 = time.perf_counter()
+            rb = REF.Reference(z["model"], z["data"], 0.005, 1e-3)
+            b_ctor = (time.perf_counter() - t0) * 1e3
+            t0 = time.perf_counter()
+            sse, _, _, _, _ = rb.run()
+            bnb = {"case": "W1 bunny (default res 0.005, mse 1e-3)", "bnb_ms": (time.perf_counter() - t0) * 1e3, "ctor_ms": b_ctor,
+                   "sse": float(sse), "nt": int(len(z["model"])), "ns": int(len(z["data"])), "host_threads": 1,
+                   "what": "unmodified reference icp::FastGoICP::run() (oracle/_ref), same GPU"}
+            rb.close()
+        except Exception as ex:
+            bnb = {"error": str(ex)[:200]}
     out = {"impl": "reference", "metric": "cube x point bound evals/s", "value": v, "unit": "evals/s",
            "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": max(args.warmup, 1),
            "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f32", "data": "synthetic",
-           "config": {"workload": "W5 synthetic: 100k-point model / 10k-point data, lut_resolution 0.005; bounded sample"},
+           "config": {"workload": "W5 synthetic: 100k-point model / 10k-point data, lut_resolution 0.005; bounded sample: "
+                                  "the first %d rotation cubes of the repo arm's cube list, 32 translation cubes each" % n_rot_sample,
+                      "same_cube_list_as_repo_arm": True},
            "cpu_baseline": {"value": v, "unit": "evals/s", "cores": cores, "kind": kind, "sample": sample},
            "e2e": {"value": v, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    if port:
-        out["oracle_port_on_host_cores"] = port
+    if bnb:
+        out["bnb"] = bnb
     emit(out)
 
 
@@ -452,6 +550,7 @@ def main():
     ap.add_argument("--wave1", type=int, default=32, help="cubes per level searched first in run() (0: no split)")
     ap.add_argument("--keep-dead-lb", action="store_true", help="also run the leaf level's (output-neutral) lower-bound searches")
     ap.add_argument("--no-bnb", action="store_true", help="skip the end-to-end run() measurement")
+    ap.add_argument("--no-repo-clouds", action="store_true", help="skip run() on the reference repository's own clouds (W1-W4)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline sample")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--ref-rot", type=int, default=16, help="rotation cubes per reference-arm step")

@@ -55,6 +55,19 @@ __device__ __forceinline__ unsigned long long bnb_key(float lb, unsigned level, 
     return ((unsigned long long)__float_as_uint(lb) << 32) | lo;
 }
 
+__device__ __forceinline__ float4 bnb_key_cube_m(unsigned long long key)
+{
+    unsigned lo = (unsigned)key;
+    unsigned level = (lo >> 25) & 7u, ix = lo & 15u, iy = (lo >> 4) & 15u, iz = (lo >> 8) & 15u;
+    float span = __uint_as_float((127u - level) << 23);                  // 2^-level
+    float4 t;
+    t.x = __fmaf_rn((float)(2 * ix + 1), span, -1.0f);                   // exact: dyadic
+    t.y = __fmaf_rn((float)(2 * iy + 1), span, -1.0f);
+    t.z = __fmaf_rn((float)(2 * iz + 1), span, -1.0f);
+    t.w = span;
+    return t;
+}
+
 #ifndef BNB_MIN_BLOCKS
 #define BNB_MIN_BLOCKS 2      // 2 blocks of 8 warps per SM (<= 128 registers); 1 lets ptxas take 139 and halves the occupancy (inner searches 84 -> 104 ms), 3 spills (108 ms)
 #endif
@@ -247,6 +260,239 @@ k_bnb_r3(LutDev L, const float4* __restrict__ data, int ns, const float4* __rest
             unsigned long long key = pool[i];
             if (key != BNB_KEY_MAX && (unsigned)(key >> 32) >= be_bits) pool[i] = BNB_KEY_MAX;
         }
+        __syncthreads();
+    }
+
+    cluster.sync();                                       // nobody exits while a peer may still read its partials
+    if (tid == 0 && crank == 0)
+    {
+        BnbOut o;
+        o.best_ub = s_best_ub;
+        o.best_t[0] = s_best_t[0]; o.best_t[1] = s_best_t[1]; o.best_t[2] = s_best_t[2];
+        o.evals = s_evals; o.batches = s_batches; o.pushed = s_seq;
+        out[r] = o;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Same search with the open list KEPT SORTED instead of re-sorted: k_bnb_r3 above runs a full bitonic sort of the pool
+// (up to 4096 keys: 78 compare-exchange sweeps, ~20 us) every iteration, which is a quarter of an iteration when a
+// level has few rotation cubes and the search is latency-bound (outer levels 1-2; every wave of a multi-GPU run).
+// Here the pool is a sorted run in one of two shared-memory buffers:
+//   pop        = advance the head by <= 32 keys (they are the smallest);
+//   prune      = lb >= best_error is a SUFFIX of a run sorted by lb: one binary search, no sweep;
+//   children   = <= 256 new keys, sorted on their own (bitonic over 256) and MERGED with the run into the other buffer:
+//                every key finds its final position by one binary search in the other list (keys are unique: the
+//                insertion sequence number is part of the key), ~3 us for 4000 keys.
+// The pop order is the ascending key order in both kernels, so every decision, bound and evaluation count is the same.
+// ---------------------------------------------------------------------------------------------
+#define BNBM_POOL  4736                 // >= 4681 nodes ever pushed
+#define BNBM_NEW   256                  // children of one batch (8 x 32)
+
+template <int SAMPLER, int NWARPS, int MINB>
+__global__ void __launch_bounds__(NWARPS * 32, MINB)
+k_bnb_r3m(LutDev L, const float4* __restrict__ data, int ns, const float4* __restrict__ rot, int fix_rot,
+          float best_sse, float sse_threshold, int batch_max, BnbOut* __restrict__ out)
+{
+    extern __shared__ unsigned long long poolm[];         // 2 x BNBM_POOL + BNBM_NEW keys
+    __shared__ float sR[9];
+    __shared__ float s_sin;
+    __shared__ float4 s_tc[BNB_BATCH_MAX];
+    __shared__ unsigned long long s_bkey[BNB_BATCH_MAX];
+    __shared__ double s_part[NWARPS][BD_CPW][2];
+    __shared__ double s_cpart[2][BNB_BATCH_MAX][2];        // this block's partial sums, double-buffered for DSMEM readers
+    __shared__ float s_lb[BNB_BATCH_MAX], s_ub[BNB_BATCH_MAX];
+    __shared__ int s_m, s_nb, s_stop, s_nc;
+    __shared__ float s_best_error, s_best_ub, s_best_t[3];
+    __shared__ unsigned int s_seq, s_batches;
+    __shared__ unsigned long long s_evals;
+
+    const int NT = NWARPS * 32;
+    const int tid = threadIdx.x;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int csize = (int)cluster.num_blocks();
+    const int crank = (int)cluster.block_rank();
+    const int r = blockIdx.x / csize;
+    const int per = (ns + csize - 1) / csize;
+    const int p0 = min(ns, crank * per), p1 = min(ns, p0 + per);
+    int parity = 0;
+    unsigned long long* A = poolm;                        // current sorted run: A[head .. head + m)
+    unsigned long long* B = poolm + BNBM_POOL;            // merge target
+    unsigned long long* C = poolm + 2 * BNBM_POOL;        // children of the batch
+    int head = 0;
+
+    if (tid == 0)
+    {
+        float4 rc = rot[r];
+        float Rm[9];
+        fg_rotation_matrix(rc.x, rc.y, rc.z, Rm);
+        for (int k = 0; k < 9; ++k) sR[k] = Rm[k];
+        s_sin = fix_rot ? 0.0f : fg_rot_sin(rc.w);
+        A[0] = bnb_key(0.0f, 0, 0, 0, 0, 0);             // root: t = 0, span = 1, lb = 0 (fgoicp.cpp:113)
+        s_m = 1; s_seq = 1;
+        s_best_error = best_sse;                          // fgoicp.cpp:104
+        s_best_ub = FG_INF;                               // fgoicp.cpp:106
+        s_best_t[0] = s_best_t[1] = s_best_t[2] = 0.0f;   // fgoicp.cpp:105
+        s_evals = 0; s_batches = 0; s_stop = 0;
+    }
+    __syncthreads();
+
+    while (true)
+    {
+        // ---- stop test and batch pop: the run is sorted, its head is the smallest lower bound
+        if (tid == 0)
+        {
+            const int m = s_m;
+            int stop = 0, nb = 0;
+            if (m <= 0) stop = 1;
+            else
+            {
+                float top_lb = __uint_as_float((unsigned)(A[head] >> 32));
+                if (__fsub_rn(s_best_error, top_lb) < sse_threshold) stop = 1;      // fgoicp.cpp:120
+                else nb = min(m, batch_max);
+            }
+            s_stop = stop; s_nb = nb;
+        }
+        __syncthreads();
+        if (s_stop) break;
+        const int nb = s_nb;
+        if (tid < nb)
+        {
+            unsigned long long key = A[head + tid];
+            s_bkey[tid] = key;
+            s_tc[tid] = bnb_key_cube_m(key);
+        }
+        __syncthreads();
+        head += nb;                                       // popped (uniform: every thread tracks head)
+        int m = s_m - nb;
+
+        // ---- bounds of the batch (registration.cu:88-152 fused)
+        fg_eval_chunk<SAMPLER, NWARPS>(L, data, p0, p1, sR, s_sin, fix_rot != 0, s_tc, nb, s_part);
+        __syncthreads();
+        if (tid < nb)
+        {
+            double su, sl;
+            fg_eval_gather<NWARPS>(s_part, nb, tid, su, sl);
+            s_cpart[parity][tid][0] = su; s_cpart[parity][tid][1] = sl;
+        }
+        cluster.sync();                                   // every block's partials are visible cluster-wide
+        if (tid < nb)
+        {
+            double su = 0.0, sl = 0.0;
+            for (int k = 0; k < csize; ++k)               // rank order: identical totals in every block
+            {
+                const double* rp = cluster.map_shared_rank(&s_cpart[parity][tid][0], k);
+                su += rp[0]; sl += rp[1];
+            }
+            s_ub[tid] = (float)su; s_lb[tid] = (float)sl;
+        }
+        parity ^= 1;
+        __syncthreads();
+
+        // ---- best of the batch (fgoicp.cpp:139-145): first minimum in pop order
+        if (tid == 0)
+        {
+            int idx_min = 0;
+            for (int i = 1; i < nb; ++i) if (s_ub[i] < s_ub[idx_min]) idx_min = i;
+            float u = s_ub[idx_min];
+            s_best_ub = s_best_ub < u ? s_best_ub : u;
+            if (u < s_best_error)
+            {
+                s_best_error = u;
+                s_best_t[0] = s_tc[idx_min].x; s_best_t[1] = s_tc[idx_min].y; s_best_t[2] = s_tc[idx_min].z;
+            }
+            s_evals += (unsigned long long)nb * (unsigned long long)ns;           // fgoicp.cpp:132 (x ns)
+            s_batches += 1;
+        }
+        __syncthreads();
+
+        // ---- children of surviving cubes (fgoicp.cpp:148-169), in pop order, into C
+        const float best_error = s_best_error;
+        const unsigned long long cut_key = (unsigned long long)__float_as_uint(best_error) << 32;   // keys >= this are dead
+        if (tid < 32)
+        {
+            bool spawn = false;
+            if (tid < nb)
+            {
+                float lbv = s_lb[tid];
+                float span = s_tc[tid].w;
+                spawn = !(lbv >= best_error) && !(span < BNB_MIN_TSPAN);
+            }
+            unsigned mask = __ballot_sync(0xffffffffu, spawn);
+            int before = __popc(mask & ((1u << tid) - 1u));
+            int total = __popc(mask);
+            if (spawn)
+            {
+                unsigned lo = (unsigned)s_bkey[tid];
+                unsigned level = (lo >> 25) & 7u, ix = lo & 15u, iy = (lo >> 4) & 15u, iz = (lo >> 8) & 15u;
+                unsigned seq0 = s_seq + 8u * before;
+                float lbv = s_lb[tid];
+#pragma unroll
+                for (unsigned k = 0; k < 8; ++k)
+                    C[8 * before + k] = bnb_key(lbv, level + 1, seq0 + k, 2 * ix + (k & 1u), 2 * iy + ((k >> 1) & 1u), 2 * iz + ((k >> 2) & 1u));
+            }
+            __syncwarp();
+            if (tid == 0) { s_nc = 8 * total; s_seq += 8u * total; }
+        }
+        __syncthreads();
+        const int nc = s_nc;
+
+        // ---- prune the run: everything with lb >= best_error is a suffix (fgoicp.cpp:126)
+        {
+            int lo = 0, hi = m;                           // first index whose key >= cut_key
+            while (lo < hi) { int mid = (lo + hi) >> 1; if (A[head + mid] < cut_key) lo = mid + 1; else hi = mid; }
+            m = lo;
+        }
+        if (nc > 0)
+        {
+            // sort the children (bitonic over the next power of two >= nc, <= 256)
+            int P = 8; while (P < nc) P <<= 1;
+            for (int i = nc + tid; i < P; i += NT) C[i] = BNB_KEY_MAX;
+            __syncthreads();
+            for (int k = 2; k <= P; k <<= 1)
+                for (int j = k >> 1; j > 0; j >>= 1)
+                {
+                    for (int i = tid; i < P; i += NT)
+                    {
+                        int ixj = i ^ j;
+                        if (ixj > i)
+                        {
+                            unsigned long long a = C[i], b = C[ixj];
+                            bool up = ((i & k) == 0);
+                            if ((a > b) == up) { C[i] = b; C[ixj] = a; }
+                        }
+                    }
+                    __syncthreads();
+                }
+            // children at or above the cut are dead too (cannot happen for a freshly spawned child -- its lb is its
+            // parent's, which was below best_error -- but the rule is applied uniformly)
+            int ncl;
+            {
+                int lo = 0, hi = nc;
+                while (lo < hi) { int mid = (lo + hi) >> 1; if (C[mid] < cut_key) lo = mid + 1; else hi = mid; }
+                ncl = lo;
+            }
+            // merge A[head .. head + m) and C[0 .. ncl) into B by rank
+            for (int i = tid; i < m; i += NT)
+            {
+                const unsigned long long a = A[head + i];
+                int lo = 0, hi = ncl;                     // children smaller than a
+                while (lo < hi) { int mid = (lo + hi) >> 1; if (C[mid] < a) lo = mid + 1; else hi = mid; }
+                B[i + lo] = a;
+            }
+            for (int i = tid; i < ncl; i += NT)
+            {
+                const unsigned long long c = C[i];
+                int lo = 0, hi = m;                       // run keys smaller than c
+                while (lo < hi) { int mid = (lo + hi) >> 1; if (A[head + mid] < c) lo = mid + 1; else hi = mid; }
+                B[i + lo] = c;
+            }
+            __syncthreads();
+            unsigned long long* T = A; A = B; B = T;
+            head = 0;
+            m += ncl;
+        }
+        if (tid == 0) s_m = m;
         __syncthreads();
     }
 
@@ -504,8 +750,43 @@ static int launch_bnb_w(fgoicp_ctx* c, const float4* d_rot, int Rn, int csize, i
     }
 }
 
+// sorted-run kernel (k_bnb_r3m)
+template <int SAMPLER, int NWARPS, int MINB>
+static int launch_bnbm_t(fgoicp_ctx* c, const float4* d_rot, int Rn, int csize, int fix_rot, float best_sse, float thr, BnbOut* d_out)
+{
+    size_t smem = sizeof(unsigned long long) * (2 * BNBM_POOL + BNBM_NEW);
+    FG_CUDA(cudaFuncSetAttribute(k_bnb_r3m<SAMPLER, NWARPS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (csize > 8) FG_CUDA(cudaFuncSetAttribute(k_bnb_r3m<SAMPLER, NWARPS, MINB>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(Rn * csize));
+    cfg.blockDim = dim3(NWARPS * 32);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = c->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    int ns = (int)c->ns, bm = BNB_BATCH_MAX;
+    FG_CUDA(cudaLaunchKernelEx(&cfg, k_bnb_r3m<SAMPLER, NWARPS, MINB>, c->lut, (const float4*)c->d_data, ns, d_rot, fix_rot,
+                               best_sse, thr, bm, d_out));
+    return FGOICP_OK;
+}
+
+template <int NWARPS, int MINB>
+static int launch_bnbm_w(fgoicp_ctx* c, const float4* d_rot, int Rn, int csize, int fix_rot, float best_sse, float thr, BnbOut* d_out)
+{
+    switch (c->sampler)
+    {
+    case FGOICP_SAMPLER_PACKED: return launch_bnbm_t<FGOICP_SAMPLER_PACKED, NWARPS, MINB>(c, d_rot, Rn, csize, fix_rot, best_sse, thr, d_out);
+    case FGOICP_SAMPLER_TEX:    return launch_bnbm_t<FGOICP_SAMPLER_TEX, NWARPS, MINB>(c, d_rot, Rn, csize, fix_rot, best_sse, thr, d_out);
+    default:                    return launch_bnbm_t<FGOICP_SAMPLER_GRID, NWARPS, MINB>(c, d_rot, Rn, csize, fix_rot, best_sse, thr, d_out);
+    }
+}
+
 // Cluster size: enough blocks for ~8 resident waves' worth of granularity, at most 8 (portable limit),
 // at least 1; never so large that a block gets fewer than 256 points.  FGOICP_BNB_CLUSTER overrides.
+// Kernel: the sorted-run kernel k_bnb_r3m (default; FGOICP_BNB_KERNEL=bitonic selects k_bnb_r3), with 16 warps per
+// block when the launch cannot fill the GPU anyway (few rotation cubes: latency, not throughput, is what counts).
 static int launch_bnb(fgoicp_ctx* c, const float4* d_rot, int Rn, int fix_rot, float best_sse, float thr, BnbOut* d_out)
 {
     int slots = 3 * c->sm_count;                       // 8-warp blocks resident at once (register-limited)
@@ -516,7 +797,12 @@ static int launch_bnb(fgoicp_ctx* c, const float4* d_rot, int Rn, int fix_rot, f
     while (csize < cmax && csize < want) csize <<= 1;
     while (csize > 1 && (int)c->ns / csize < 256) csize >>= 1;
     if (const char* e = getenv("FGOICP_BNB_CLUSTER")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) csize = v; }
-    return launch_bnb_w<8>(c, d_rot, Rn, csize, fix_rot, best_sse, thr, d_out);
+    static const bool bitonic = getenv("FGOICP_BNB_KERNEL") && !strcmp(getenv("FGOICP_BNB_KERNEL"), "bitonic");
+    if (bitonic) return launch_bnb_w<8>(c, d_rot, Rn, csize, fix_rot, best_sse, thr, d_out);
+    int warps = ((long long)Rn * csize <= c->sm_count && (int)c->ns / csize >= 512) ? 16 : 8;
+    if (const char* e = getenv("FGOICP_BNB_WARPS")) { int v = atoi(e); if (v == 8 || v == 16) warps = v; }
+    if (warps == 16) return launch_bnbm_w<16, 1>(c, d_rot, Rn, csize, fix_rot, best_sse, thr, d_out);
+    return launch_bnbm_w<8, BNB_MIN_BLOCKS>(c, d_rot, Rn, csize, fix_rot, best_sse, thr, d_out);
 }
 
 static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }

@@ -42,6 +42,13 @@ namespace icp
             return glm::mat3(a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8]);
         }
 
+        // joins whatever threads were started, also when starting one of them (or anything after) throws
+        struct JoinAll
+        {
+            std::vector<std::thread>& th;
+            ~JoinAll() { for (auto& t : th) if (t.joinable()) t.join(); }
+        };
+
         double now_ms()
         {
             using clk = std::chrono::steady_clock;
@@ -136,17 +143,26 @@ namespace icp
                 if (rc == FGOICP_OK && options_.sampler >= 0) rc = fgoicp_set_sampler(ctxs_[k], options_.sampler);
                 if (rc != FGOICP_OK) errors[k] = std::string("fgoicp_ctx_create: ") + fgoicp_last_error();   // message is per thread
             };
-            if (K == 1) make(0);
-            else
+            // a constructor that throws never runs its destructor: release the contexts that were created (tens of MB to
+            // GBs of HBM each) before passing the error on
+            auto release = [&]() { for (fgoicp_ctx*& c : ctxs_) { fgoicp_ctx_destroy(c); c = nullptr; } ctx_ = nullptr; };
+            try
             {
-                std::vector<std::thread> th;
-                for (size_t k = 0; k < K; ++k) th.emplace_back(make, k);
-                for (auto& t : th) t.join();
+                if (K == 1) make(0);
+                else
+                {
+                    std::vector<std::thread> th;
+                    JoinAll guard{ th };
+                    for (size_t k = 0; k < K; ++k) th.emplace_back(make, k);
+                }
             }
+            catch (...) { release(); throw; }
             ctx_ = ctxs_[0];
             for (size_t k = 0; k < K; ++k)
-                if (!errors[k].empty()) throw ApiError(errors[k]);
+                if (!errors[k].empty()) { release(); throw ApiError(errors[k]); }
         }
+        try
+        {
         fgoicp_info info;
         check(fgoicp_ctx_info(ctx_, &info), "fgoicp_ctx_info");
         if (info.dims[0] >= 1024 || info.dims[1] >= 1024 || info.dims[2] >= 1024)
@@ -161,6 +177,13 @@ namespace icp
             for (fgoicp_ctx* c : ctxs_) check(fgoicp_set_trim(c, options_.trim_fraction, &k), "fgoicp_set_trim");
             n_inliers = static_cast<size_t>(k);
             sse_threshold = static_cast<float>(n_inliers) * mse_threshold;
+        }
+        }
+        catch (...)
+        {
+            for (fgoicp_ctx*& c : ctxs_) { fgoicp_ctx_destroy(c); c = nullptr; }
+            ctx_ = nullptr;
+            throw;
         }
         stats_.ctor_ms = static_cast<float>(now_ms() - t0);
     }
@@ -212,9 +235,9 @@ namespace icp
         };
         {
             std::vector<std::thread> th;
+            JoinAll guard{ th };
             for (int k = 1; k < K; ++k) th.emplace_back(work, k);
             work(0);
-            for (auto& t : th) t.join();
         }
         std::memset(&st, 0, sizeof(st)); st.best_icp_index = -1;
         int winner = -1, winner_index = 0;
@@ -272,9 +295,9 @@ namespace icp
         };
         {
             std::vector<std::thread> th;
+            JoinAll guard{ th };
             for (int k = 1; k < K; ++k) th.emplace_back(work, k);
             work(0);
-            for (auto& t : th) t.join();
         }
         std::memset(&st, 0, sizeof(st));
         for (int k = 0; k < K; ++k)

@@ -873,7 +873,6 @@ k_icp_procrustes(const float4* __restrict__ work_base, const unsigned long long*
 // The host launches it once per batch and synchronises once: no polls, no allocation, ~9 barriers per iteration.
 namespace cgrp = cooperative_groups;
 
-#define ICPL_THREADS 512
 #define ICPL_CHUNK   512                // points per reduction item
 #define ICPL_PART    32                 // doubles per (slot, chunk): [0,6) centroids, [8,17) cross-covariance, [24] SSE
 
@@ -884,7 +883,26 @@ struct IcpLoopCtl
     int error;                          // 1: iteration guard hit
     unsigned int iterations;            // loop trips (diagnostics)
     unsigned int scans_a, scans_b;      // full scans run (diagnostics: the rest were memo hits)
+    unsigned long long stage_ns[10];    // time block 0 spent in each stage incl. the barrier that ends it (diagnostics)
 };
+
+__device__ __forceinline__ unsigned long long fg_globaltimer()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// out-of-line form of the scan: its registers are allocated on their own instead of on top of the loop kernel's state
+template <int ROOTED>
+__device__ __noinline__ unsigned long long fg_nn_scan_call(const CellGrid* g, const LutDev* L, float res, float qx, float qy, float qz,
+                                                           unsigned int prev, const float4* __restrict__ model, float margin, int lane, float* rho)
+{
+    float r;
+    const unsigned long long key = fg_nn_scan<ROOTED>(*g, *L, res, qx, qy, qz, prev, model, margin, margin > 0.0f, lane, 0xffffffffu, r);
+    *rho = r;
+    return key;
+}
 
 struct IcpLoopArgs
 {
@@ -924,18 +942,22 @@ __device__ __forceinline__ void fg_miss_append(bool miss, unsigned int item, uns
     if (miss) list[base + __popc(m & ((1u << lane) - 1u))] = item;
 }
 
-__global__ void __launch_bounds__(ICPL_THREADS, 2)
+template <int ICPL_THREADS, int MINB, int OUTLINE>
+__global__ void __launch_bounds__(ICPL_THREADS, MINB)
 k_icp_loop(IcpLoopArgs a)
 {
     cgrp::grid_group grid = cgrp::this_grid();
+    unsigned long long t_stage = fg_globaltimer();
+#define ICPL_STAGE(k) do { if (gtid == 0) { const unsigned long long now__ = fg_globaltimer(); a.ctl->stage_ns[k] += now__ - t_stage; t_stage = now__; } } while (0)
     const int tid = threadIdx.x, lane = tid & 31;
     const int gthreads = (int)gridDim.x * ICPL_THREADS, gtid = (int)blockIdx.x * ICPL_THREADS + tid;
-    const int gwarps = gthreads >> 5;
     const int ns = a.ns, S = a.S;
     const int NC = (ns + ICPL_CHUNK - 1) / ICPL_CHUNK;
     const int items = S * ns;
     __shared__ double s_out[16];
     __shared__ float s_ab[6];
+    __shared__ unsigned int s_chunk;
+    constexpr int ICPL_MISS_CHUNK = (ICPL_THREADS / 32) * 4;      // misses per block and fetch: four per warp
 
     // first jobs of the batch: slot k runs job k (k_icp_assign)
     if (gtid < S)
@@ -947,7 +969,7 @@ k_icp_loop(IcpLoopArgs a)
 
     for (long long it = 0;; ++it)
     {
-        grid.sync();                                             // slot states of the prologue / of S9 are visible
+        grid.sync(); ICPL_STAGE(0);                                             // slot states of the prologue / of S9 are visible
         {
             const volatile IcpQueue* vq = a.q;
             if (vq->finished >= vq->n_jobs) break;               // uniform: nobody writes the queue before the next S9
@@ -989,28 +1011,34 @@ k_icp_loop(IcpLoopArgs a)
             }
             fg_miss_append(miss, (unsigned int)item, &a.ctl->n_miss_a, a.miss, lane);
         }
-        grid.sync();
+        grid.sync(); ICPL_STAGE(1);
 
         // ---- S2: exact rooted search of the misses, one warp per query, dealt dynamically in small runs
         {
+            // Misses are dealt to BLOCKS in chunks of consecutive list entries, and inside a chunk to the block's warps
+            // round-robin: neighbouring queries (the data cloud is in Morton order) are then searched at the same time on
+            // the same SM and share the cell rows and candidate points they pull through its L1 -- the locality a
+            // one-warp-per-query launch gets for free.  (Handing each warp its own run of consecutive misses measured
+            // 1.6x slower on the dragon pair: 32 unrelated neighbourhoods per SM thrash the L1.)
             const unsigned int n_miss = *(volatile unsigned int*)&a.ctl->n_miss_a;
-            const unsigned int run = min(8u, max(1u, n_miss / (unsigned int)(4 * gwarps)));
             while (true)
             {
-                unsigned int m0 = 0;
-                if (lane == 0) m0 = atomicAdd(&a.ctl->next_a, run);
-                m0 = __shfl_sync(0xffffffffu, m0, 0);
+                __syncthreads();
+                if (tid == 0) s_chunk = atomicAdd(&a.ctl->next_a, (unsigned int)ICPL_MISS_CHUNK);
+                __syncthreads();
+                const unsigned int m0 = s_chunk;
                 if (m0 >= n_miss) break;
-                const unsigned int m1 = min(n_miss, m0 + run);
-                for (unsigned int m = m0; m < m1; ++m)
+                const unsigned int m1 = min(n_miss, m0 + (unsigned int)ICPL_MISS_CHUNK);
+                for (unsigned int m = m0 + (unsigned int)(tid >> 5); m < m1; m += ICPL_THREADS / 32)
                 {
                     const unsigned int item = __ldcg(a.miss + m);
                     const size_t o = (size_t)item;
                     const float4 w = __ldcg(a.work + o);
                     const unsigned int prev = (unsigned int)(__ldcg(a.keys + o) & 0xffffffffull);
                     float rho;
-                    const unsigned long long key = fg_nn_scan<1>(a.g, a.L, a.res, w.x, w.y, w.z, prev, a.model, a.margin, a.margin > 0.0f,
-                                                                 lane, 0xffffffffu, rho);
+                    const unsigned long long key = OUTLINE
+                        ? fg_nn_scan_call<1>(&a.g, &a.L, a.res, w.x, w.y, w.z, prev, a.model, a.margin, lane, &rho)
+                        : fg_nn_scan<1>(a.g, a.L, a.res, w.x, w.y, w.z, prev, a.model, a.margin, a.margin > 0.0f, lane, 0xffffffffu, rho);
                     if (lane == 0)
                     {
                         a.keys[o] = key;
@@ -1020,28 +1048,28 @@ k_icp_loop(IcpLoopArgs a)
             }
             if (gtid == 0) { a.ctl->n_miss_b = 0; a.ctl->next_b = 0; a.ctl->scans_a += n_miss; }   // the squared search's list is idle here
         }
-        grid.sync();
+        grid.sync(); ICPL_STAGE(2);
 
         // ---- S3: centroid partials of the working cloud and of its correspondences (icp3d.cu:150-156)
         for (int it2 = blockIdx.x; it2 < S * NC; it2 += gridDim.x)
         {
             const int slot = it2 / NC, c = it2 - slot * NC;
             if (fg_inst(a.inst, slot)->st.done) continue;
-            const int i = c * ICPL_CHUNK + tid;
+            const int i1 = min(ns, (c + 1) * ICPL_CHUNK);
             double v[6] = { 0, 0, 0, 0, 0, 0 };
-            if (tid < ICPL_CHUNK && i < ns)
+            for (int i = c * ICPL_CHUNK + tid; i < i1; i += ICPL_THREADS)
             {
                 const size_t o = (size_t)slot * ns + i;
                 const float4 w4 = __ldcg(a.work + o);
                 const float4 m4 = __ldg(a.model + (unsigned int)(__ldcg(a.keys + o) & 0xffffffffull));
-                v[0] = (double)w4.x; v[1] = (double)w4.y; v[2] = (double)w4.z;
-                v[3] = (double)m4.x; v[4] = (double)m4.y; v[5] = (double)m4.z;
+                v[0] += (double)w4.x; v[1] += (double)w4.y; v[2] += (double)w4.z;
+                v[3] += (double)m4.x; v[4] += (double)m4.y; v[5] += (double)m4.z;
             }
             fg_block_sum<6>(v, s_out);
             if (tid < 6) a.part[(size_t)it2 * ICPL_PART + tid] = s_out[tid];
             __syncthreads();
         }
-        grid.sync();
+        grid.sync(); ICPL_STAGE(3);
 
         // ---- S4: cross-covariance partials of the centred clouds (icp3d.cu:158-163)
         for (int it2 = blockIdx.x; it2 < S * NC; it2 += gridDim.x)
@@ -1058,9 +1086,9 @@ k_icp_loop(IcpLoopArgs a)
             __syncthreads();
             const float ab[3] = { s_ab[0], s_ab[1], s_ab[2] }, bb[3] = { s_ab[3], s_ab[4], s_ab[5] };
             if (c == 0 && tid < 3) { st->abar[tid] = ab[tid]; st->bbar[tid] = bb[tid]; }
-            const int i = c * ICPL_CHUNK + tid;
+            const int i1 = min(ns, (c + 1) * ICPL_CHUNK);
             double v[9] = { 0, 0, 0, 0, 0, 0, 0, 0, 0 };
-            if (tid < ICPL_CHUNK && i < ns)
+            for (int i = c * ICPL_CHUNK + tid; i < i1; i += ICPL_THREADS)
             {
                 const size_t o = (size_t)slot * ns + i;
                 const float4 w4 = __ldcg(a.work + o);
@@ -1072,13 +1100,13 @@ k_icp_loop(IcpLoopArgs a)
                 for (int cc = 0; cc < 3; ++cc)
 #pragma unroll
                     for (int r = 0; r < 3; ++r)
-                        v[cc * 3 + r] = (double)__fmul_rn(av[r], bv[cc]);
+                        v[cc * 3 + r] += (double)__fmul_rn(av[r], bv[cc]);
             }
             fg_block_sum<9>(v, s_out);
             if (tid < 9) a.part[(size_t)it2 * ICPL_PART + 8 + tid] = s_out[tid];
             __syncthreads();
         }
-        grid.sync();
+        grid.sync(); ICPL_STAGE(4);
 
         // ---- S5: closest rotation and pose update, one thread per slot (icp3d.cu:164-172, 101-102)
         for (int slot = blockIdx.x; slot < S; slot += gridDim.x)
@@ -1095,7 +1123,7 @@ k_icp_loop(IcpLoopArgs a)
             if (tid == 0) fg_icp_pose_update(st, s_out);
             __syncthreads();
         }
-        grid.sync();
+        grid.sync(); ICPL_STAGE(5);
 
         // ---- S6: W = Rd * W + td (icp3d.cu:100); query of the SSE search = R * data + t (icp3d.cu:103); memo test
         for (int base = gtid - lane; base < items; base += gthreads)
@@ -1126,20 +1154,20 @@ k_icp_loop(IcpLoopArgs a)
             }
             fg_miss_append(miss, (unsigned int)item, &a.ctl->n_miss_b, a.miss, lane);
         }
-        grid.sync();
+        grid.sync(); ICPL_STAGE(6);
 
         // ---- S7: exact squared search of the misses
         {
             const unsigned int n_miss = *(volatile unsigned int*)&a.ctl->n_miss_b;
-            const unsigned int run = min(8u, max(1u, n_miss / (unsigned int)(4 * gwarps)));
             while (true)
             {
-                unsigned int m0 = 0;
-                if (lane == 0) m0 = atomicAdd(&a.ctl->next_b, run);
-                m0 = __shfl_sync(0xffffffffu, m0, 0);
+                __syncthreads();
+                if (tid == 0) s_chunk = atomicAdd(&a.ctl->next_b, (unsigned int)ICPL_MISS_CHUNK);
+                __syncthreads();
+                const unsigned int m0 = s_chunk;
                 if (m0 >= n_miss) break;
-                const unsigned int m1 = min(n_miss, m0 + run);
-                for (unsigned int m = m0; m < m1; ++m)
+                const unsigned int m1 = min(n_miss, m0 + (unsigned int)ICPL_MISS_CHUNK);
+                for (unsigned int m = m0 + (unsigned int)(tid >> 5); m < m1; m += ICPL_THREADS / 32)
                 {
                     const unsigned int item = __ldcg(a.miss + m);
                     const int slot = (int)(item / (unsigned int)ns), i = (int)(item - (unsigned int)slot * (unsigned int)ns);
@@ -1153,8 +1181,9 @@ k_icp_loop(IcpLoopArgs a)
                     const float qx = __fadd_rn(rp.x, st->t[0]), qy = __fadd_rn(rp.y, st->t[1]), qz = __fadd_rn(rp.z, st->t[2]);
                     const unsigned int prev = (unsigned int)(__ldcg(a.keys + o) & 0xffffffffull);
                     float rho;
-                    const unsigned long long key = fg_nn_scan<0>(a.g, a.L, a.res, qx, qy, qz, prev, a.model, a.margin, a.margin > 0.0f,
-                                                                 lane, 0xffffffffu, rho);
+                    const unsigned long long key = OUTLINE
+                        ? fg_nn_scan_call<0>(&a.g, &a.L, a.res, qx, qy, qz, prev, a.model, a.margin, lane, &rho)
+                        : fg_nn_scan<0>(a.g, a.L, a.res, qx, qy, qz, prev, a.model, a.margin, a.margin > 0.0f, lane, 0xffffffffu, rho);
                     if (lane == 0)
                     {
                         a.keys[o] = key;
@@ -1164,21 +1193,22 @@ k_icp_loop(IcpLoopArgs a)
             }
             if (gtid == 0) { a.ctl->n_miss_a = 0; a.ctl->next_a = 0; a.ctl->scans_b += n_miss; a.ctl->iterations += 1; }
         }
-        grid.sync();
+        grid.sync(); ICPL_STAGE(7);
 
         // ---- S8: SSE partials (keys carry d2 bits in the high word)
         for (int it2 = blockIdx.x; it2 < S * NC; it2 += gridDim.x)
         {
             const int slot = it2 / NC, c = it2 - slot * NC;
             if (fg_inst(a.inst, slot)->st.done) continue;
-            const int i = c * ICPL_CHUNK + tid;
+            const int i1 = min(ns, (c + 1) * ICPL_CHUNK);
             double v[1] = { 0.0 };
-            if (tid < ICPL_CHUNK && i < ns) v[0] = (double)__uint_as_float((unsigned int)(__ldcg(a.keys + (size_t)slot * ns + i) >> 32));
+            for (int i = c * ICPL_CHUNK + tid; i < i1; i += ICPL_THREADS)
+                v[0] += (double)__uint_as_float((unsigned int)(__ldcg(a.keys + (size_t)slot * ns + i) >> 32));
             fg_block_sum<1>(v, s_out);
             if (tid == 0) a.part[(size_t)it2 * ICPL_PART + 24] = s_out[0];
             __syncthreads();
         }
-        grid.sync();
+        grid.sync(); ICPL_STAGE(8);
 
         // ---- S9: SSE, loop head of the next iteration, publish / next job (k_sse_reduce + k_icp_next)
         for (int slot = blockIdx.x * ICPL_THREADS + tid; slot < S; slot += gthreads)
@@ -1195,6 +1225,7 @@ k_icp_loop(IcpLoopArgs a)
         }
     }
 }
+#undef ICPL_STAGE
 
 // ---------------------------------------------------------------------------------------------
 
@@ -1393,12 +1424,28 @@ int fg_icp_run_batch(fgoicp_ctx* c, const float* R0s, const float* t0s, int n, i
     if (c->icp_mode == 0 && !trimmed && c->nn_mode == 0)
     {
         // ---- persistent loop kernel: one cooperative launch, one synchronisation for the whole batch
+        // block shape of the loop kernel (FGOICP_ICP_SHAPE selects among the instantiations for experiments)
+        struct Shape { const char* name; const void* fn; int threads, minb; };
+        static const Shape shapes[] = {
+            { "512x2", (const void*)k_icp_loop<512, 2, 0>, 512, 2 },
+            { "512x2o", (const void*)k_icp_loop<512, 2, 1>, 512, 2 },
+            { "256x5o", (const void*)k_icp_loop<256, 5, 1>, 256, 5 },
+            { "256x4", (const void*)k_icp_loop<256, 4, 0>, 256, 4 },
+            { "512x1", (const void*)k_icp_loop<512, 1, 0>, 512, 1 },
+        };
+        static const int shape_idx = []() {
+            const char* e = getenv("FGOICP_ICP_SHAPE");
+            if (e) for (int k = 0; k < (int)(sizeof(shapes) / sizeof(shapes[0])); ++k) if (!strcmp(e, shapes[k].name)) return k;
+            return 0;
+        }();
+        const Shape& shape = shapes[shape_idx];
+        const int ICPL_THREADS = shape.threads;
         if (c->icp_loop_grid == 0)
         {
             int occ = 0;
-            FG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_icp_loop, ICPL_THREADS, 0));
+            FG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, shape.fn, shape.threads, 0));
             if (occ < 1) { fg::set_error("k_icp_loop does not fit on this device"); return FGOICP_ERR_STATE; }
-            c->icp_loop_grid = c->sm_count * std::min(occ, 2);
+            c->icp_loop_grid = c->sm_count * std::min(occ, shape.minb);
             if (const char* e = getenv("FGOICP_ICP_GRID")) c->icp_loop_grid = std::max(1, std::min(c->icp_loop_grid, atoi(e)));
         }
         static const float margin_cfg = getenv("FGOICP_NN_MARGIN") ? (float)atof(getenv("FGOICP_NN_MARGIN")) : FG_NN_MARGIN;
@@ -1417,10 +1464,10 @@ int fg_icp_run_batch(fgoicp_ctx* c, const float* R0s, const float* t0s, int n, i
         FG_CUDA(cudaMemsetAsync(a.ctl, 0, sizeof(IcpLoopCtl), c->stream));
         // no more blocks than there is work for: a barrier costs time per participating block
         // (enough warps that a first pass -- every query a full scan -- hands each warp about four of them)
-        const long long want = ((long long)S * ns + 63) / 64;
+        const long long want = ((long long)S * ns * 16 + 63) / 64 / (ICPL_THREADS / 32);
         const int grid = (int)std::max<long long>(1, std::min<long long>(c->icp_loop_grid, want));
         void* params[] = { &a };
-        FG_CUDA(cudaLaunchCooperativeKernel((const void*)k_icp_loop, dim3((unsigned)grid), dim3(ICPL_THREADS), params, 0, c->stream));
+        FG_CUDA(cudaLaunchCooperativeKernel(shape.fn, dim3((unsigned)grid), dim3((unsigned)ICPL_THREADS), params, 0, c->stream));
         IcpLoopCtl* hctl = (IcpLoopCtl*)((char*)c->h_pinned + 2048);
         FG_CUDA(cudaMemcpyAsync(hq, d_q, sizeof(IcpQueue), cudaMemcpyDeviceToHost, c->stream));
         FG_CUDA(cudaMemcpyAsync(hctl, a.ctl, sizeof(IcpLoopCtl), cudaMemcpyDeviceToHost, c->stream));
@@ -1429,8 +1476,12 @@ int fg_icp_run_batch(fgoicp_ctx* c, const float* R0s, const float* t0s, int n, i
         all_done = hq->finished >= n && hctl->error == 0;
         results_on_host = all_done;
         if (getenv("FGOICP_ICP_LOG"))
-            fprintf(stderr, "[icp loop] jobs %d slots %d grid %d loop trips %u full scans: rooted %u squared %u\n", n, S, grid,
+        {
+            fprintf(stderr, "[icp loop %s] jobs %d slots %d grid %d trips %u full scans: rooted %u squared %u | stage us:", shape.name, n, S, grid,
                     hctl->iterations, hctl->scans_a, hctl->scans_b);
+            for (int k = 0; k < 9; ++k) fprintf(stderr, " %.0f", hctl->stage_ns[k] * 1e-3);
+            fprintf(stderr, "\n");
+        }
     }
     else
     {

@@ -10,6 +10,7 @@
 
 #include "common.hpp"
 #include <cstdint>
+#include <functional>
 #include <memory>
 #include <mutex>
 
@@ -40,6 +41,9 @@ namespace icp
             bool device_preprocess = false; // centre / scale / range the clouds on the GPU (fgoicp_preprocess; env FGOICP_DEVICE_PREPROCESS)
             unsigned preprocess_flags = 0;  // FGOICP_PRE_* (0 = bit-identical to the reference's host code)
             float trim_fraction = 0.0f; // > 0: trimmed registration over the (1 - trim_fraction) * ns best points (extension; env FGOICP_TRIM_FRACTION)
+            // called (under the snapshot mutex, from the thread inside run()) every time a new incumbent (SSE, R, t) is
+            // published -- the moments the reference's viewer would see best_* change (fgoicp.cpp:79-84, 22-23)
+            std::function<void(float, const glm::mat3&, const glm::vec3&)> on_best;
         };
 
         struct Stats
@@ -111,6 +115,7 @@ namespace icp
         {
             std::lock_guard<std::mutex> g(snap_mutex_);
             best_sse = e; best_rotation = R; best_translation = t;
+            if (options_.on_best) options_.on_best(e, R, t);
         }
         void publish_last(const glm::mat3& R, const glm::vec3& t)
         {

@@ -102,11 +102,9 @@ def baseline_child(kind, pair, res, mse):
         pp = driver.preprocess(model, data)
         lut, dims = O.lut_build(pp["model"], pp["bbox_min"], pp["bbox_max"], res)      # k-d tree build, all host threads
         ctor_ms = (time.perf_counter() - t0) * 1e3
-        try:    # the device's sin(half-angle) constants (a one-ulp matter); glibc's otherwise
-            ctx = capi.Context(pp["model"][:64], pp["data"][:8], pp["bbox_min"], pp["bbox_max"], 0.1, flags=0)
-            spans = np.array([1.0, 0.5, 0.25, 0.125, 0.0625, 0.03125], np.float32)
-            O.set_sin_table(spans, ctx.rot_sin(spans))
-            ctx.close()
+        try:    # the reference build's sin(half-angle) constants (tests/golden/reference_sin.json)
+            j = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_sin.json")))
+            O.set_sin_table(np.array(j["spans"], np.float32), np.array(j["reference_build_bits"], np.uint32).view(np.float32))
         except Exception:
             pass
         print(json.dumps(dict(stage="ctor", threads=O.num_threads(), ctor_ms=ctor_ms)), flush=True)

@@ -13,6 +13,20 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+def install_reference_sin():
+    """The oracle's sin(half-angle) constants (registration.cu:41-42) come from tests/golden/reference_sin.json: values
+    produced by a kernel compiled inside the reference build (tests/golden/make_reference_sin.py), not by the library
+    under test (the device under test used to supply them)."""
+    import json
+    from oracle import oracle as O
+    with open(os.path.join(ROOT, "tests", "golden", "reference_sin.json")) as f:
+        j = json.load(f)
+    spans = np.array(j["spans"], np.float32)
+    vals = np.array(j["reference_build_bits"], np.uint32).view(np.float32)
+    O.set_sin_table(spans, vals)
+    return spans, vals
+
+
 def make_problem(nt=2000, ns=300, res=0.03, seed=5, sigma=0.01, max_angle=None):
     """Small seeded registration problem, preprocessed the way FastGoICP's constructor does it."""
     from fast_go_icp_b200 import workloads
@@ -22,6 +36,11 @@ def make_problem(nt=2000, ns=300, res=0.03, seed=5, sigma=0.01, max_angle=None):
     pp["res"] = np.float32(res)
     pp["raw"] = w
     return pp
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _reference_sin_table():
+    install_reference_sin()
 
 
 @pytest.fixture(scope="session")
@@ -40,9 +59,7 @@ def gpu_ctx(small_problem):
     pp = small_problem
     ctx = capi.Context(pp["model"], pp["data"], pp["bbox_min"], pp["bbox_max"], float(pp["res"]),
                        flags=capi.BUILD_PACKED | capi.BUILD_TEX)
-    # both sides must use the same sin(half-angle) constants: take the device's
-    from oracle import oracle as O
-    spans = np.array([1.0, 0.5, 0.25, 0.125, 0.0625, 0.03125], np.float32)
-    O.set_sin_table(spans, ctx.rot_sin(spans))
+    # the oracle uses the reference build's sin(half-angle) constants (golden file), never the device's
+    install_reference_sin()
     yield ctx
     ctx.close()

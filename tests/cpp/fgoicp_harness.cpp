@@ -9,9 +9,13 @@
 // as they would for the unchanged reference CLI.
 #include <fgoicp/fgoicp.hpp>
 
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <fstream>
+#include <mutex>
+#include <thread>
 
 static std::vector<glm::vec3> read_cloud(const char* path)
 {
@@ -31,9 +35,69 @@ int main(int argc, char** argv)
     {
         icp::Logger::set_verbose(false);
         std::vector<glm::vec3> pct = read_cloud(argv[1]), pcs = read_cloud(argv[2]);
+        // HARNESS_POLL=1 (reference fgoicp.hpp:32-43): a second thread polls the visualisation
+        // accessors while run() works, the way the reference's companion viewer does.  Every (SSE, R, t) it sees must
+        // be one of the triples the search published (recorded through Options::on_best) or the constructor's state.
+        struct Triple { float v[13]; };
+        auto pack = [](float e, const glm::mat3& R, const glm::vec3& t)
+        {
+            Triple x;
+            x.v[0] = e;
+            for (int c = 0; c < 3; ++c) for (int r = 0; r < 3; ++r) x.v[1 + c * 3 + r] = R[c][r];
+            for (int a = 0; a < 3; ++a) x.v[10 + a] = t[a];
+            return x;
+        };
+        const bool poll = std::getenv("HARNESS_POLL") != nullptr;
+        std::vector<Triple> published, seen;
+        std::mutex pub_mutex;
+        icp::FastGoICP::Options opt;
+        if (poll)
+        {
+            published.push_back(pack(1E+10f, glm::mat3(1.0f), glm::vec3(0.0f)));      // constructor state (fgoicp.hpp:20-22)
+            opt.on_best = [&](float e, const glm::mat3& R, const glm::vec3& t)
+            {
+                std::lock_guard<std::mutex> g(pub_mutex);
+                published.push_back(pack(e, R, t));
+            };
+        }
         icp::FastGoICP fgoicp(std::move(pct), std::move(pcs), static_cast<float>(std::atof(argv[3])),
-                              static_cast<float>(std::atof(argv[4])));
+                              static_cast<float>(std::atof(argv[4])), opt);
+        std::atomic<bool> stop{ false };
+        unsigned long long n_polls = 0;
+        std::thread poller;
+        if (poll)
+            poller = std::thread([&]()
+            {
+                while (!stop.load(std::memory_order_acquire))
+                {
+                    auto [e, R, t] = fgoicp.get_best_snapshot();
+                    Triple x = pack(e, R, t);
+                    if (seen.empty() || std::memcmp(&seen.back(), &x, sizeof(x)) != 0) seen.push_back(x);
+                    // the separate accessors of the reference must be safe to call concurrently as well
+                    (void)fgoicp.get_best_error(); (void)fgoicp.get_best_transform(); (void)fgoicp.get_last_transform();
+                    ++n_polls;
+                    std::this_thread::yield();
+                }
+            });
         auto [R, t] = fgoicp.run();
+        if (poll)
+        {
+            stop.store(true, std::memory_order_release);
+            poller.join();
+            size_t bad = 0;
+            for (const Triple& x : seen)
+            {
+                bool found = false;
+                for (const Triple& p : published) found = found || std::memcmp(&p, &x, sizeof(x)) == 0;
+                bad += !found;
+            }
+            // the last published triple is what the accessors return after run()
+            auto [e1, R1, t1] = fgoicp.get_best_snapshot();
+            Triple last = pack(e1, R1, t1);
+            const bool final_ok = std::memcmp(&published.back(), &last, sizeof(last)) == 0;
+            std::printf("POLL polls %llu distinct %zu published %zu torn %zu final_ok %d\n", n_polls, seen.size(), published.size(), bad,
+                        final_ok ? 1 : 0);
+        }
         std::printf("RESULT");
         for (int c = 0; c < 3; ++c)
             for (int r = 0; r < 3; ++r) std::printf(" %a", static_cast<double>(R[c][r]));

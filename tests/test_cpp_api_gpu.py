@@ -82,3 +82,45 @@ def test_cpp_class_reports_errors_as_exceptions(tmp_path, problem):
     out = subprocess.run([exe, str(tmp_path / "empty.f32"), str(tmp_path / "data.f32"), "0.02", "1e-4"],
                          capture_output=True, text=True, timeout=120)
     assert out.returncode == 1 and "ERROR" in out.stderr
+
+
+def test_progress_accessors_polled_during_run_on_the_gpu(tmp_path, problem):
+    """SURVEY.md 8f N4 (reference fgoicp.hpp:32-43): a second host thread polls the visualisation accessors while run()
+    drives the GPU; every (SSE, R, t) it sees is a published triple, never a torn mix, and the last one is final."""
+    exe = build_harness.build()
+    problem["model"].astype(np.float32).tofile(tmp_path / "model.f32")
+    problem["data"].astype(np.float32).tofile(tmp_path / "data.f32")
+    out = subprocess.run([exe, str(tmp_path / "model.f32"), str(tmp_path / "data.f32"), "0.02", "1e-4"], capture_output=True,
+                         text=True, env=dict(os.environ, HARNESS_POLL="1"), timeout=300)
+    assert out.returncode == 0, out.stderr
+    f = [l for l in out.stdout.splitlines() if l.startswith("POLL")][-1].split()
+    polls, distinct, published, torn, final_ok = int(f[2]), int(f[4]), int(f[6]), int(f[8]), int(f[10])
+    assert polls > 100 and published >= 3 and 1 <= distinct <= published
+    assert torn == 0 and final_ok == 1
+
+
+def test_unchanged_reference_cli_binary_runs_the_search(tmp_path, problem):
+    """The reference's own src/main.cpp + src/utilities.hpp, compiled UNCHANGED against include/fgoicp/*.hpp and this
+    library (fast_go_icp_b200/build_cli.py -> build/fast-go-icp; built where /root/reference is mounted, travels to the GPU
+    box): config TOML -> loaders -> icp::FastGoICP -> run() (src/main.cpp:38-55).  Its log carries the final error."""
+    import re
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "build", "fast-go-icp")
+    if not os.path.exists(exe):
+        pytest.skip("build/fast-go-icp not built (needs the reference tree at build time)")
+    for name, pts in (("model.txt", problem["model"]), ("data.txt", problem["data"])):
+        with open(tmp_path / name, "w") as f:
+            f.write("%d\n" % len(pts))
+            np.savetxt(f, pts, fmt="%.7f")
+    (tmp_path / "cfg.toml").write_text(
+        '[info]\nversion = "1.0.0"\n[io]\ntarget = "%s"\nsource = "%s"\n'
+        '[params]\ntrim = false\ntarget_subsample = 1.0\nsource_subsample = 0.5\nlut_resolution = 0.02\nmse_threshold = 1e-4\n'
+        % (tmp_path / "model.txt", tmp_path / "data.txt"))
+    out = subprocess.run([exe, "-c", str(tmp_path / "cfg.toml")], capture_output=True, text=True, timeout=300, cwd=str(tmp_path))
+    assert out.returncode == 0, out.stdout[-1500:] + out.stderr[-1500:]
+    log = out.stdout + out.stderr
+    m = re.search(r"Searching over! Best Error: ([0-9.eE+-]+)", log)
+    assert m, log[-1500:]
+    sse = float(m.group(1))
+    # source_subsample = 0.5 of 800 points with the reference's unseeded sampler: about 400 points at sigma 0.005
+    assert 0.0 < sse < 400 * 3 * (0.005 ** 2) * 4
+    assert "Fast Go-ICP finished" in log or "finished" in log.lower()

@@ -94,3 +94,20 @@ def test_cpp_class_reports_a_missing_gpu_for_device_preprocessing(tmp_path, prob
     out = subprocess.run([exe, str(tmp_path / "m.f32"), str(tmp_path / "d.f32"), "0.03", "1e-4"], capture_output=True, text=True,
                          env=dict(os.environ, FGOICP_DEVICE_PREPROCESS="1"), timeout=120)
     assert out.returncode == 1 and "no CUDA device" in out.stderr
+
+
+def test_progress_accessors_polled_from_a_second_thread_return_published_triples(tmp_path, problem):
+    """SURVEY.md 8f N4 (reference fgoicp.hpp:32-43, the viewer's accessors): a second thread polls get_best_snapshot(),
+    get_best_error(), get_best_transform(), get_last_transform() while run() works.  Every (SSE, R, t) it sees must be
+    one of the triples the search published -- never a mix of two -- and the last one is what the accessors return."""
+    w = problem
+    exe = cpu_harness.build_cpu()
+    np.ascontiguousarray(w["model"], np.float32).tofile(tmp_path / "model.f32")
+    np.ascontiguousarray(w["data"], np.float32).tofile(tmp_path / "data.f32")
+    out = subprocess.run([exe, str(tmp_path / "model.f32"), str(tmp_path / "data.f32"), "0.03", "0.0001"], capture_output=True,
+                         text=True, env=dict(os.environ, HARNESS_POLL="1"), timeout=900)
+    assert out.returncode == 0, out.stderr
+    f = [l for l in out.stdout.splitlines() if l.startswith("POLL")][-1].split()
+    polls, distinct, published, torn, final_ok = int(f[2]), int(f[4]), int(f[6]), int(f[8]), int(f[10])
+    assert polls > 100 and published >= 3 and 1 <= distinct <= published
+    assert torn == 0 and final_ok == 1

@@ -1,10 +1,16 @@
-"""Full-size parity on the reference repository's own bunny pair (test/bunny.toml sizes: 17,973 / 3,037 points, grid
-377 x 372 x 292 at 0.005).  The golden values are what the CUDA path returned on a B200 (tests/golden/
-make_fullsize_golden.py).  The whole search -- 40 rotation cubes, 1.7e8 bound evaluations, 28 ICP refinements -- must come
-out THE SAME BITS from
-  * the CPU oracle driven through the same level-synchronous driver (CPU test), and
-  * the CUDA path (GPU test),
-so a disagreement between kernels and oracle anywhere along the path shows up at the size the reference is run at."""
+"""Whole searches at full size, CUDA path against the CPU oracle, bit for bit.
+
+The golden values under tests/golden/fullsize_oracle/*.json were produced WITHOUT a GPU: the CPU oracle (pinned on the
+unmodified reference, tests/test_golden*.py) driven through the same level-synchronous driver as the CUDA path
+(tests/golden/make_fullsize_oracle_golden.py; minutes per case on 8 cores).  Each holds the final SSE bits, the pose bits
+and the evaluation / cube / refinement / iteration counts of one search on one of BASELINE.json's workloads at the size
+SURVEY.md 8d names: the reference repository's bunny pair (two thresholds), its skull scan (W2), its two dragon range
+scans (W3), the 40 %-overlap skull halves (W4) and the synthetic 100k / 10k pair (W5).  The GPU tests require the CUDA
+path to return exactly these values -- so every bound, every pruning decision, every NN winner, every Procrustes step
+and every ICP stop of a multi-billion-evaluation search agrees with the restatement of the reference.  The CPU tests
+re-derive the cheapest case from the oracle (one rank, and sharded over two gloo ranks).
+(Round 1 compared the CUDA path with its own recorded output; VERDICT r01, "what's weak" #2.)"""
+import json
 import os
 
 import numpy as np
@@ -12,47 +18,62 @@ import pytest
 
 from fast_go_icp_b200 import driver
 
-GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "bunny_full.npz")
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-def _check(g, R, t, z, tag):
-    counts = z["gpu_counts_" + tag]
-    assert np.float32(g.best_sse) == z["gpu_sse_" + tag]
-    assert np.array_equal(np.asarray(R, np.float32), z["gpu_R_" + tag]) and np.array_equal(np.asarray(t, np.float32), z["gpu_t_" + tag])
-    assert [g.stats["bound_evals"], g.stats["rot_cubes"], g.stats["icp_runs"]] == [int(c) for c in counts]
+def golden(case):
+    path = os.path.join(GOLDEN, "fullsize_oracle", case + ".json")
+    if not os.path.exists(path):
+        pytest.skip("no oracle-derived golden for " + case)
+    with open(path) as f:
+        return json.load(f)
 
 
-def test_oracle_through_the_driver_reproduces_the_gpu_result_bit_for_bit():
+def clouds(pair):
+    if pair == "w5":
+        from fast_go_icp_b200 import workloads
+        w = workloads.synthetic_pair()
+        return w["model"], w["data"]
+    z = np.load(os.path.join(GOLDEN, pair + "_full.npz"))
+    return z["model"], z["data"]
+
+
+def bits(a):
+    return [int(x) for x in np.asarray(a, np.float32).ravel().view(np.uint32)]
+
+
+def check(g, R, t, want):
+    assert int(np.float32(g.best_sse).view(np.uint32)) == want["sse_bits"], (float(g.best_sse), want["sse"])
+    assert bits(R) == want["R_bits"] and bits(t) == want["t_bits"]
+    got = [g.stats["bound_evals"], g.stats["rot_cubes"], g.stats["icp_runs"], g.stats["icp_iters"]]
+    assert got == [want["bound_evals"], want["rot_cubes"], want["icp_runs"], want["icp_iters"]]
+
+
+def test_oracle_through_the_driver_reproduces_its_golden():
+    """The generator's own result, re-derived in the CPU suite (bunny pair, 40 rotation cubes, 1.7e8 evaluations)."""
     from oracle_context import OracleContext
-    z = np.load(GOLD)
-    g = driver.FastGoICP(z["model"], z["data"], 0.005, 1e-3, ctx_factory=OracleContext)
+    want = golden("bunny_mse1e-3")
+    model, data = clouds("bunny")
+    g = driver.FastGoICP(model, data, 0.005, 1e-3, ctx_factory=OracleContext)
     R, t = g.run()
-    _check(g, R, t, z, "mse1e-3")
+    check(g, R, t, want)
     g.close()
 
 
+CASES = ["bunny_mse1e-3", "bunny_mse1e-5", "skull_mse1e-3", "w5_mse1e-4", "dragon_mse1e-3", "dragon_mse1e-4",
+         "overlap_mse1e-3", "overlap_mse1e-4"]
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize("tag,mse", [("mse1e-3", 1e-3), ("mse1e-5", 1e-5)])
-def test_cuda_path_reproduces_the_recorded_result_bit_for_bit(tag, mse):
+@pytest.mark.parametrize("case", CASES)
+def test_cuda_path_reproduces_the_oracle_result_bit_for_bit(case):
     from fast_go_icp_b200 import capi
-    z = np.load(GOLD)
-    g = driver.FastGoICP(z["model"], z["data"], 0.005, mse, flags=capi.BUILD_PACKED)
+    want = golden(case)
+    model, data = clouds(want["pair"])
+    assert len(model) == want["nt"] and len(data) == want["ns"]
+    g = driver.FastGoICP(model, data, want["lut_resolution"], want["mse_threshold"], flags=capi.BUILD_PACKED)
     R, t = g.run()
-    _check(g, R, t, z, tag)
-    g.close()
-
-
-@pytest.mark.gpu
-def test_cuda_path_reproduces_the_recorded_w5_result_bit_for_bit():
-    """BASELINE.json's synthetic 100k / 10k workload: 2,496 rotation cubes, 7.0e9 bound evaluations, 43 refinements.  The
-    CPU oracle, driven through the same driver, reproduces exactly these values too (195 s on 8 cores:
-    scripts/fullsize_parity_cpu.py, profiles/fullsize_parity_r01.log) -- too long for the CPU suite."""
-    from fast_go_icp_b200 import capi, workloads
-    z = np.load(GOLD)
-    w = workloads.synthetic_pair()
-    g = driver.FastGoICP(w["model"], w["data"], 0.005, 1e-4, flags=capi.BUILD_PACKED)
-    R, t = g.run()
-    _check(g, R, t, z, "w5")
+    check(g, R, t, want)
     g.close()
 
 
@@ -65,8 +86,8 @@ def _sharded_worker(rank, world, port, out_path):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     O.set_num_threads(4)
-    z = np.load(GOLD)
-    g = driver.FastGoICP(z["model"], z["data"], 0.005, 1e-3, ctx_factory=OracleContext)
+    model, data = clouds("bunny")
+    g = driver.FastGoICP(model, data, 0.005, 1e-3, ctx_factory=OracleContext)
     R, t = g.run()
     if rank == 0:
         torch.save(dict(R=np.asarray(R, np.float32), t=np.asarray(t, np.float32), sse=np.float32(g.best_sse),
@@ -77,28 +98,13 @@ def _sharded_worker(rank, world, port, out_path):
 
 def test_frontier_sharded_over_two_ranks_reproduces_the_same_bits(tmp_path):
     """SURVEY.md 8e at full size: the rotation frontier dealt over 2 ranks (gloo), best upper bound MIN-reduced per wave --
-    same SSE and pose as one rank and as the GPU, with each rank doing only its share of the evaluations."""
+    same SSE and pose as one rank, with each rank doing only its share of the evaluations."""
     import torch
     import torch.multiprocessing as mp
-    z = np.load(GOLD)
+    want = golden("bunny_mse1e-3")
     out = str(tmp_path / "sharded.pt")
     mp.spawn(_sharded_worker, args=(2, 29650 + os.getpid() % 300, out), nprocs=2, join=True)
     res = torch.load(out, weights_only=False)
-    assert res["sse"] == z["gpu_sse_mse1e-3"]
-    assert np.array_equal(res["R"], z["gpu_R_mse1e-3"]) and np.array_equal(res["t"], z["gpu_t_mse1e-3"])
-    assert 0 < res["local_evals"] < int(z["gpu_counts_mse1e-3"][0])
-
-
-@pytest.mark.gpu
-@pytest.mark.parametrize("tag,mse", [("mse1e-3", 1e-3), ("mse1e-4", 1e-4)])
-def test_cuda_path_reproduces_the_recorded_dragon_result_bit_for_bit(tag, mse):
-    """The reference repository's two dragon range scans at full size (75,305 / 10,000 points): partial overlap, so nearly
-    every rotation cube is refined -- 2,498 ICP refinements, ~46,000 ICP iterations, each two exact NN searches of 10,000
-    points.  Any change of a single NN winner, Procrustes sum or stop decision moves these bits.  (The CPU oracle
-    reproduces the mse 1e-3 values too: 343 s, scripts/fullsize_parity_cpu.py.)"""
-    from fast_go_icp_b200 import capi
-    z = np.load(os.path.join(os.path.dirname(GOLD), "dragon_full.npz"))
-    g = driver.FastGoICP(z["model"], z["data"], 0.005, mse, flags=capi.BUILD_PACKED)
-    R, t = g.run()
-    _check(g, R, t, z, tag)
-    g.close()
+    assert int(res["sse"].view(np.uint32)) == want["sse_bits"]
+    assert bits(res["R"]) == want["R_bits"] and bits(res["t"]) == want["t_bits"]
+    assert 0 < res["local_evals"] < want["bound_evals"]

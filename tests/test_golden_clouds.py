@@ -96,8 +96,9 @@ def test_oracle_full_run_vs_reference(name):
     """End to end on the CPU: the oracle's best-first run() against the reference's own run()."""
     pp, P = problem(name), name + "_"
     e, R, t, _ = O.run(pp["model"], pp["data"], *_lut(pp), float(G[P + "mse"]))
-    assert abs(e - G[P + "run_sse"]) <= 1e-3 * G[P + "run_sse"]
-    assert np.allclose(R, G[P + "run_Rn"], atol=3e-3) and np.allclose(t, G[P + "run_tn"], atol=3e-3)
+    # BASELINE.json north_star: MSE within 1e-6 relative (achieved: bunny 2.3e-7, skull 9e-8; pose 3e-7 / 3e-8)
+    assert abs(e - G[P + "run_sse"]) <= 1e-6 * G[P + "run_sse"]
+    assert np.allclose(R, G[P + "run_Rn"], atol=2e-6, rtol=0) and np.allclose(t, G[P + "run_tn"], atol=2e-6, rtol=0)
 
 
 # ---- GPU ------------------------------------------------------------------------------------------------
@@ -112,9 +113,7 @@ def ctxs():
             pp = problem(name)
             c = capi.Context(pp["model"], pp["data"], pp["bbox_min"], pp["bbox_max"], pp["res"],
                              flags=capi.BUILD_PACKED | capi.BUILD_TEX)
-            spans = np.array([1.0, 0.5, 0.25, 0.125, 0.0625, 0.03125], np.float32)
-            O.set_sin_table(spans, c.rot_sin(spans))
-            made[name] = c
+            made[name] = c          # (the oracle's sin constants come from tests/golden/reference_sin.json: conftest)
         return made[name]
     yield get
     for c in made.values():
@@ -167,12 +166,18 @@ def test_cuda_vs_reference_and_oracle(name, ctxs):
             assert ev[i] == wev and np.isclose(ub[i], wub, rtol=ULP, atol=0) and np.array_equal(bt[i], wbt)
 
 
+# (relative SSE, absolute pose) tolerance of run() against the reference's run() where the north_star figures
+# (1e-6, far inside the BnB leaf) cannot be asserted; every other pair is held to them.  Filled from the achieved
+# differences recorded on the B200 (profiles/run_parity_r02.md).
+RUN_TOL = {}
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", PAIRS)
 def test_cuda_full_run_vs_reference(name):
     """run() through the Python driver against the reference's own run() on the same pair.
-    * reference visiting order ("bestfirst"): final SSE within 1e-3 relative (the final ICP stops at a 0.05 %
-      improvement), pose within 3e-3 in the normalised frame;
+    * reference visiting order ("bestfirst"): final SSE within BASELINE.json's 1e-6 relative of the reference's, pose
+      within 2e-6 in the normalised frame (RUN_TOL below lists the pairs where that cannot hold, and why);
     * level-synchronous schedule (default; whole levels in flight): the search stops as soon as
       best_sse - lb <= sse_threshold, so a different visiting order may stop at a different incumbent; both are
       optimal to within sse_threshold, which is what is asserted."""
@@ -181,9 +186,10 @@ def test_cuda_full_run_vs_reference(name):
     g = driver.FastGoICP(CLOUDS[name + "_model"], CLOUDS[name + "_data"], float(G[P + "res"]), float(G[P + "mse"]),
                          schedule="bestfirst")
     R, t = g.run()
-    assert abs(g.best_sse - G[P + "run_sse"]) <= 1e-3 * G[P + "run_sse"]
-    assert np.allclose(g.best_R, G[P + "run_Rn"], atol=3e-3) and np.allclose(g.best_t, G[P + "run_tn"], atol=3e-3)
-    assert np.allclose(t, G[P + "run_t"], atol=1e-2 / float(g.pp["scale"]))
+    sse_tol, pose_tol = RUN_TOL.get(name, (1e-6, 2e-6))
+    assert abs(g.best_sse - G[P + "run_sse"]) <= sse_tol * G[P + "run_sse"]
+    assert np.allclose(g.best_R, G[P + "run_Rn"], atol=pose_tol, rtol=0) and np.allclose(g.best_t, G[P + "run_tn"], atol=pose_tol, rtol=0)
+    assert np.allclose(t, G[P + "run_t"], atol=10 * pose_tol / float(g.pp["scale"]), rtol=0)
     g.close()
     g = driver.FastGoICP(CLOUDS[name + "_model"], CLOUDS[name + "_data"], float(G[P + "res"]), float(G[P + "mse"]))
     g.run()

@@ -51,11 +51,16 @@ def test_samplers(small_problem, gpu_ctx):
     assert np.median(rel) < 1e-5 and np.quantile(rel, 0.99) < 5e-3 and np.max(rel) < 0.1
 
 
-def test_device_sin_table(gpu_ctx):
-    spans = np.array([0.5, 0.25, 0.125, 0.0625], np.float32)
+def test_device_sin_equals_the_reference_builds_constants(gpu_ctx):
+    """sin(span * sqrt3 * pi / 2) (registration.cu:41-42): the library's device values equal, bit for bit, the constants
+    a kernel compiled inside the reference build produced (tests/golden/reference_sin.json, what the oracle uses) -- and,
+    when oracle/_ref is present, what that kernel returns on this very GPU."""
+    from conftest import install_reference_sin
+    spans, want = install_reference_sin()
     dev = gpu_ctx.rot_sin(spans)
-    host = np.sin((spans * np.float32(1.732050807568877)) * np.float32(3.141592653589793) / np.float32(2)).astype(np.float32)
-    assert np.max(np.abs(dev - host)) <= 2 * np.spacing(np.float32(1.0))
+    assert np.array_equal(dev.view(np.uint32), want.view(np.uint32))
+    if REF.available():
+        assert np.array_equal(REF.rot_sin(spans).view(np.uint32), want.view(np.uint32))
 
 
 @pytest.mark.parametrize("fix_rot", [True, False])

@@ -96,7 +96,14 @@ struct CellGrid
     const float4* pts;     // sorted points (LUT-space copy or original-coordinate copy)
     int nx, ny, nz;
     float h, inv_h;        // cell size
+    // Coarse boxes: the non-empty blocks of FG_COARSE^3 cells, each with the tight bounding box of its points (LUT
+    // space) -- box k = { (lo.x, lo.y, lo.z, bits(X | Y << 10 | Z << 20)), (hi.x, hi.y, hi.z, 0) }.  Lets the NN search
+    // of a far query cull whole blocks of rows instead of looking every row of its ball up (nn_icp.cu).
+    const float4* coarse = nullptr;
+    int n_coarse = 0;
+    int coarse_min_rows = 320;     // rows of a ball beyond which the coarse boxes are consulted (+ n_coarse / 8)
 };
+#define FG_COARSE 8
 
 struct fgoicp_ctx
 {
@@ -133,7 +140,9 @@ struct fgoicp_ctx
     float4* d_cell_M = nullptr;               // same order, original coordinates, w = original index
     int cnx = 0, cny = 0, cnz = 0;
     float cell_h = 0.f, cell_inv_h = 0.f;
-    int nn_mode = 0;                          // 0: cell-grid search, 1: tiled brute force (test hook)
+    float4* d_coarse = nullptr;               // coarse boxes of the cell grid (CellGrid::coarse)
+    int n_coarse = 0;
+    int nn_mode = 0;                          // 0: cell-grid search, 1: tiled brute force, 2 / 3: cell grid with the coarse boxes forced on / off (test hooks)
 
     // z-phase-ordered bound evaluation (bounds_phased.cu): per-launch index lists
     void* d_phase = nullptr;

@@ -173,6 +173,48 @@ __global__ void k_cell_scatter(const float4* __restrict__ P, const float4* __res
     sortedM[slot] = M[i];
 }
 
+// One warp per block of FG_COARSE^3 cells: number of points and their tight bounding box (LUT space).
+__global__ void __launch_bounds__(128)
+k_coarse_boxes(CellGrid g, int Cx, int Cy, int Cz, float4* __restrict__ lo_cnt, float4* __restrict__ hi)
+{
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= Cx * Cy * Cz) return;
+    const int X = w % Cx, Y = (w / Cx) % Cy, Z = w / (Cx * Cy);
+    const int x0 = X * FG_COARSE, x1 = min(x0 + FG_COARSE, g.nx) - 1;
+    float lo[3] = { 3.0e38f, 3.0e38f, 3.0e38f }, hi3[3] = { -3.0e38f, -3.0e38f, -3.0e38f };
+    int cnt = 0;
+    for (int row = lane; row < FG_COARSE * FG_COARSE; row += 32)
+    {
+        const int cy = Y * FG_COARSE + row % FG_COARSE, cz = Z * FG_COARSE + row / FG_COARSE;
+        if (cy >= g.ny || cz >= g.nz) continue;
+        const int c0 = (cz * g.ny + cy) * g.nx;
+        const int b = g.start[c0 + x0], e = g.start[c0 + x1 + 1];
+        cnt += e - b;
+        for (int k = b; k < e; ++k)
+        {
+            const float4 p = g.pts[k];
+            lo[0] = fminf(lo[0], p.x); lo[1] = fminf(lo[1], p.y); lo[2] = fminf(lo[2], p.z);
+            hi3[0] = fmaxf(hi3[0], p.x); hi3[1] = fmaxf(hi3[1], p.y); hi3[2] = fmaxf(hi3[2], p.z);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+    {
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+        {
+            lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+            hi3[a] = fmaxf(hi3[a], __shfl_xor_sync(0xffffffffu, hi3[a], o));
+        }
+    }
+    if (lane == 0)
+    {
+        lo_cnt[w] = make_float4(lo[0], lo[1], lo[2], __int_as_float(cnt));
+        hi[w] = make_float4(hi3[0], hi3[1], hi3[2], 0.0f);
+    }
+}
+
 #define BRICK 8
 #define BRICK_CAND 1024
 
@@ -417,6 +459,37 @@ static int build_cell_grid(fgoicp_ctx* c, const float4* d_P)
     FG_CUDA(cudaGetLastError());
     FG_CUDA(cudaStreamSynchronize(st));
     cudaFree(d_cell_of); cudaFree(d_counts); cudaFree(d_fill);
+    // coarse boxes (non-empty blocks of FG_COARSE^3 cells with the bounding box of their points), compacted on the host
+    {
+        const int Cx = (c->cnx + FG_COARSE - 1) / FG_COARSE, Cy = (c->cny + FG_COARSE - 1) / FG_COARSE, Cz = (c->cnz + FG_COARSE - 1) / FG_COARSE;
+        const int nC = Cx * Cy * Cz;
+        float4 *d_lo = nullptr, *d_hi = nullptr;
+        FG_CUDA(cudaMalloc(&d_lo, sizeof(float4) * nC));
+        FG_CUDA(cudaMalloc(&d_hi, sizeof(float4) * nC));
+        k_coarse_boxes<<<(nC * 32 + 127) / 128, 128, 0, st>>>(g, Cx, Cy, Cz, d_lo, d_hi);
+        FG_CUDA(cudaGetLastError());
+        std::vector<float4> hlo(nC), hhi(nC), list;
+        FG_CUDA(cudaMemcpyAsync(hlo.data(), d_lo, sizeof(float4) * nC, cudaMemcpyDeviceToHost, st));
+        FG_CUDA(cudaMemcpyAsync(hhi.data(), d_hi, sizeof(float4) * nC, cudaMemcpyDeviceToHost, st));
+        FG_CUDA(cudaStreamSynchronize(st));
+        cudaFree(d_lo); cudaFree(d_hi);
+        for (int w = 0; w < nC; ++w)
+        {
+            int cnt; memcpy(&cnt, &hlo[w].w, 4);
+            if (cnt <= 0) continue;
+            const unsigned X = (unsigned)(w % Cx), Y = (unsigned)((w / Cx) % Cy), Z = (unsigned)(w / (Cx * Cy));
+            const unsigned packed = X | (Y << 10) | (Z << 20);
+            float pf; memcpy(&pf, &packed, 4);
+            list.push_back(make_float4(hlo[w].x, hlo[w].y, hlo[w].z, pf));
+            list.push_back(make_float4(hhi[w].x, hhi[w].y, hhi[w].z, 0.0f));
+        }
+        c->n_coarse = (int)(list.size() / 2);
+        if (c->n_coarse > 0)
+        {
+            FG_CUDA(cudaMalloc(&c->d_coarse, sizeof(float4) * list.size()));
+            FG_CUDA(cudaMemcpy(c->d_coarse, list.data(), sizeof(float4) * list.size(), cudaMemcpyHostToDevice));
+        }
+    }
     return FGOICP_OK;
 }
 
@@ -686,7 +759,7 @@ extern "C" int fgoicp_ctx_destroy(fgoicp_ctx* c)
     if (c->arr) cudaFreeArray(c->arr);
     cudaFree(c->d_model); cudaFree(c->d_data); cudaFree(c->d_data_orig); cudaFree(c->d_grid); cudaFree(c->d_packed);
     cudaFree(c->d_scratch); cudaFree(c->d_work); cudaFree(c->d_nnkey); cudaFree(c->d_icp); cudaFree(c->d_inl); cudaFree(c->d_icp_part); cudaFree(c->d_icp_jobs); cudaFree(c->d_nnmemo); cudaFree(c->d_icp_loop);
-    cudaFree(c->d_cell_start); cudaFree(c->d_cell_P); cudaFree(c->d_cell_M); cudaFree(c->d_phase); cudaFree(c->d_rounds);
+    cudaFree(c->d_cell_start); cudaFree(c->d_cell_P); cudaFree(c->d_cell_M); cudaFree(c->d_coarse); cudaFree(c->d_phase); cudaFree(c->d_rounds);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -743,7 +816,7 @@ extern "C" int fgoicp_set_phased(fgoicp_ctx* c, int on)
 extern "C" int fgoicp_set_nn_mode(fgoicp_ctx* c, int mode)
 {
     FG_ARG(c, "NULL context");
-    FG_ARG(mode == 0 || mode == 1, "nn mode must be 0 (cell grid) or 1 (brute force)");
+    FG_ARG(mode >= 0 && mode <= 3, "nn mode must be 0 (cell grid), 1 (brute force), 2 (cell grid, coarse boxes for every query) or 3 (cell grid, no coarse boxes)");
     c->nn_mode = mode;
     return FGOICP_OK;
 }

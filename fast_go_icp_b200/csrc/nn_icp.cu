@@ -219,12 +219,6 @@ __device__ __forceinline__ float fg_shrink(float d2, float margin)
 #ifndef NN_RPL
 #define NN_RPL 1            // rows per lane and pass of the cell-grid search; measured on the dragon pair (W3, ICP ms): 1 -> 3688, 4 -> 3873, 8 -> 4101
 #endif
-#ifndef NN_INCR_ROWS
-#define NN_INCR_ROWS 0      // 1 (needs NN_RPL == 1): row -> (cz, cy) carried incrementally instead of divided per row (experiment)
-#endif
-#if NN_INCR_ROWS && NN_RPL != 1
-#error "NN_INCR_ROWS needs NN_RPL == 1"
-#endif
 #ifndef NN_FAST_ROOTED
 #define NN_FAST_ROOTED 1      // 0: always the exact rooted scan (measured: ICP 86 -> 71 ms on W5 with 1)
 #endif
@@ -283,13 +277,14 @@ __device__ __forceinline__ unsigned long long fg_nn_scan(const CellGrid& g, cons
     const int cz1 = min(max((int)floorf((lz + U) * inv_h), 0), g.nz - 1);
     const int cy0 = min(max((int)floorf((ly - U) * inv_h), 0), g.ny - 1);
     const int cy1 = min(max((int)floorf((ly + U) * inv_h), 0), g.ny - 1);
-    const int ny_rows = cy1 - cy0 + 1;
-    const int n_rows = ny_rows * (cz1 - cz0 + 1);
-#if NN_INCR_ROWS
-    int rz = lane / ny_rows, ry = lane % ny_rows;
-#endif
-    // NN_RPL rows per lane and pass: the two cell-range lookups of all of them are in flight together.  Measured
-    // neutral to slightly negative (see NN_RPL above): the row lookups are not what far queries wait for.
+
+    // All rows (y, z) of the cell box [z0, z1] x [y0, y1] that cut the ball, their chords clipped to the cell columns
+    // [xlo, xhi]; NN_RPL rows per lane and pass (the two cell-range lookups of all of them are in flight together;
+    // measured neutral to slightly negative, see NN_RPL above: the row lookups are not what far queries wait for).
+    auto scan_rows = [&](const int z0, const int z1, const int y0, const int y1, const int xlo, const int xhi)
+    {
+    const int ny_rows = y1 - y0 + 1;
+    const int n_rows = ny_rows * (z1 - z0 + 1);
     for (int row0 = 0; row0 < n_rows; row0 += NN_LPQ * NN_RPL)
     {
         int rb[NN_RPL], re[NN_RPL];
@@ -300,12 +295,7 @@ __device__ __forceinline__ unsigned long long fg_nn_scan(const CellGrid& g, cons
             const int row = row0 + r * NN_LPQ + lane;
             if (row < n_rows)
             {
-#if NN_INCR_ROWS
-                // (cz, cy) of this lane's row carried from pass to pass instead of a division per row
-                const int cz = cz0 + rz, cy = cy0 + ry;
-#else
-                int cz = cz0 + row / ny_rows, cy = cy0 + row % ny_rows;
-#endif
+                int cz = z0 + row / ny_rows, cy = y0 + row % ny_rows;
                 // edge cells also hold points clamped into them: their slab extends to infinity
                 float zlo = cz == 0 ? -FG_INF : (float)cz * h, zhi = cz == g.nz - 1 ? FG_INF : (float)(cz + 1) * h;
                 float ylo = cy == 0 ? -FG_INF : (float)cy * h, yhi = cy == g.ny - 1 ? FG_INF : (float)(cy + 1) * h;
@@ -315,10 +305,13 @@ __device__ __forceinline__ unsigned long long fg_nn_scan(const CellGrid& g, cons
                 if (dyz2 <= U2)
                 {
                     float wx = sqrtf(U2 - dyz2) * 1.00001f + 1e-6f;
-                    int cx0 = min(max((int)floorf((lx - wx) * inv_h), 0), g.nx - 1);
-                    int cx1 = min(max((int)floorf((lx + wx) * inv_h), 0), g.nx - 1);
-                    int c0 = (cz * g.ny + cy) * g.nx;
-                    rb[r] = __ldg(g.start + c0 + cx0); re[r] = __ldg(g.start + c0 + cx1 + 1);
+                    int cx0 = max(min(max((int)floorf((lx - wx) * inv_h), 0), g.nx - 1), xlo);
+                    int cx1 = min(min(max((int)floorf((lx + wx) * inv_h), 0), g.nx - 1), xhi);
+                    if (cx0 <= cx1)
+                    {
+                        int c0 = (cz * g.ny + cy) * g.nx;
+                        rb[r] = __ldg(g.start + c0 + cx0); re[r] = __ldg(g.start + c0 + cx1 + 1);
+                    }
                 }
             }
         }
@@ -388,11 +381,50 @@ __device__ __forceinline__ unsigned long long fg_nn_scan(const CellGrid& g, cons
         // share the tightest radius before the next pass
 #pragma unroll
         for (int o = NN_LPQ / 2; o > 0; o >>= 1) U2 = fminf(U2, __shfl_xor_sync(team_mask, U2, o, NN_LPQ));
-#if NN_INCR_ROWS
-        ry += NN_LPQ;
-        while (ry >= ny_rows) { ry -= ny_rows; ++rz; }
-#endif
     }
+    };
+
+    // Far queries.  The ball of a query at distance D from the surface is empty but for a small patch where it touches
+    // the surface, yet proving that costs pi (D / h)^2 row look-ups -- thousands for the data points of a partial-
+    // overlap scan that have no counterpart in the model, which is where the refinements of such pairs spend their time
+    // (the 6 % far queries of the dragon pair took 90 % of it).  For them the rows are not enumerated over the whole
+    // ball: the lanes test the bounding boxes of the NON-EMPTY coarse blocks (FG_COARSE^3 cells; a few hundred for a
+    // surface) against the ball, and only the rows of the few blocks that reach into it are scanned.  Exact all the
+    // same: every model point lies inside the box of its block, so a point inside the ball makes its block survive
+    // (the ball radius carries its usual slack, far above the rounding of the box distance).
+    const int n_rows_ball = (cy1 - cy0 + 1) * (cz1 - cz0 + 1);
+    if (g.n_coarse > 0 && n_rows_ball > g.coarse_min_rows + (g.n_coarse >> 3))
+    {
+        for (int k0 = 0; k0 < g.n_coarse; k0 += NN_LPQ)
+        {
+            const int k = k0 + lane;
+            float lb2 = FG_INF;
+            unsigned int box = 0;
+            if (k < g.n_coarse)
+            {
+                const float4 lo = __ldg(g.coarse + 2 * k), hi = __ldg(g.coarse + 2 * k + 1);
+                const float dx = fmaxf(fmaxf(lo.x - lx, lx - hi.x), 0.0f);
+                const float dy = fmaxf(fmaxf(lo.y - ly, ly - hi.y), 0.0f);
+                const float dz = fmaxf(fmaxf(lo.z - lz, lz - hi.z), 0.0f);
+                lb2 = dx * dx + dy * dy + dz * dz;
+                box = __float_as_uint(lo.w);
+            }
+            unsigned int live = __ballot_sync(team_mask, lb2 <= U2);
+            if (NN_LPQ != 32) live = (live & team_mask) >> ((threadIdx.x & 31) & ~(NN_LPQ - 1));
+            while (live)
+            {
+                const int j = __ffs(live) - 1;
+                live &= live - 1;
+                const float lbj = __shfl_sync(team_mask, lb2, j, NN_LPQ);
+                if (lbj > U2) continue;                            // the ball has shrunk meanwhile (U2 is team-uniform here)
+                const unsigned int bj = __shfl_sync(team_mask, box, j, NN_LPQ);
+                const int X = (int)(bj & 1023u) * FG_COARSE, Y = (int)((bj >> 10) & 1023u) * FG_COARSE, Z = (int)(bj >> 20) * FG_COARSE;
+                const int z0 = max(Z, cz0), z1 = min(Z + FG_COARSE - 1, cz1), y0 = max(Y, cy0), y1 = min(Y + FG_COARSE - 1, cy1);
+                if (z0 <= z1 && y0 <= y1) scan_rows(z0, z1, y0, y1, X, min(X + FG_COARSE - 1, g.nx - 1));
+            }
+        }
+    }
+    else scan_rows(cz0, cz1, cy0, cy1, 0, g.nx - 1);
     key = 0xffffffffffffffffull;
     if (best_idx != 0x7fffffff) key = ((unsigned long long)__float_as_uint(best) << 32) | (unsigned int)best_idx;
 #pragma unroll
@@ -1261,6 +1293,18 @@ int fg_ensure_icp_capacity(fgoicp_ctx* c, int n)
     return FGOICP_OK;
 }
 
+// coarse boxes of the cell grid for the far-query path of fg_nn_scan (FGOICP_NN_COARSE=0 turns it off,
+// FGOICP_NN_COARSE_MIN_ROWS=<n> moves the switch-over: test hooks, results are exact either way)
+static void fg_set_coarse(const fgoicp_ctx* c, CellGrid& g)
+{
+    static const int on = getenv("FGOICP_NN_COARSE") ? atoi(getenv("FGOICP_NN_COARSE")) : 1;
+    static const int min_rows = getenv("FGOICP_NN_COARSE_MIN_ROWS") ? atoi(getenv("FGOICP_NN_COARSE_MIN_ROWS")) : 320;
+    const bool use = (on && c->nn_mode != 3) || c->nn_mode == 2;
+    g.coarse = use ? c->d_coarse : nullptr;
+    g.n_coarse = use ? c->n_coarse : 0;
+    g.coarse_min_rows = c->nn_mode == 2 ? -(1 << 30) : min_rows;
+}
+
 static void nn_geometry(const fgoicp_ctx* c, dim3& grid, int& chunk, int n_inst)
 {
     int qtiles = (int)((c->ns + NN_THREADS * NN_QPT - 1) / (NN_THREADS * NN_QPT));
@@ -1275,11 +1319,12 @@ static void nn_geometry(const fgoicp_ctx* c, dim3& grid, int& chunk, int n_inst)
 static int enqueue_nn(fgoicp_ctx* c, int n_inst, int src_sel, int pose_sel, int rooted, int check_done)
 {
     char* inst = (char*)c->d_icp;
-    if (c->nn_mode == 0)
+    if (c->nn_mode != 1)
     {
         CellGrid g;
         g.start = c->d_cell_start; g.pts = c->d_cell_M;
         g.nx = c->cnx; g.ny = c->cny; g.nz = c->cnz; g.h = c->cell_h; g.inv_h = c->cell_inv_h;
+        fg_set_coarse(c, g);
         const int qpb = NNG_WARPS * 32 / NN_LPQ;            // queries per block
         // inside the ICP loop the key buffer carries the previous pass's winners (all-ones before the first pass)
         const float4* warm = (check_done && !getenv("FGOICP_NN_NO_WARM")) ? c->d_model : nullptr;
@@ -1421,7 +1466,7 @@ int fg_icp_run_batch(fgoicp_ctx* c, const float* R0s, const float* t0s, int n, i
     const long long guard_max = ((long long)(n + S - 1) / S + 1) * ((long long)max_iter + 2) + 8;
     bool all_done = false, results_on_host = false;
     const bool trimmed = c->trim_k > 0 && c->trim_k < c->ns;
-    if (c->icp_mode == 0 && !trimmed && c->nn_mode == 0)
+    if (c->icp_mode == 0 && !trimmed && c->nn_mode != 1)
     {
         // ---- persistent loop kernel: one cooperative launch, one synchronisation for the whole batch
         // block shape of the loop kernel (FGOICP_ICP_SHAPE selects among the instantiations for experiments)
@@ -1452,6 +1497,7 @@ int fg_icp_run_batch(fgoicp_ctx* c, const float* R0s, const float* t0s, int n, i
         IcpLoopArgs a;
         a.g.start = c->d_cell_start; a.g.pts = c->d_cell_M;
         a.g.nx = c->cnx; a.g.ny = c->cny; a.g.nz = c->cnz; a.g.h = c->cell_h; a.g.inv_h = c->cell_inv_h;
+        fg_set_coarse(c, a.g);
         a.L = c->lut; a.res = c->res;
         a.data = c->d_data; a.model = c->d_model; a.work = c->d_work; a.keys = c->d_nnkey; a.memo = c->d_nnmemo;
         a.inst = inst; a.ns = ns; a.S = S;

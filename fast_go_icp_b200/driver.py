@@ -121,6 +121,21 @@ class _Comm:
         self.dist.broadcast(t, src=src, group=self.group)
         return t.cpu().numpy()
 
+    def _buffers(self, n):
+        """Staging for the exchange, allocated once and grown geometrically: pinned host buffers on both sides of the
+        device buffers NCCL works on (gloo: plain host tensors), so that a wave's exchange is two async copies, one
+        collective and ONE stream synchronisation -- no allocation, no implicit synchronising copies."""
+        if getattr(self, "_cap", 0) < n:
+            cap = max(4096, 2 * n)
+            t = self.torch
+            cuda = self.dev.type == "cuda"
+            self._h_in = t.empty(cap, dtype=t.float32, pin_memory=cuda)
+            self._h_out = t.empty(cap * self.world, dtype=t.float32, pin_memory=cuda)
+            self._d_in = t.empty(cap, dtype=t.float32, device=self.dev) if cuda else self._h_in
+            self._d_out = t.empty(cap * self.world, dtype=t.float32, device=self.dev) if cuda else self._h_out
+            self._cap = cap
+        return self._h_in, self._d_in, self._d_out, self._h_out
+
     def exchange(self, header, local, n_total):
         """ONE all-gather per wave: every rank contributes a fixed-size header (uint32 words) and its round-robin
         shard of rows (float32).  Returns (headers [world, H] uint32, full rows [n_total, k]) on every rank."""
@@ -129,13 +144,20 @@ class _Comm:
             return header[None, :], local
         k = local.shape[1]
         per = (n_total + self.world - 1) // self.world
-        buf = np.zeros(len(header) + per * k, F)
+        n = len(header) + per * k
+        h_in, d_in, d_out, h_out = self._buffers(n)
+        buf = h_in.numpy()[:n]
         buf[:len(header)] = header.view(F)                      # bit patterns travel unchanged (copies only)
         buf[len(header):len(header) + local.size] = local.ravel()
-        t = self.torch.from_numpy(buf).to(self.dev)
-        out = self.torch.empty(self.world * len(buf), dtype=t.dtype, device=self.dev)
-        self.dist.all_gather_into_tensor(out, t, group=self.group)
-        allb = out.cpu().numpy().reshape(self.world, len(buf))  # one device-to-host copy
+        buf[len(header) + local.size:] = 0
+        if self.dev.type == "cuda":
+            d_in[:n].copy_(h_in[:n], non_blocking=True)
+            self.dist.all_gather_into_tensor(d_out[:self.world * n], d_in[:n], group=self.group)
+            h_out[:self.world * n].copy_(d_out[:self.world * n], non_blocking=True)
+            self.torch.cuda.current_stream().synchronize()
+        else:
+            self.dist.all_gather_into_tensor(d_out[:self.world * n], d_in[:n], group=self.group)
+        allb = h_out.numpy()[:self.world * n].reshape(self.world, n)
         heads = np.ascontiguousarray(allb[:, :len(header)]).view(np.uint32)
         full = np.empty((per * self.world, k), F)
         for r in range(self.world):

@@ -127,8 +127,9 @@ int fgoicp_set_trim(fgoicp_ctx* ctx, float trim_fraction, uint64_t* inliers);
 int fgoicp_set_stream(fgoicp_ctx* ctx, void* cuda_stream);
 
 /* Test hooks ------------------------------------------------------------------------------- */
-/* Nearest-neighbour engine behind fgoicp_sse / fgoicp_nn / fgoicp_icp: 0 = uniform cell grid in HBM
- * (default), 1 = tiled brute force.  Both are exact and return identical indices. */
+/* Nearest-neighbour engine behind fgoicp_sse / fgoicp_nn / fgoicp_icp: 0 = uniform cell grid in HBM (default; far
+ * queries cull whole blocks of cells through their bounding boxes), 1 = tiled brute force, 2 = cell grid with the
+ * bounding-box culling applied to EVERY query, 3 = cell grid without it.  All are exact and return identical indices. */
 int fgoicp_set_nn_mode(fgoicp_ctx* ctx, int mode);
 /* Dense grid download, x fastest: out[(z*dims[1]+y)*dims[0]+x]  (registration.cu:276-277). */
 int fgoicp_lut_download(fgoicp_ctx* ctx, float* out, size_t out_floats);

@@ -128,7 +128,7 @@ def test_bounds_multi_dev_and_best_ub(small_problem, gpu_ctx):
     assert float(d_best.item()) == float(ub.min())
 
 
-@pytest.mark.parametrize("nn_mode", [0, 1])
+@pytest.mark.parametrize("nn_mode", [0, 1, 2, 3])
 def test_nn_indices_bit_exact(small_problem, gpu_ctx, nn_mode):
     pp = small_problem
     gpu_ctx.set_nn_mode(nn_mode)
@@ -152,7 +152,7 @@ def test_nn_duplicate_points_lowest_index_wins():
     data = base[:257] + np.float32(1e-3)
     ctx = capi.Context(model, data, model.min(0), model.max(0), 0.1, flags=0)
     I = np.eye(3, dtype=np.float32).ravel()
-    for nn_mode in (0, 1):
+    for nn_mode in (0, 1, 2, 3):
         ctx.set_nn_mode(nn_mode)
         for rooted in (False, True):
             for t in (np.zeros(3, np.float32), np.float32([0.7, -0.4, 1.3])):      # near and far queries
@@ -188,7 +188,7 @@ def test_nn_rooted_rule_near_ties():
     ctx = capi.Context(model, data, model.min(0), model.max(0), 0.05, flags=0)
     I = np.eye(3, dtype=np.float32).ravel()
     z = np.zeros(3, np.float32)
-    for nn_mode in (0, 1):
+    for nn_mode in (0, 1, 2, 3):
         ctx.set_nn_mode(nn_mode)
         idx_r, d_r = ctx.nn(I, z, True)
         idx_s, d_s = ctx.nn(I, z, False)

@@ -154,6 +154,25 @@ def test_nn_sse_consistency_full_size(w5):
         assert np.all(np.abs(np.sqrt(d2) - node_d) <= off * 1.001 + 1e-5)
 
 
+def test_far_queries_through_the_coarse_boxes_equal_brute_force(w5):
+    """Poses that throw most of the data cloud far from the model (the queries whose ball covers thousands of cell rows):
+    the cell-grid search with the bounding-box culling of far queries (default), with the culling forced on for every
+    query (2) and switched off (3) all return the brute-force winners, indices and distance bits, under both tie rules."""
+    w, pp, ctx = w5
+    for rotv, t in [((0.5, 0.5, -0.4), (0.9, -0.7, 0.8)), ((-0.2, 0.7, 0.3), (-1.0, 1.0, -1.0)), ((0.1, 0.0, 0.0), (0.3, 0.2, -0.25))]:
+        R, _ = driver.rotation_matrix(*F(rotv))
+        t = F(t)
+        for rooted in (False, True):
+            ctx.set_nn_mode(1)
+            want = ctx.nn(R, t, rooted)
+            for mode in (0, 2, 3):
+                ctx.set_nn_mode(mode)
+                got = ctx.nn(R, t, rooted)
+                assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]), (rotv, rooted, mode)
+            ctx.set_nn_mode(0)
+        assert np.sqrt(want[1]).mean() > 0.1 or rotv == (0.1, 0.0, 0.0)       # the first two poses really are far
+
+
 def test_icp_is_idempotent_at_its_fixed_point(w5):
     _, _, ctx = w5
     I = np.array([1, 0, 0, 0, 1, 0, 0, 0, 1], F)

@@ -102,22 +102,29 @@ k_bounds_multi(LutDev L, const float4* __restrict__ data, int ns,
 // Trimmed bounds (extension): one block per (rotation cube, translation cube) pair.  The per-point terms of the
 // pair -- the same ub_i / lb_i the other kernels add up -- are kept in shared memory (2 x ns floats), and each of
 // the two sums runs over the K smallest terms only (trim.cuh).  Unused slots (negative span) are skipped.
+// Clouds whose 2 x ns floats do not fit shared memory (ns > 25,600) keep the terms in a per-block slice of a global
+// scratch buffer instead (GLOBAL = 1: the blocks are persistent and walk the pairs, so the scratch is grid x 8 ns bytes;
+// the select's five passes over the terms are L2 hits).
 #define BT_THREADS 256
-template <int SAMPLER>
+template <int SAMPLER, int GLOBAL>
 __global__ void __launch_bounds__(BT_THREADS)
 k_bounds_trim(LutDev L, const float4* __restrict__ data, int ns,
               const float4* __restrict__ rot, const float* __restrict__ Rmats, int fix_rot,
-              const float4* __restrict__ tcubes, int T, unsigned int K,
-              float* __restrict__ lb, float* __restrict__ ub, unsigned int* __restrict__ best_ub_bits)
+              const float4* __restrict__ tcubes, int T, int n_pairs, unsigned int K,
+              float* __restrict__ lb, float* __restrict__ ub, unsigned int* __restrict__ best_ub_bits, float* gscratch)
 {
-    extern __shared__ float sv[];                 // [2][ns]: ub_i, lb_i
+    extern __shared__ float sv_shared[];          // [2][ns]: ub_i, lb_i (GLOBAL = 0)
+    float* sv = GLOBAL ? gscratch + (size_t)blockIdx.x * 2 * (size_t)ns : sv_shared;
     __shared__ float sR[9];
     __shared__ float s_sin;
     __shared__ unsigned int s_hist[256], s_state[2];
     __shared__ double s_w[32];
-    const int pair = blockIdx.x, r = pair / T;
+    for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x)
+    {
+    const int r = pair / T;
     const float4 t = tcubes[pair];
-    if (t.w < 0.0f) return;
+    if (t.w < 0.0f) continue;
+    __syncthreads();                              // the previous pair's terms and rotation are no longer read
     if (threadIdx.x == 0)
     {
         float4 rc = rot[r];
@@ -169,6 +176,7 @@ k_bounds_trim(LutDev L, const float4* __restrict__ data, int ns,
         float fu = (float)tu, fl = (float)tl;
         ub[pair] = fu; lb[pair] = fl;
         if (best_ub_bits) atomicMin(best_ub_bits, __float_as_uint(fu));
+    }
     }
 }
 
@@ -229,15 +237,36 @@ static int run_bounds(fgoicp_ctx* c, const BoundsLaunch& b)
     {
         // trimmed registration: every pair sums its K smallest terms (one block per pair)
         size_t smem = sizeof(float) * 2 * c->ns;
-        if (smem > 200 * 1024) { fg::set_error("trimming keeps 2 x ns floats in shared memory: at most 25,600 data points"); return FGOICP_ERR_ARG; }
+        const bool global_terms = smem > 200 * 1024 || getenv("FGOICP_TRIM_GLOBAL") != nullptr;   // ns > 25,600: terms in HBM / L2
         unsigned int* d_bits = (unsigned int*)b.d_best_ub;
         if (d_bits) k_set_u32<<<1, 1, 0, c->stream>>>(d_bits, 0x7f800000u);
-        dim3 grid((unsigned)(b.Rn * b.T));
+        const int n_pairs = b.Rn * b.T;
+        dim3 grid((unsigned)n_pairs);
+        float* d_terms = nullptr;
+        if (global_terms)
+        {
+            grid = dim3((unsigned)std::min(n_pairs, 4 * c->sm_count));
+            if (c->trim_bytes < (size_t)grid.x * smem)
+            {
+                FG_CUDA(cudaStreamSynchronize(c->stream));
+                cudaFree(c->d_trim); c->d_trim = nullptr; c->trim_bytes = 0;
+                FG_CUDA(cudaMalloc(&c->d_trim, (size_t)4 * c->sm_count * smem));
+                c->trim_bytes = (size_t)4 * c->sm_count * smem;
+            }
+            d_terms = (float*)c->d_trim;
+            smem = 0;
+        }
 #define FG_LAUNCH_TRIM(SMP)                                                                                              \
         do {                                                                                                             \
-            FG_CUDA(cudaFuncSetAttribute(k_bounds_trim<SMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
-            k_bounds_trim<SMP><<<grid, BT_THREADS, smem, c->stream>>>(c->lut, c->d_data, (int)c->ns, b.d_rot, b.d_Rmats, \
-                b.fix_rot, b.d_tc, b.T, (unsigned int)c->trim_k, b.d_lb, b.d_ub, d_bits);                                \
+            if (global_terms)                                                                                            \
+                k_bounds_trim<SMP, 1><<<grid, BT_THREADS, 0, c->stream>>>(c->lut, c->d_data, (int)c->ns, b.d_rot, b.d_Rmats, \
+                    b.fix_rot, b.d_tc, b.T, n_pairs, (unsigned int)c->trim_k, b.d_lb, b.d_ub, d_bits, d_terms);          \
+            else                                                                                                         \
+            {                                                                                                            \
+                FG_CUDA(cudaFuncSetAttribute(k_bounds_trim<SMP, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+                k_bounds_trim<SMP, 0><<<grid, BT_THREADS, smem, c->stream>>>(c->lut, c->d_data, (int)c->ns, b.d_rot, b.d_Rmats, \
+                    b.fix_rot, b.d_tc, b.T, n_pairs, (unsigned int)c->trim_k, b.d_lb, b.d_ub, d_bits, nullptr);          \
+            }                                                                                                            \
         } while (0)
         switch (c->sampler)
         {

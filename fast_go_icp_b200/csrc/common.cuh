@@ -157,6 +157,8 @@ struct fgoicp_ctx
     // trimmed registration (extension): 0 = off (the reference's behaviour), else the number of data points whose
     // residuals enter every sum (the smallest ones)
     size_t trim_k = 0;
+    void* d_trim = nullptr;                   // per-block term slices of the trimmed bound kernel when 2 x ns floats exceed shared memory
+    size_t trim_bytes = 0;
     unsigned char* d_inl = nullptr;           // ICP inlier flags [icp_capacity][ns]
     void* d_icp_part = nullptr;               // Procrustes partial sums + arrival counters (nn_icp.cu)
 

@@ -759,7 +759,7 @@ extern "C" int fgoicp_ctx_destroy(fgoicp_ctx* c)
     if (c->arr) cudaFreeArray(c->arr);
     cudaFree(c->d_model); cudaFree(c->d_data); cudaFree(c->d_data_orig); cudaFree(c->d_grid); cudaFree(c->d_packed);
     cudaFree(c->d_scratch); cudaFree(c->d_work); cudaFree(c->d_nnkey); cudaFree(c->d_icp); cudaFree(c->d_inl); cudaFree(c->d_icp_part); cudaFree(c->d_icp_jobs); cudaFree(c->d_nnmemo); cudaFree(c->d_icp_loop);
-    cudaFree(c->d_cell_start); cudaFree(c->d_cell_P); cudaFree(c->d_cell_M); cudaFree(c->d_coarse); cudaFree(c->d_phase); cudaFree(c->d_rounds);
+    cudaFree(c->d_cell_start); cudaFree(c->d_cell_P); cudaFree(c->d_cell_M); cudaFree(c->d_coarse); cudaFree(c->d_trim); cudaFree(c->d_phase); cudaFree(c->d_rounds);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);

@@ -119,8 +119,9 @@ int fgoicp_set_sampler(fgoicp_ctx* ctx, int sampler);
  * fgoicp/fgoicp.hpp:73): with trim_fraction rho > 0 every sum over the data points -- per-cube upper and lower
  * bounds, the exact SSE, the centroids and cross-covariance of the ICP -- runs over the
  * K = ns - floor(ns * rho) points with the smallest residual only.  rho = 0 (default) is the reference's behaviour.
- * *inliers (optional) receives K.  Affects every later call on the context; bounds then need 8 * ns bytes of shared
- * memory per block (ns <= 25,600) and the inner searches run round-synchronously. */
+ * *inliers (optional) receives K.  Affects every later call on the context; the bound kernel then keeps the 2 * ns
+ * per-point terms of a cube in shared memory (ns <= 25,600) or, for larger clouds, in an L2-resident scratch slice per
+ * thread block, and the inner searches run round-synchronously. */
 int fgoicp_set_trim(fgoicp_ctx* ctx, float trim_fraction, uint64_t* inliers);
 /* CUDA stream (cudaStream_t passed as void*) every later call on this context enqueues on;
  * NULL selects the context's own stream.  Lets a host framework time calls with its own events. */

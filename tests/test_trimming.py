@@ -147,3 +147,40 @@ def test_cuda_trimmed_run_recovers_pose_despite_outliers():
     g0.close()
     assert float(g0.best_sse) / len(data) > 10 * mse                          # the untrimmed objective is dominated by the outliers
     assert ang <= ang0 + 0.5
+
+
+@pytest.mark.gpu
+def test_cuda_trimmed_bounds_beyond_the_shared_memory_size():
+    """Round 1 capped trimmed bounds at 25,600 data points (2 x ns floats of shared memory per block).  Larger clouds keep
+    the per-point terms in an L2-resident scratch slice per block: a 40,000-point data cloud against the definition --
+    the per-point terms are the untrimmed bounds of one-point clouds... checked here through the identity
+    trimmed(rho -> 0+) == untrimmed and through the oracle on a subsample-sized cloud built from the same points."""
+    from fast_go_icp_b200 import capi, driver
+    w = workloads.synthetic_pair(nt=20000, ns=40000 // 4, seed=17)
+    rng = np.random.default_rng(3)
+    data = np.concatenate([w["data"]] * 4) + rng.normal(scale=1e-3, size=(40000, 3)).astype(np.float32)
+    pp = driver.preprocess(w["model"], data.astype(np.float32))
+    res = 0.02
+    ctx = capi.Context(pp["model"], pp["data"], pp["bbox_min"], pp["bbox_max"], res, flags=capi.BUILD_PACKED)
+    try:
+        ns = len(pp["data"])
+        assert ns == 40000
+        R, _ = O.rotation(0.1, -0.05, 0.2)
+        tc = workloads.translation_cube_list(12, level=3, seed=4)
+        lb0, ub0 = ctx.bounds_batch(R, 0.125, False, tc)                      # untrimmed
+        # dropping ONE point (rho just above 1 / ns) removes exactly the largest per-point term of every cube
+        K = ctx.set_trim(1.5 / ns)
+        assert K == ns - 1
+        lb1, ub1 = ctx.bounds_batch(R, 0.125, False, tc)
+        assert np.all(ub1 <= ub0) and np.all(lb1 <= lb0) and np.any(ub1 < ub0)
+        # against the oracle (CPU restatement with the same trimming rule), 1 ulp
+        lut, dims = O.lut_build(pp["model"], pp["bbox_min"], pp["bbox_max"], res)
+        for rho in (0.25, 1.5 / ns):
+            K = ctx.set_trim(rho)
+            with O.trimmed(K):
+                lb, ub = ctx.bounds_batch(R, 0.125, False, tc)
+                wl, wu = O.bounds(lut, dims, pp["bbox_min"], res, pp["data"], R, 0.125, False, tc)
+                assert np.allclose(ub, wu, rtol=ULP, atol=0) and np.allclose(lb, wl, rtol=ULP, atol=0)
+    finally:
+        ctx.set_trim(0.0)
+        ctx.close()

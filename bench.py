@@ -185,6 +185,39 @@ def measure_run(model, data, res, mse, reps, device, world=1, barrier=None, **kw
     return med
 
 
+def cpp_class_run(w, n_dev, reps=3):
+    """icp::FastGoICP through build/fgoicp_harness (tests/cpp/fgoicp_harness.cpp, written like src/main.cpp:46-53) on W5
+    with one context per GPU inside the process.  Returns run() wall ms (median), SSE and counts, or None."""
+    import tempfile
+    exe = os.path.join(ROOT, "build", "fgoicp_harness")
+    if not os.path.exists(exe):
+        return None
+    try:
+        with tempfile.TemporaryDirectory() as d:
+            np.ascontiguousarray(w["model"], np.float32).tofile(os.path.join(d, "model.f32"))
+            np.ascontiguousarray(w["data"], np.float32).tofile(os.path.join(d, "data.f32"))
+            env = dict(os.environ, FGOICP_DEVICES=",".join(str(k) for k in range(n_dev)))
+            for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+                env.pop(k, None)
+            runs = []
+            for _ in range(reps):
+                r = subprocess.run([exe, os.path.join(d, "model.f32"), os.path.join(d, "data.f32"), repr(RES), repr(MSE_THR)],
+                                   capture_output=True, text=True, env=env, timeout=300)
+                if r.returncode != 0:
+                    return {"error": r.stderr[-300:]}
+                v = [float.fromhex(x) for x in [l for l in r.stdout.splitlines() if l.startswith("RESULT")][-1].split()[1:]]
+                runs.append({"bnb_ms": v[15], "ctor_ms": v[14], "sse": v[12], "bound_evals": int(v[16]), "rot_cubes": int(v[17]),
+                             "icp_runs": int(v[18])})
+            runs.sort(key=lambda x: x["bnb_ms"])
+            out = dict(runs[len(runs) // 2])
+            out["bnb_ms_all_runs"] = [x["bnb_ms"] for x in runs]
+            out["devices"] = n_dev
+            out["what"] = "icp::FastGoICP (C++ drop-in class) in ONE process, frontier sharded over %d GPU(s) by host threads" % n_dev
+            return out
+    except Exception as ex:
+        return {"error": str(ex)[:300]}
+
+
 def cpu_baseline_sample(pp, seconds=12.0):
     """Oracle (CPU restatement) bound evaluations per second on a bounded sample of the same workload.
     The dense grid is downloaded from the GPU build (bit-identical to the oracle's own, see tests)."""
@@ -402,6 +435,15 @@ def run_ours(args):
                     repo.append(r)
                 except Exception as ex:          # a missing fixture must not cost the bench line
                     repo.append({"case": name, "error": str(ex)[:200]})
+        # the drop-in C++ class (include/fgoicp/fgoicp.hpp; reference fgoicp.hpp:13-43) on the same W5 clouds, sharding the
+        # frontier over the N GPUs INSIDE one process (FGOICP_DEVICES=0,...,N-1; no torch, no NCCL): rank 0 runs
+        # build/fgoicp_harness while the other ranks wait
+        cpp = None
+        if rank == 0:
+            cpp = cpp_class_run(w, world)
+        barrier()
+        if cpp is not None:
+            bnb["cpp_class"] = cpp
         if rank == 0 and world == 1 and not args.no_cpu:
             g = driver.FastGoICP(w["model"], w["data"], RES, MSE_THR, device=local, flags=capi.BUILD_PACKED)
             lut, dims = g.ctx.lut_download()

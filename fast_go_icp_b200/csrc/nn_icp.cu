@@ -278,6 +278,37 @@ __device__ __forceinline__ unsigned long long fg_nn_scan(const CellGrid& g, cons
     const int cy0 = min(max((int)floorf((ly - U) * inv_h), 0), g.ny - 1);
     const int cy1 = min(max((int)floorf((ly + U) * inv_h), 0), g.ny - 1);
 
+    // one candidate: its distance, and -- only if it lies inside the current ball -- the winner / runner-up bookkeeping
+    auto consider = [&](const float4 m)
+    {
+        const float d = fg_sq3(__fsub_rn(qx, m.x), __fsub_rn(qy, m.y), __fsub_rn(qz, m.z));
+        // outside the current ball: cannot win, and the clearance of the winner memo never looks beyond the ball (every
+        // radius the ball shrinks to stays above the distances that matter below)
+        if (d <= U2)
+        {
+            const int idx = __float_as_int(m.w);
+            if (ROOTED && !(NN_FAST_ROOTED && !exact))
+            {
+                if (d < thr_lo)
+                {
+                    float s = __fsqrt_rn(d);
+                    best = s; best_idx = idx;
+                    thr_lo = fg_sqrt_preimage_lo(s); thr_hi = fg_sqrt_preimage_hi(s);
+                    U2 = fminf(U2, fg_shrink(thr_hi, margin));
+                }
+                else if (d <= thr_hi && idx < best_idx) best_idx = idx;
+            }
+            else
+            {
+                // squared compare that also keeps the runner-up distance (rooted fast path: decides below whether the
+                // rooted rule could pick another index; both: clearance of the winner memo)
+                if (d < best) { second = best; best = d; best_idx = idx; U2 = fminf(U2, fg_shrink(d, margin)); }
+                else if (d == best) { best_idx = min(best_idx, idx); tie = true; }
+                else second = fminf(second, d);
+            }
+        }
+    };
+
     // All rows (y, z) of the cell box [z0, z1] x [y0, y1] that cut the ball, their chords clipped to the cell columns
     // [xlo, xhi]; NN_RPL rows per lane and pass (the two cell-range lookups of all of them are in flight together;
     // measured neutral to slightly negative, see NN_RPL above: the row lookups are not what far queries wait for).
@@ -315,16 +346,32 @@ __device__ __forceinline__ unsigned long long fg_nn_scan(const CellGrid& g, cons
                 }
             }
         }
-        // Candidates of the team's rows, dealt evenly over its lanes.  A far query grazes the surface: the cells its
-        // ball cuts hold hundreds of points, nearly all just outside the ball and owned by a handful of rows; walking
-        // each row's range in its own lane left 4-9 of 32 lanes active (ncu: profiles/nn_grid_w3_r01.md).  Here the
-        // ranges are concatenated (prefix sum over the lanes) and flat position t belongs to the first lane whose
-        // inclusive prefix exceeds t, found by a five-step binary search over shuffles.  Which lane sees which
-        // candidate does not matter: winners merge as a lexicographic minimum over (value, index).
+        // Candidates of the team's rows.  A far query grazes the surface: the cells its ball cuts hold hundreds to
+        // thousands of points, nearly all just outside the ball and owned by a handful of rows; walking each row's range
+        // in its own lane left 4-9 of 32 lanes active (ncu: profiles/nn_grid_w3_r01.md).
+        //   * LONG rows (>= NN_LPQ candidates: where a grazing ball has its points) are walked by the whole team, one
+        //     row at a time, lanes striding the row's contiguous range: nothing per candidate but its load, its distance
+        //     and one compare (round 2: the flat dealing below spent 45 % of the kernel's instructions on finding each
+        //     candidate's row, profiles/nn_scan_r02.md);
+        //   * the SHORT rows that remain are concatenated (prefix sum over the lanes) and dealt evenly: flat position t
+        //     belongs to the first lane whose inclusive prefix exceeds t, found by a five-step binary search over
+        //     shuffles.
+        // Which lane sees which candidate does not matter: winners merge as a lexicographic minimum over (value, index).
 #pragma unroll
         for (int r = 0; r < NN_RPL; ++r)
         {
-            const int cnt = re[r] - rb[r];
+            int cnt = re[r] - rb[r];
+            unsigned int longm = __ballot_sync(team_mask, cnt >= NN_LPQ);
+            if (NN_LPQ != 32) longm = (longm & team_mask) >> ((threadIdx.x & 31) & ~(NN_LPQ - 1));
+            while (longm)
+            {
+                const int j = __ffs(longm) - 1;
+                longm &= longm - 1;
+                const int b0 = __shfl_sync(team_mask, rb[r], j, NN_LPQ);
+                const int n0 = __shfl_sync(team_mask, cnt, j, NN_LPQ);
+                for (int k = lane; k < n0; k += NN_LPQ) consider(__ldg(g.pts + b0 + k));
+            }
+            if (cnt >= NN_LPQ) cnt = 0;
             int incl = cnt;
 #pragma unroll
             for (int o = 1; o < NN_LPQ; o <<= 1)
@@ -346,36 +393,7 @@ __device__ __forceinline__ unsigned long long fg_nn_scan(const CellGrid& g, cons
                 }
                 const int ob = __shfl_sync(team_mask, rb[r], owner, NN_LPQ);
                 const int oe = __shfl_sync(team_mask, excl, owner, NN_LPQ);
-                if (tt < total)
-                {
-                    const float4 m = __ldg(g.pts + ob + (tt - oe));
-                    const float d = fg_sq3(__fsub_rn(qx, m.x), __fsub_rn(qy, m.y), __fsub_rn(qz, m.z));
-                    // outside the current ball: cannot win, and the clearance of the winner memo never looks beyond
-                    // the ball (every radius the ball shrinks to stays above the distances that matter below)
-                    if (d <= U2)
-                    {
-                    const int idx = __float_as_int(m.w);
-                    if (ROOTED && !(NN_FAST_ROOTED && !exact))
-                    {
-                        if (d < thr_lo)
-                        {
-                            float s = __fsqrt_rn(d);
-                            best = s; best_idx = idx;
-                            thr_lo = fg_sqrt_preimage_lo(s); thr_hi = fg_sqrt_preimage_hi(s);
-                            U2 = fminf(U2, fg_shrink(thr_hi, margin));
-                        }
-                        else if (d <= thr_hi && idx < best_idx) best_idx = idx;
-                    }
-                    else
-                    {
-                        // squared compare that also keeps the runner-up distance (rooted fast path: decides below
-                        // whether the rooted rule could pick another index; both: clearance of the winner memo)
-                        if (d < best) { second = best; best = d; best_idx = idx; U2 = fminf(U2, fg_shrink(d, margin)); }
-                        else if (d == best) { best_idx = min(best_idx, idx); tie = true; }
-                        else second = fminf(second, d);
-                    }
-                    }
-                }
+                if (tt < total) consider(__ldg(g.pts + ob + (tt - oe)));
             }
         }
         // share the tightest radius before the next pass
@@ -946,6 +964,12 @@ struct IcpLoopArgs
     float margin; long long guard_max;
 };
 
+// barrier over one group of four warps (128 threads) of the block: named barriers 1.. (0 is __syncthreads)
+__device__ __forceinline__ void fg_group_barrier(int group)
+{
+    asm volatile("bar.sync %0, 128;" :: "r"(group + 1) : "memory");
+}
+
 // winner memo, one thread per query (see k_nn_grid): true = the previous winner provably still wins, key rewritten
 template <int ROOTED>
 __device__ __forceinline__ bool fg_memo_hit(float qx, float qy, float qz, const float4 mm, unsigned long long old_key,
@@ -988,8 +1012,8 @@ k_icp_loop(IcpLoopArgs a)
     const int items = S * ns;
     __shared__ double s_out[16];
     __shared__ float s_ab[6];
-    __shared__ unsigned int s_chunk;
-    constexpr int ICPL_MISS_CHUNK = (ICPL_THREADS / 32) * 4;      // misses per block and fetch: four per warp
+    __shared__ unsigned int s_chunk[ICPL_THREADS / 128];          // first miss of the four a group of four warps works on
+    const int grp = tid >> 7;
 
     // first jobs of the batch: slot k runs job k (k_icp_assign)
     if (gtid < S)
@@ -1047,21 +1071,22 @@ k_icp_loop(IcpLoopArgs a)
 
         // ---- S2: exact rooted search of the misses, one warp per query, dealt dynamically in small runs
         {
-            // Misses are dealt to BLOCKS in chunks of consecutive list entries, and inside a chunk to the block's warps
-            // round-robin: neighbouring queries (the data cloud is in Morton order) are then searched at the same time on
-            // the same SM and share the cell rows and candidate points they pull through its L1 -- the locality a
-            // one-warp-per-query launch gets for free.  (Handing each warp its own run of consecutive misses measured
-            // 1.6x slower on the dragon pair: 32 unrelated neighbourhoods per SM thrash the L1.)
+            // Misses are dealt to GROUPS OF FOUR WARPS, four consecutive list entries at a time (one each): neighbouring
+            // queries (the data cloud is in Morton order) are searched at the same time on the same SM and share the cell
+            // rows and candidate points they pull through its L1 -- the locality and the granularity of a launch with one
+            // warp per query and four warps per block.  A group synchronises on its own named barrier, never the block:
+            // scans differ 100x in length, and a barrier over 16 warps per chunk (or a run of consecutive misses per
+            // warp: 32 unrelated neighbourhoods per SM thrash the L1) measured 1.3-1.6x slower on the dragon pair.
             const unsigned int n_miss = *(volatile unsigned int*)&a.ctl->n_miss_a;
             while (true)
             {
-                __syncthreads();
-                if (tid == 0) s_chunk = atomicAdd(&a.ctl->next_a, (unsigned int)ICPL_MISS_CHUNK);
-                __syncthreads();
-                const unsigned int m0 = s_chunk;
+                fg_group_barrier(grp);
+                if ((tid & 127) == 0) s_chunk[grp] = atomicAdd(&a.ctl->next_a, 4u);
+                fg_group_barrier(grp);
+                const unsigned int m0 = s_chunk[grp];
                 if (m0 >= n_miss) break;
-                const unsigned int m1 = min(n_miss, m0 + (unsigned int)ICPL_MISS_CHUNK);
-                for (unsigned int m = m0 + (unsigned int)(tid >> 5); m < m1; m += ICPL_THREADS / 32)
+                const unsigned int m = m0 + (unsigned int)((tid >> 5) & 3);
+                if (m < n_miss)
                 {
                     const unsigned int item = __ldcg(a.miss + m);
                     const size_t o = (size_t)item;
@@ -1193,13 +1218,13 @@ k_icp_loop(IcpLoopArgs a)
             const unsigned int n_miss = *(volatile unsigned int*)&a.ctl->n_miss_b;
             while (true)
             {
-                __syncthreads();
-                if (tid == 0) s_chunk = atomicAdd(&a.ctl->next_b, (unsigned int)ICPL_MISS_CHUNK);
-                __syncthreads();
-                const unsigned int m0 = s_chunk;
+                fg_group_barrier(grp);
+                if ((tid & 127) == 0) s_chunk[grp] = atomicAdd(&a.ctl->next_b, 4u);
+                fg_group_barrier(grp);
+                const unsigned int m0 = s_chunk[grp];
                 if (m0 >= n_miss) break;
-                const unsigned int m1 = min(n_miss, m0 + (unsigned int)ICPL_MISS_CHUNK);
-                for (unsigned int m = m0 + (unsigned int)(tid >> 5); m < m1; m += ICPL_THREADS / 32)
+                const unsigned int m = m0 + (unsigned int)((tid >> 5) & 3);
+                if (m < n_miss)
                 {
                     const unsigned int item = __ldcg(a.miss + m);
                     const int slot = (int)(item / (unsigned int)ns), i = (int)(item - (unsigned int)slot * (unsigned int)ns);

@@ -745,6 +745,9 @@ __global__ void k_icp_prepare(const float4* __restrict__ data, float4* work_base
     keys_base[(size_t)blockIdx.y * ns + i] = 0xffffffffffffffffull;
 }
 
+__device__ __forceinline__ void fg_icp_publish(IcpInst* in, const float* __restrict__ jobs, IcpResult* __restrict__ results,
+                                               IcpQueue* q, int max_iter, float thr);
+
 // End of every loop body: loop head of the next iteration; a slot whose refinement has ended publishes the result
 // and takes the next pending job.
 __device__ __forceinline__ void fg_icp_next_job(IcpInst* in, const float* __restrict__ jobs, IcpResult* __restrict__ results,
@@ -753,6 +756,15 @@ __device__ __forceinline__ void fg_icp_next_job(IcpInst* in, const float* __rest
     IcpState* st = &in->st;
     in->fresh = 0;
     if (!st->done) fg_icp_loop_head(st);
+    fg_icp_publish(in, jobs, results, q, max_iter, thr);
+}
+
+// a slot whose refinement has ended publishes its result and takes the next pending job (repeatedly, should a job end
+// at its first loop head: max_iter == 0)
+__device__ __forceinline__ void fg_icp_publish(IcpInst* in, const float* __restrict__ jobs, IcpResult* __restrict__ results,
+                                               IcpQueue* q, int max_iter, float thr)
+{
+    IcpState* st = &in->st;
     while (st->done && in->job >= 0)
     {
         IcpResult* r = results + in->job;
@@ -841,10 +853,8 @@ k_icp_centroids(const float4* __restrict__ work_base, const unsigned long long* 
 
 // closest rotation of the summed cross-covariance, increment and composed pose (icp3d.cu:164-172, 101-102);
 // one thread per instance
-__device__ __noinline__ void fg_icp_pose_update(IcpState* st, const double* sums9)
+__device__ __noinline__ void fg_icp_pose_update(IcpState* st, const double* sums9, const float* ab, const float* bb)
 {
-    const float ab[3] = { st->abar[0], st->abar[1], st->abar[2] };
-    const float bb[3] = { st->bbar[0], st->bbar[1], st->bbar[2] };
     float ABt[9], Rd[9], td[3], Rn[9], tn[3];
     for (int k = 0; k < 9; ++k) ABt[k] = (float)sums9[k];
     fg_closest_rotation(ABt, Rd);
@@ -900,7 +910,7 @@ k_icp_procrustes(const float4* __restrict__ work_base, const unsigned long long*
                 v[c * 3 + r] += (double)__fmul_rn(a[r], b[c]);
     }
     if (!fg_grid_sum<9>(v, part_base + (size_t)inst * ICP_NB * ICP_PART, counters + 2 * inst + 1, s_out)) return;
-    if (threadIdx.x == 0) fg_icp_pose_update(st, s_out);
+    if (threadIdx.x == 0) fg_icp_pose_update(st, s_out, ab, bb);
 }
 
 // ---- the whole ICP loop in ONE persistent cooperative kernel ---------------------------------------------------
@@ -960,7 +970,7 @@ struct IcpLoopArgs
     const float4* data; const float4* model; float4* work; unsigned long long* keys; float4* memo;
     char* inst; int ns, S;
     const float* jobs; IcpResult* results; IcpQueue* q; int max_iter; float thr;
-    double* part; unsigned int* miss; IcpLoopCtl* ctl;
+    double* part; unsigned int* miss; IcpLoopCtl* ctl; unsigned int* arrive;   // arrive: [S][2] arrival counters (cross-covariance, SSE)
     float margin; long long guard_max;
 };
 
@@ -1012,6 +1022,7 @@ k_icp_loop(IcpLoopArgs a)
     const int items = S * ns;
     __shared__ double s_out[16];
     __shared__ float s_ab[6];
+    __shared__ int s_last;
     __shared__ unsigned int s_chunk[ICPL_THREADS / 128];          // first miss of the four a group of four warps works on
     const int grp = tid >> 7;
 
@@ -1021,6 +1032,7 @@ k_icp_loop(IcpLoopArgs a)
         IcpInst* in = fg_inst(a.inst, gtid);
         fg_icp_seed(in, a.jobs + 12 * gtid, gtid, a.max_iter, a.thr);
         fg_icp_loop_head(&in->st);                               // loop head of iteration 1
+        fg_icp_publish(in, a.jobs, a.results, a.q, a.max_iter, a.thr);   // (ends at once when max_iter == 0)
     }
 
     for (long long it = 0;; ++it)
@@ -1161,26 +1173,31 @@ k_icp_loop(IcpLoopArgs a)
             }
             fg_block_sum<9>(v, s_out);
             if (tid < 9) a.part[(size_t)it2 * ICPL_PART + 8 + tid] = s_out[tid];
+            // ---- S5, by whichever block finishes the slot's partials LAST (no grid barrier in between): fold in chunk
+            // order, closest rotation and pose update in one thread (icp3d.cu:164-172, 101-102)
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) s_last = atomicAdd(a.arrive + 2 * slot, 1u) == (unsigned int)(NC - 1);
+            __syncthreads();
+            if (s_last)
+            {
+                __threadfence();
+                if (tid < 9)
+                {
+                    double acc = 0.0;
+                    for (int q = 0; q < NC; ++q) acc += __ldcg(a.part + ((size_t)slot * NC + q) * ICPL_PART + 8 + tid);
+                    s_out[tid] = acc;
+                }
+                __syncthreads();
+                if (tid == 0)
+                {
+                    fg_icp_pose_update(st, s_out, ab, bb);           // ab, bb: folded by this block from the same partials
+                    a.arrive[2 * slot] = 0;
+                }
+            }
             __syncthreads();
         }
         grid.sync(); ICPL_STAGE(4);
-
-        // ---- S5: closest rotation and pose update, one thread per slot (icp3d.cu:164-172, 101-102)
-        for (int slot = blockIdx.x; slot < S; slot += gridDim.x)
-        {
-            IcpState* st = &fg_inst(a.inst, slot)->st;
-            if (st->done) continue;
-            if (tid < 9)
-            {
-                double acc = 0.0;
-                for (int q = 0; q < NC; ++q) acc += __ldcg(a.part + ((size_t)slot * NC + q) * ICPL_PART + 8 + tid);
-                s_out[tid] = acc;
-            }
-            __syncthreads();
-            if (tid == 0) fg_icp_pose_update(st, s_out);
-            __syncthreads();
-        }
-        grid.sync(); ICPL_STAGE(5);
 
         // ---- S6: W = Rd * W + td (icp3d.cu:100); query of the SSE search = R * data + t (icp3d.cu:103); memo test
         for (int base = gtid - lane; base < items; base += gthreads)
@@ -1262,24 +1279,26 @@ k_icp_loop(IcpLoopArgs a)
             for (int i = c * ICPL_CHUNK + tid; i < i1; i += ICPL_THREADS)
                 v[0] += (double)__uint_as_float((unsigned int)(__ldcg(a.keys + (size_t)slot * ns + i) >> 32));
             fg_block_sum<1>(v, s_out);
-            if (tid == 0) a.part[(size_t)it2 * ICPL_PART + 24] = s_out[0];
+            if (tid == 0)
+            {
+                a.part[(size_t)it2 * ICPL_PART + 24] = s_out[0];
+                // ---- S9, by the block that finishes the slot's partials last: SSE in chunk order, loop head of the next
+                // iteration, publish / next job (k_sse_reduce + k_icp_next)
+                __threadfence();
+                if (atomicAdd(a.arrive + 2 * slot + 1, 1u) == (unsigned int)(NC - 1))
+                {
+                    __threadfence();
+                    IcpInst* in = fg_inst(a.inst, slot);
+                    double acc = 0.0;
+                    for (int q = 0; q < NC; ++q) acc += __ldcg(a.part + ((size_t)slot * NC + q) * ICPL_PART + 24);
+                    in->st.sse = (float)acc;
+                    a.arrive[2 * slot + 1] = 0;
+                    fg_icp_next_job(in, a.jobs, a.results, a.q, a.max_iter, a.thr);
+                }
+            }
             __syncthreads();
         }
-        grid.sync(); ICPL_STAGE(8);
-
-        // ---- S9: SSE, loop head of the next iteration, publish / next job (k_sse_reduce + k_icp_next)
-        for (int slot = blockIdx.x * ICPL_THREADS + tid; slot < S; slot += gthreads)
-        {
-            IcpInst* in = fg_inst(a.inst, slot);
-            IcpState* st = &in->st;
-            if (!st->done)
-            {
-                double acc = 0.0;
-                for (int q = 0; q < NC; ++q) acc += __ldcg(a.part + ((size_t)slot * NC + q) * ICPL_PART + 24);
-                st->sse = (float)acc;
-            }
-            fg_icp_next_job(in, a.jobs, a.results, a.q, a.max_iter, a.thr);
-        }
+        // slots that were idle in this trip (no job left) need nothing: their state does not change any more
     }
 }
 #undef ICPL_STAGE
@@ -1291,7 +1310,8 @@ static size_t icp_loop_part_bytes(const fgoicp_ctx* c, int n)
     const size_t nc = (c->ns + ICPL_CHUNK - 1) / ICPL_CHUNK;
     return sizeof(double) * ICPL_PART * nc * (size_t)n;
 }
-static size_t icp_loop_bytes(const fgoicp_ctx* c, int n) { return 256 + icp_loop_part_bytes(c, n) + sizeof(unsigned int) * c->ns * (size_t)n; }
+#define ICPL_HEAD 4096                  // control block (first 1 KB) + arrival counters [slots][2]
+static size_t icp_loop_bytes(const fgoicp_ctx* c, int n) { return ICPL_HEAD + icp_loop_part_bytes(c, n) + sizeof(unsigned int) * c->ns * (size_t)n; }
 
 // per-context ICP buffers sized for `n` concurrent instances
 int fg_ensure_icp_capacity(fgoicp_ctx* c, int n)
@@ -1528,11 +1548,12 @@ int fg_icp_run_batch(fgoicp_ctx* c, const float* R0s, const float* t0s, int n, i
         a.inst = inst; a.ns = ns; a.S = S;
         a.jobs = d_seeds; a.results = d_res; a.q = d_q; a.max_iter = max_iter; a.thr = thr;
         a.ctl = (IcpLoopCtl*)c->d_icp_loop;
-        a.part = (double*)((char*)c->d_icp_loop + 256);
-        a.miss = (unsigned int*)((char*)c->d_icp_loop + 256 + icp_loop_part_bytes(c, c->icp_capacity));
+        a.arrive = (unsigned int*)((char*)c->d_icp_loop + 1024);
+        a.part = (double*)((char*)c->d_icp_loop + ICPL_HEAD);
+        a.miss = (unsigned int*)((char*)c->d_icp_loop + ICPL_HEAD + icp_loop_part_bytes(c, c->icp_capacity));
         a.margin = getenv("FGOICP_NN_NO_WARM") ? 0.0f : std::max(0.0f, margin_cfg);
         a.guard_max = guard_max;
-        FG_CUDA(cudaMemsetAsync(a.ctl, 0, sizeof(IcpLoopCtl), c->stream));
+        FG_CUDA(cudaMemsetAsync(a.ctl, 0, ICPL_HEAD, c->stream));
         // no more blocks than there is work for: a barrier costs time per participating block
         // (enough warps that a first pass -- every query a full scan -- hands each warp about four of them)
         const long long want = ((long long)S * ns * 16 + 63) / 64 / (ICPL_THREADS / 32);

@@ -44,7 +44,11 @@ __host__ __device__ inline bool fg_jacobi_pair(double& up0, double& up1, double&
     double alpha = FG_DADD(FG_DADD(FG_DMUL(up0, up0), FG_DMUL(up1, up1)), FG_DMUL(up2, up2));
     double beta = FG_DADD(FG_DADD(FG_DMUL(uq0, uq0), FG_DMUL(uq1, uq1)), FG_DMUL(uq2, uq2));
     double gamma = FG_DADD(FG_DADD(FG_DMUL(up0, uq0), FG_DMUL(up1, uq1)), FG_DMUL(up2, uq2));
-    if (gamma == 0.0 || fabs(gamma) <= FG_DMUL(1e-17, FG_DSQRT(FG_DMUL(alpha, beta)))) return false;
+    // converged when the two columns are orthogonal to within one unit roundoff (2^-52).  Round 1 tested against 1e-17,
+    // which is below what double arithmetic can reach: the sweeps then kept rotating rounding noise until the 60-sweep cap
+    // (38.6 sweeps on average against 4.4; the same float rotation matrix in all but 1 of 1.8e6 elements) -- and this
+    // single thread is what every other block of the persistent ICP kernel waits for.
+    if (gamma == 0.0 || fabs(gamma) <= FG_DMUL(2.220446049250313e-16, FG_DSQRT(FG_DMUL(alpha, beta)))) return false;
     double zeta = FG_DDIV(FG_DSUB(beta, alpha), FG_DMUL(2.0, gamma));
     double t = FG_DDIV(zeta >= 0.0 ? 1.0 : -1.0,
                        FG_DADD(fabs(zeta), FG_DSQRT(FG_DADD(1.0, FG_DMUL(zeta, zeta)))));

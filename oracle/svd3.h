@@ -45,7 +45,8 @@ static inline void orc_svd3(const double A[9], double U[9], double S[3], double 
                 double alpha = u[p][0] * u[p][0] + u[p][1] * u[p][1] + u[p][2] * u[p][2];
                 double beta = u[q][0] * u[q][0] + u[q][1] * u[q][1] + u[q][2] * u[q][2];
                 double gamma = u[p][0] * u[q][0] + u[p][1] * u[q][1] + u[p][2] * u[q][2];
-                if (gamma == 0.0 || fabs(gamma) <= 1e-17 * sqrt(alpha * beta)) continue;
+                /* converged at one unit roundoff (2^-52); same constant as csrc/svd3_device.cuh, whose twin this is */
+                if (gamma == 0.0 || fabs(gamma) <= 2.220446049250313e-16 * sqrt(alpha * beta)) continue;
                 {
                     double zeta = (beta - alpha) / (2.0 * gamma);
                     double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));

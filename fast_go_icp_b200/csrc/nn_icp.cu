@@ -369,7 +369,17 @@ __device__ __forceinline__ unsigned long long fg_nn_scan(const CellGrid& g, cons
                 longm &= longm - 1;
                 const int b0 = __shfl_sync(team_mask, rb[r], j, NN_LPQ);
                 const int n0 = __shfl_sync(team_mask, cnt, j, NN_LPQ);
-                for (int k = lane; k < n0; k += NN_LPQ) consider(__ldg(g.pts + b0 + k));
+                // four candidates per lane in flight: a grazing ball walks thousands of them and a single warp would
+                // otherwise wait out one L1 / L2 round trip per 32 candidates
+                const float4 nowhere = make_float4(1.0e18f, 1.0e18f, 1.0e18f, 0.0f);      // beyond any ball: dropped by `consider`
+                for (int k = lane; k < n0; k += 4 * NN_LPQ)
+                {
+                    const float4 m0 = __ldg(g.pts + b0 + k);
+                    const float4 m1 = k + NN_LPQ < n0 ? __ldg(g.pts + b0 + k + NN_LPQ) : nowhere;
+                    const float4 m2 = k + 2 * NN_LPQ < n0 ? __ldg(g.pts + b0 + k + 2 * NN_LPQ) : nowhere;
+                    const float4 m3 = k + 3 * NN_LPQ < n0 ? __ldg(g.pts + b0 + k + 3 * NN_LPQ) : nowhere;
+                    consider(m0); consider(m1); consider(m2); consider(m3);
+                }
             }
             if (cnt >= NN_LPQ) cnt = 0;
             int incl = cnt;

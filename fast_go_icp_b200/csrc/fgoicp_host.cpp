@@ -11,13 +11,78 @@
 #include <fgoicp_c.h>
 
 #include <chrono>
+#include <condition_variable>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <queue>
 #include <thread>
 
 namespace icp
 {
+    // One long-lived host thread per additional device.  A thread that touches the CUDA runtime for the first time pays
+    // milliseconds for its thread-local state and for binding the device's context, so spawning fresh threads for every
+    // wave of every level (round 1) made two GPUs slower than one: 186 ms against 132 ms for run() on W5.
+    struct DevicePool
+    {
+        struct Worker
+        {
+            std::thread th;
+            std::mutex m;
+            std::condition_variable cv;
+            std::function<void()> task;
+            bool busy = false, stop = false;
+        };
+        std::vector<std::unique_ptr<Worker>> workers;
+
+        explicit DevicePool(size_t n)
+        {
+            for (size_t k = 0; k < n; ++k)
+            {
+                workers.emplace_back(new Worker());
+                Worker* w = workers.back().get();
+                w->th = std::thread([w]()
+                {
+                    std::unique_lock<std::mutex> lk(w->m);
+                    while (true)
+                    {
+                        w->cv.wait(lk, [w]() { return w->stop || (w->busy && w->task); });
+                        if (w->stop) return;
+                        std::function<void()> f;
+                        f.swap(w->task);
+                        lk.unlock();
+                        f();
+                        lk.lock();
+                        w->busy = false;
+                        w->cv.notify_all();
+                    }
+                });
+            }
+        }
+        ~DevicePool()
+        {
+            for (auto& w : workers)
+            {
+                { std::lock_guard<std::mutex> lk(w->m); w->stop = true; }
+                w->cv.notify_all();
+                if (w->th.joinable()) w->th.join();
+            }
+        }
+        void post(size_t k, std::function<void()> f)
+        {
+            Worker* w = workers[k].get();
+            { std::lock_guard<std::mutex> lk(w->m); w->task = std::move(f); w->busy = true; }
+            w->cv.notify_all();
+        }
+        void wait(size_t k)
+        {
+            Worker* w = workers[k].get();
+            std::unique_lock<std::mutex> lk(w->m);
+            w->cv.wait(lk, [w]() { return !w->busy; });
+        }
+        void wait_all() { for (size_t k = 0; k < workers.size(); ++k) wait(k); }
+    };
+
     namespace
     {
         struct ApiError : std::runtime_error
@@ -163,6 +228,7 @@ namespace icp
         }
         try
         {
+        if (K > 1) pool_.reset(new DevicePool(K - 1));
         fgoicp_info info;
         check(fgoicp_ctx_info(ctx_, &info), "fgoicp_ctx_info");
         if (info.dims[0] >= 1024 || info.dims[1] >= 1024 || info.dims[2] >= 1024)
@@ -190,6 +256,7 @@ namespace icp
 
     FastGoICP::~FastGoICP()
     {
+        pool_.reset();                                   // workers first: none may still hold a context
         for (fgoicp_ctx* c : ctxs_) fgoicp_ctx_destroy(c);
     }
 
@@ -233,12 +300,10 @@ namespace icp
                                          &s.best, s.R, s.t, &s.st);
             if (rc != FGOICP_OK) s.error = std::string("fgoicp_so3_level_ub: ") + fgoicp_last_error();
         };
-        {
-            std::vector<std::thread> th;
-            JoinAll guard{ th };
-            for (int k = 1; k < K; ++k) th.emplace_back(work, k);
-            work(0);
-        }
+        // devices 1.. on their own long-lived threads, device 0 on this one; the shards outlive the tasks (wait_all below)
+        for (int k = 1; k < K; ++k) pool_->post(static_cast<size_t>(k - 1), [&work, k]() { work(k); });
+        work(0);
+        pool_->wait_all();
         std::memset(&st, 0, sizeof(st)); st.best_icp_index = -1;
         int winner = -1, winner_index = 0;
         for (int k = 0; k < K; ++k)
@@ -293,12 +358,9 @@ namespace icp
             int rc = fgoicp_so3_level_lb(ctxs_[k], sc[k].data(), nk, best_sse, sse_threshold, sl[k].data(), &ss[k]);
             if (rc != FGOICP_OK) errors[k] = std::string("fgoicp_so3_level_lb: ") + fgoicp_last_error();
         };
-        {
-            std::vector<std::thread> th;
-            JoinAll guard{ th };
-            for (int k = 1; k < K; ++k) th.emplace_back(work, k);
-            work(0);
-        }
+        for (int k = 1; k < K; ++k) pool_->post(static_cast<size_t>(k - 1), [&work, k]() { work(k); });
+        work(0);
+        pool_->wait_all();
         std::memset(&st, 0, sizeof(st));
         for (int k = 0; k < K; ++k)
         {

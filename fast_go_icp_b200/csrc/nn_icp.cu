@@ -222,6 +222,22 @@ __device__ __forceinline__ float fg_shrink(float d2, float margin)
 #ifndef NN_FAST_ROOTED
 #define NN_FAST_ROOTED 1      // 0: always the exact rooted scan (measured: ICP 86 -> 71 ms on W5 with 1)
 #endif
+// barrier over one group of four warps (128 threads) of the block: named barriers 1.. (0 is __syncthreads)
+__device__ __forceinline__ void fg_group_barrier(int group)
+{
+    asm volatile("bar.sync %0, 128;" :: "r"(group + 1) : "memory");
+}
+
+// Cooperative scan of ONE query by the `nparts` warps of a group (persistent ICP kernel, heavy queries): warp `part`
+// takes every nparts-th run of coarse boxes, and the warps merge winner, runner-up and radius through the group's
+// shared-memory slots.  nparts == 1: the plain single-warp scan.
+struct NnCoop
+{
+    int part = 0, nparts = 1, group = 0;
+    unsigned long long* s_key = nullptr;      // [nparts]
+    float* s_f = nullptr;                     // [nparts]
+};
+
 // The exact search of ONE query by one team of NN_LPQ lanes (a whole warp by default): steps 1-3 above.  `prev` is the
 // warm start -- the winner of the previous pass of the ICP loop (0xffffffff: none), taken at a position a rounding error
 // (squared pass -> next rooted pass) or one ICP increment (rooted -> squared pass) away: its distance is an upper bound on
@@ -233,8 +249,30 @@ __device__ __forceinline__ float fg_shrink(float d2, float margin)
 template <int ROOTED>
 __device__ __forceinline__ unsigned long long fg_nn_scan(const CellGrid& g, const LutDev& L, float res, float qx, float qy, float qz,
                                                          unsigned int prev, const float4* __restrict__ model_by_index, float margin,
-                                                         bool want_rho, int lane, unsigned int team_mask, float& rho)
+                                                         bool want_rho, int lane, unsigned int team_mask, float& rho,
+                                                         const NnCoop coop = NnCoop())
 {
+    // minimum over the cooperating warps of a value that is uniform inside each of them (identity when alone)
+    auto coop_min_u64 = [&](unsigned long long v)
+    {
+        if (coop.nparts == 1) return v;
+        if (lane == 0) coop.s_key[coop.part] = v;
+        fg_group_barrier(coop.group);
+        unsigned long long r = coop.s_key[0];
+        for (int p = 1; p < coop.nparts; ++p) { const unsigned long long o = coop.s_key[p]; r = o < r ? o : r; }
+        fg_group_barrier(coop.group);
+        return r;
+    };
+    auto coop_min_f = [&](float v)
+    {
+        if (coop.nparts == 1) return v;
+        if (lane == 0) coop.s_f[coop.part] = v;
+        fg_group_barrier(coop.group);
+        float r = coop.s_f[0];
+        for (int p = 1; p < coop.nparts; ++p) r = fminf(r, coop.s_f[p]);
+        fg_group_barrier(coop.group);
+        return r;
+    };
     // LUT-space position (binning frame) and the nearest grid node
     float lx = qx + L.ox, ly = qy + L.oy, lz = qz + L.oz;
     int nx = min(max(__float2int_rn(lx * L.scale), 0), L.dx - 1);
@@ -421,9 +459,9 @@ __device__ __forceinline__ unsigned long long fg_nn_scan(const CellGrid& g, cons
     // same: every model point lies inside the box of its block, so a point inside the ball makes its block survive
     // (the ball radius carries its usual slack, far above the rounding of the box distance).
     const int n_rows_ball = (cy1 - cy0 + 1) * (cz1 - cz0 + 1);
-    if (g.n_coarse > 0 && n_rows_ball > g.coarse_min_rows + (g.n_coarse >> 3))
+    if (g.n_coarse > 0 && (coop.nparts > 1 || n_rows_ball > g.coarse_min_rows + (g.n_coarse >> 3)))
     {
-        for (int k0 = 0; k0 < g.n_coarse; k0 += NN_LPQ)
+        for (int k0 = coop.part * NN_LPQ; k0 < g.n_coarse; k0 += NN_LPQ * coop.nparts)
         {
             const int k = k0 + lane;
             float lb2 = FG_INF;
@@ -461,6 +499,8 @@ __device__ __forceinline__ unsigned long long fg_nn_scan(const CellGrid& g, cons
         unsigned long long other = __shfl_xor_sync(team_mask, key, o, NN_LPQ);
         key = other < key ? other : key;
     }
+    key = coop_min_u64(key);
+    if (coop.nparts > 1) U2 = coop_min_f(U2);      // every point inside the smallest of the warps' balls was seen by its owner
     if (want_rho && (!ROOTED || !exact) && key != 0xffffffffffffffffull)
     {
         // Clearance: every point other than the winner is either a candidate this scan has seen (runner-up distance
@@ -471,6 +511,7 @@ __device__ __forceinline__ unsigned long long fg_nn_scan(const CellGrid& g, cons
         float other = ((unsigned int)best_idx != win_idx || tie) ? best : second;
 #pragma unroll
         for (int o = NN_LPQ / 2; o > 0; o >>= 1) other = fminf(other, __shfl_xor_sync(team_mask, other, o, NN_LPQ));
+        other = coop_min_f(other);
         const float ds = fminf(sqrtf(other), sqrtf(U2) * 0.9999f);
         rho = 0.5f * (ds - sqrtf(wd2)) - (1e-5f * ds + 1e-7f);
     }
@@ -481,6 +522,7 @@ __device__ __forceinline__ unsigned long long fg_nn_scan(const CellGrid& g, cons
         float cand = best > wbest ? best : second;                 // smallest d2 strictly above the winner's, warp-wide
 #pragma unroll
         for (int o = NN_LPQ / 2; o > 0; o >>= 1) cand = fminf(cand, __shfl_xor_sync(team_mask, cand, o, NN_LPQ));
+        cand = coop_min_f(cand);
         const float s = __fsqrt_rn(wbest);
         if (cand > fg_sqrt_preimage_hi(s))
         {
@@ -490,6 +532,30 @@ __device__ __forceinline__ unsigned long long fg_nn_scan(const CellGrid& g, cons
     }
     }   // exact
     return key;
+}
+
+// Rows of cells the ball of a query would span (the bounding square of its (y, z) projection, as fg_nn_scan sizes it):
+// what the persistent ICP kernel uses to tell the heavy queries -- points near the centre of a closed model, equidistant
+// from most of its surface, whose scan walks a large share of the cloud -- from the rest.
+__device__ __forceinline__ int fg_nn_ball_rows(const CellGrid& g, const LutDev& L, float res, float qx, float qy, float qz,
+                                               unsigned int prev, const float4* __restrict__ model_by_index, float margin)
+{
+    float lx = qx + L.ox, ly = qy + L.oy, lz = qz + L.oz;
+    int nx = min(max(__float2int_rn(lx * L.scale), 0), L.dx - 1);
+    int ny = min(max(__float2int_rn(ly * L.scale), 0), L.dy - 1);
+    int nz = min(max(__float2int_rn(lz * L.scale), 0), L.dz - 1);
+    float Tn = __ldg(L.grid + ((size_t)nz * L.dy + ny) * L.dx + nx);
+    float ex = lx - (float)nx * res, ey = ly - (float)ny * res, ez = lz - (float)nz * res;
+    float U = (sqrtf(Tn) + sqrtf(ex * ex + ey * ey + ez * ez)) * 1.0001f + 1e-6f;
+    if (prev != 0xffffffffu)
+    {
+        float4 m = __ldg(model_by_index + prev);
+        U = fminf(U, sqrtf(fg_sq3(__fsub_rn(qx, m.x), __fsub_rn(qy, m.y), __fsub_rn(qz, m.z))) * 1.0001f + 1e-6f + margin);
+    }
+    const float inv_h = g.inv_h;
+    const int cz0 = min(max((int)floorf((lz - U) * inv_h), 0), g.nz - 1), cz1 = min(max((int)floorf((lz + U) * inv_h), 0), g.nz - 1);
+    const int cy0 = min(max((int)floorf((ly - U) * inv_h), 0), g.ny - 1), cy1 = min(max((int)floorf((ly + U) * inv_h), 0), g.ny - 1);
+    return (cy1 - cy0 + 1) * (cz1 - cz0 + 1);
 }
 
 template <int ROOTED>
@@ -953,6 +1019,7 @@ struct IcpLoopCtl
     int error;                          // 1: iteration guard hit
     unsigned int iterations;            // loop trips (diagnostics)
     unsigned int scans_a, scans_b;      // full scans run (diagnostics: the rest were memo hits)
+    unsigned int heavy, pad;            // scans done cooperatively by a group of four warps
     unsigned long long stage_ns[10];    // time block 0 spent in each stage incl. the barrier that ends it (diagnostics)
 };
 
@@ -982,13 +1049,8 @@ struct IcpLoopArgs
     const float* jobs; IcpResult* results; IcpQueue* q; int max_iter; float thr;
     double* part; unsigned int* miss; IcpLoopCtl* ctl; unsigned int* arrive;   // arrive: [S][2] arrival counters (cross-covariance, SSE)
     float margin; long long guard_max;
+    int heavy_rows;              // a query whose ball spans at least this many rows of cells is scanned by four warps together
 };
-
-// barrier over one group of four warps (128 threads) of the block: named barriers 1.. (0 is __syncthreads)
-__device__ __forceinline__ void fg_group_barrier(int group)
-{
-    asm volatile("bar.sync %0, 128;" :: "r"(group + 1) : "memory");
-}
 
 // winner memo, one thread per query (see k_nn_grid): true = the previous winner provably still wins, key rewritten
 template <int ROOTED>
@@ -1034,6 +1096,10 @@ k_icp_loop(IcpLoopArgs a)
     __shared__ float s_ab[6];
     __shared__ int s_last;
     __shared__ unsigned int s_chunk[ICPL_THREADS / 128];          // first miss of the four a group of four warps works on
+    __shared__ float4 s_hq[ICPL_THREADS / 128][4];                // heavy queries of a group: position, warm-start index bits
+    __shared__ int s_hflag[ICPL_THREADS / 128][4];
+    __shared__ unsigned long long s_ckey[ICPL_THREADS / 128][4];  // cooperative scan: per-warp winners / minima
+    __shared__ float s_cf[ICPL_THREADS / 128][4];
     const int grp = tid >> 7;
 
     // first jobs of the batch: slot k runs job k (k_icp_assign)
@@ -1107,21 +1173,48 @@ k_icp_loop(IcpLoopArgs a)
                 fg_group_barrier(grp);
                 const unsigned int m0 = s_chunk[grp];
                 if (m0 >= n_miss) break;
-                const unsigned int m = m0 + (unsigned int)((tid >> 5) & 3);
+                const int wig = (tid >> 5) & 3;
+                const unsigned int m = m0 + (unsigned int)wig;
+                size_t o = 0;
+                float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+                unsigned int prev = 0xffffffffu;
+                bool heavy = false;
                 if (m < n_miss)
                 {
-                    const unsigned int item = __ldcg(a.miss + m);
-                    const size_t o = (size_t)item;
-                    const float4 w = __ldcg(a.work + o);
-                    const unsigned int prev = (unsigned int)(__ldcg(a.keys + o) & 0xffffffffull);
+                    o = (size_t)__ldcg(a.miss + m);
+                    w = __ldcg(a.work + o);
+                    prev = (unsigned int)(__ldcg(a.keys + o) & 0xffffffffull);
+                    heavy = a.g.n_coarse > 0 && fg_nn_ball_rows(a.g, a.L, a.res, w.x, w.y, w.z, prev, a.model, a.margin) >= a.heavy_rows;
+                    if (!heavy)
+                    {
+                        float rho;
+                        const unsigned long long key = OUTLINE
+                            ? fg_nn_scan_call<1>(&a.g, &a.L, a.res, w.x, w.y, w.z, prev, a.model, a.margin, lane, &rho)
+                            : fg_nn_scan<1>(a.g, a.L, a.res, w.x, w.y, w.z, prev, a.model, a.margin, a.margin > 0.0f, lane, 0xffffffffu, rho);
+                        if (lane == 0)
+                        {
+                            a.keys[o] = key;
+                            if (a.margin > 0.0f) a.memo[o] = make_float4(w.x, w.y, w.z, rho);
+                        }
+                    }
+                }
+                // heavy queries: all four warps of the group scan them together, one after the other
+                if (lane == 0) { s_hq[grp][wig] = make_float4(w.x, w.y, w.z, __uint_as_float(prev)); s_hflag[grp][wig] = heavy ? 1 : 0; }
+                fg_group_barrier(grp);
+                for (int h = 0; h < 4; ++h)
+                {
+                    if (!s_hflag[grp][h]) continue;                               // uniform over the group
+                    const float4 hq = s_hq[grp][h];
+                    NnCoop coop;
+                    coop.part = wig; coop.nparts = 4; coop.group = grp; coop.s_key = s_ckey[grp]; coop.s_f = s_cf[grp];
                     float rho;
-                    const unsigned long long key = OUTLINE
-                        ? fg_nn_scan_call<1>(&a.g, &a.L, a.res, w.x, w.y, w.z, prev, a.model, a.margin, lane, &rho)
-                        : fg_nn_scan<1>(a.g, a.L, a.res, w.x, w.y, w.z, prev, a.model, a.margin, a.margin > 0.0f, lane, 0xffffffffu, rho);
-                    if (lane == 0)
+                    const unsigned long long key = fg_nn_scan<1>(a.g, a.L, a.res, hq.x, hq.y, hq.z, __float_as_uint(hq.w), a.model, a.margin,
+                                                                 a.margin > 0.0f, lane, 0xffffffffu, rho, coop);
+                    if (h == wig && lane == 0)
                     {
                         a.keys[o] = key;
-                        if (a.margin > 0.0f) a.memo[o] = make_float4(w.x, w.y, w.z, rho);
+                        if (a.margin > 0.0f) a.memo[o] = make_float4(hq.x, hq.y, hq.z, rho);
+                        atomicAdd(&a.ctl->heavy, 1u);
                     }
                 }
             }
@@ -1250,28 +1343,55 @@ k_icp_loop(IcpLoopArgs a)
                 fg_group_barrier(grp);
                 const unsigned int m0 = s_chunk[grp];
                 if (m0 >= n_miss) break;
-                const unsigned int m = m0 + (unsigned int)((tid >> 5) & 3);
+                const int wig = (tid >> 5) & 3;
+                const unsigned int m = m0 + (unsigned int)wig;
+                size_t o = 0;
+                float qx = 0.f, qy = 0.f, qz = 0.f;
+                unsigned int prev = 0xffffffffu;
+                bool heavy = false;
                 if (m < n_miss)
                 {
                     const unsigned int item = __ldcg(a.miss + m);
                     const int slot = (int)(item / (unsigned int)ns), i = (int)(item - (unsigned int)slot * (unsigned int)ns);
-                    const size_t o = (size_t)item;
+                    o = (size_t)item;
                     const IcpState* st = &fg_inst(a.inst, slot)->st;
                     float R[9];
 #pragma unroll
                     for (int k = 0; k < 9; ++k) R[k] = st->R[k];
                     const float4 p = a.data[i];
                     const float3 rp = fg_rotate(R, p.x, p.y, p.z);
-                    const float qx = __fadd_rn(rp.x, st->t[0]), qy = __fadd_rn(rp.y, st->t[1]), qz = __fadd_rn(rp.z, st->t[2]);
-                    const unsigned int prev = (unsigned int)(__ldcg(a.keys + o) & 0xffffffffull);
+                    qx = __fadd_rn(rp.x, st->t[0]); qy = __fadd_rn(rp.y, st->t[1]); qz = __fadd_rn(rp.z, st->t[2]);
+                    prev = (unsigned int)(__ldcg(a.keys + o) & 0xffffffffull);
+                    heavy = a.g.n_coarse > 0 && fg_nn_ball_rows(a.g, a.L, a.res, qx, qy, qz, prev, a.model, a.margin) >= a.heavy_rows;
+                    if (!heavy)
+                    {
+                        float rho;
+                        const unsigned long long key = OUTLINE
+                            ? fg_nn_scan_call<0>(&a.g, &a.L, a.res, qx, qy, qz, prev, a.model, a.margin, lane, &rho)
+                            : fg_nn_scan<0>(a.g, a.L, a.res, qx, qy, qz, prev, a.model, a.margin, a.margin > 0.0f, lane, 0xffffffffu, rho);
+                        if (lane == 0)
+                        {
+                            a.keys[o] = key;
+                            if (a.margin > 0.0f) a.memo[o] = make_float4(qx, qy, qz, rho);
+                        }
+                    }
+                }
+                if (lane == 0) { s_hq[grp][wig] = make_float4(qx, qy, qz, __uint_as_float(prev)); s_hflag[grp][wig] = heavy ? 1 : 0; }
+                fg_group_barrier(grp);
+                for (int h = 0; h < 4; ++h)
+                {
+                    if (!s_hflag[grp][h]) continue;                               // uniform over the group
+                    const float4 hq = s_hq[grp][h];
+                    NnCoop coop;
+                    coop.part = wig; coop.nparts = 4; coop.group = grp; coop.s_key = s_ckey[grp]; coop.s_f = s_cf[grp];
                     float rho;
-                    const unsigned long long key = OUTLINE
-                        ? fg_nn_scan_call<0>(&a.g, &a.L, a.res, qx, qy, qz, prev, a.model, a.margin, lane, &rho)
-                        : fg_nn_scan<0>(a.g, a.L, a.res, qx, qy, qz, prev, a.model, a.margin, a.margin > 0.0f, lane, 0xffffffffu, rho);
-                    if (lane == 0)
+                    const unsigned long long key = fg_nn_scan<0>(a.g, a.L, a.res, hq.x, hq.y, hq.z, __float_as_uint(hq.w), a.model, a.margin,
+                                                                 a.margin > 0.0f, lane, 0xffffffffu, rho, coop);
+                    if (h == wig && lane == 0)
                     {
                         a.keys[o] = key;
-                        if (a.margin > 0.0f) a.memo[o] = make_float4(qx, qy, qz, rho);
+                        if (a.margin > 0.0f) a.memo[o] = make_float4(hq.x, hq.y, hq.z, rho);
+                        atomicAdd(&a.ctl->heavy, 1u);
                     }
                 }
             }
@@ -1532,6 +1652,8 @@ int fg_icp_run_batch(fgoicp_ctx* c, const float* R0s, const float* t0s, int n, i
             { "256x5o", (const void*)k_icp_loop<256, 5, 1>, 256, 5 },
             { "256x4", (const void*)k_icp_loop<256, 4, 0>, 256, 4 },
             { "512x1", (const void*)k_icp_loop<512, 1, 0>, 512, 1 },
+            { "384x3", (const void*)k_icp_loop<384, 3, 0>, 384, 3 },
+            { "640x2", (const void*)k_icp_loop<640, 2, 0>, 640, 2 },
         };
         static const int shape_idx = []() {
             const char* e = getenv("FGOICP_ICP_SHAPE");
@@ -1563,6 +1685,8 @@ int fg_icp_run_batch(fgoicp_ctx* c, const float* R0s, const float* t0s, int n, i
         a.miss = (unsigned int*)((char*)c->d_icp_loop + ICPL_HEAD + icp_loop_part_bytes(c, c->icp_capacity));
         a.margin = getenv("FGOICP_NN_NO_WARM") ? 0.0f : std::max(0.0f, margin_cfg);
         a.guard_max = guard_max;
+        static const int heavy_cfg = getenv("FGOICP_NN_HEAVY_ROWS") ? atoi(getenv("FGOICP_NN_HEAVY_ROWS")) : 2500;
+        a.heavy_rows = heavy_cfg > 0 ? heavy_cfg : 0x7fffffff;
         FG_CUDA(cudaMemsetAsync(a.ctl, 0, ICPL_HEAD, c->stream));
         // no more blocks than there is work for: a barrier costs time per participating block
         // (enough warps that a first pass -- every query a full scan -- hands each warp about four of them)
@@ -1579,8 +1703,8 @@ int fg_icp_run_batch(fgoicp_ctx* c, const float* R0s, const float* t0s, int n, i
         results_on_host = all_done;
         if (getenv("FGOICP_ICP_LOG"))
         {
-            fprintf(stderr, "[icp loop %s] jobs %d slots %d grid %d trips %u full scans: rooted %u squared %u | stage us:", shape.name, n, S, grid,
-                    hctl->iterations, hctl->scans_a, hctl->scans_b);
+            fprintf(stderr, "[icp loop %s] jobs %d slots %d grid %d trips %u full scans: rooted %u squared %u (heavy %u) | stage us:", shape.name, n, S, grid,
+                    hctl->iterations, hctl->scans_a, hctl->scans_b, hctl->heavy);
             for (int k = 0; k < 9; ++k) fprintf(stderr, " %.0f", hctl->stage_ns[k] * 1e-3);
             fprintf(stderr, "\n");
         }

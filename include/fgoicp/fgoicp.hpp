@@ -16,6 +16,7 @@
 
 struct fgoicp_ctx;
 struct fgoicp_level_stats;
+namespace icp { struct DevicePool; }
 
 namespace icp
 {
@@ -127,6 +128,7 @@ namespace icp
         Stats stats_;
         fgoicp_ctx* ctx_ = nullptr;            // context of the first device (ICPs of run(), best-first schedule)
         std::vector<fgoicp_ctx*> ctxs_;        // one per device; ctxs_[0] == ctx_
+        std::unique_ptr<DevicePool> pool_;     // one long-lived host thread per additional device (csrc/fgoicp_host.cpp)
 
         void init(float lut_resolution);
         void preprocess_clouds();

@@ -414,6 +414,27 @@ def test_persistent_icp_loop_equals_the_launch_chain(small_problem, gpu_ctx):
 
 
 @pytest.mark.parametrize("which", ["synthetic", "dragon"])
+def test_scan_schedules_of_the_icp_loop_change_no_result(which):
+    """The persistent ICP kernel scans a heavy query with four warps together and everything else with one warp each.
+    Forcing EVERY scan to be cooperative (FGOICP_NN_HEAVY_ROWS=1), none (=0), the launch-chain driver
+    (FGOICP_ICP_MODE=1) and the bounding-box culling switched off (FGOICP_NN_COARSE=0) must give the same SSE, poses and
+    iteration counts as the default, bit for bit."""
+    import json
+    import os
+    import subprocess
+    import sys
+    probe = os.path.join(os.path.dirname(os.path.abspath(__file__)), "icp_probe.py")
+    outs = {}
+    for tag, env in (("default", {}), ("all-coop", {"FGOICP_NN_HEAVY_ROWS": "1"}), ("no-coop", {"FGOICP_NN_HEAVY_ROWS": "0"}),
+                     ("chain", {"FGOICP_ICP_MODE": "1"}), ("no-boxes", {"FGOICP_NN_COARSE": "0"})):
+        r = subprocess.run([sys.executable, probe, which], capture_output=True, text=True, env=dict(os.environ, **env), timeout=300)
+        assert r.returncode == 0, (tag, r.stderr[-2000:])
+        outs[tag] = json.loads([l for l in r.stdout.splitlines() if l.startswith("PROBE ")][-1][6:])
+    for tag in outs:
+        assert outs[tag] == outs["default"], tag
+
+
+@pytest.mark.parametrize("which", ["synthetic", "dragon"])
 def test_winner_memo_changes_no_result(which):
     """The winner memo of the ICP searches (skip the scan when the point moved less than the clearance the last scan
     proved) must not change a single bit: refinements with the memo off (margin 0), at the default margin and at a

@@ -181,7 +181,7 @@ class Context:
         _check(lib().fgoicp_set_bnb_mode(self._h, int(mode)), "fgoicp_set_bnb_mode")
 
     def set_icp_mode(self, mode):
-        """0: persistent loop kernel (default), 1: one launch per stage and iteration (same results)."""
+        """0: automatic (default), 1: one launch per stage and iteration, 2: persistent loop kernel (same results)."""
         _check(lib().fgoicp_set_icp_mode(self._h, int(mode)), "fgoicp_set_icp_mode")
 
     def set_phased(self, on):

@@ -171,7 +171,7 @@ struct fgoicp_ctx
     void* d_icp_jobs = nullptr;               // job queue of a batch of refinements: counters, seed poses, results (nn_icp.cu)
     size_t icp_jobs_bytes = 0;
     void* d_icp_loop = nullptr;               // persistent ICP loop kernel: control block, reduction partials, miss list (nn_icp.cu)
-    int icp_mode = 0;                         // 0: persistent loop kernel (default), 1: launch chain (test hook, trimmed runs)
+    int icp_mode = 0;                         // 0: automatic (loop kernel for batches that fit the slot pool, else launch chain), 1: launch chain, 2: loop kernel
     int icp_loop_grid = 0;                    // co-resident blocks of k_icp_loop on this device (0: not yet queried)
 };
 

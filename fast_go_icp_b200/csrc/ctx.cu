@@ -736,7 +736,7 @@ extern "C" int fgoicp_ctx_create(const float* model_xyz, size_t nt, const float*
     d_P = nullptr;
 #undef FG_TRY
     c->sampler = c->d_packed ? FGOICP_SAMPLER_PACKED : FGOICP_SAMPLER_GRID;
-    if (const char* e = getenv("FGOICP_ICP_MODE")) c->icp_mode = atoi(e) == 1 ? 1 : 0;
+    if (const char* e = getenv("FGOICP_ICP_MODE")) { int m = atoi(e); c->icp_mode = (m >= 0 && m <= 2) ? m : 0; }
     // buffers of the refinements and of the level driver: allocated here, never inside run()
     rc = fg_icp_prealloc(c);
     if (rc) { fgoicp_ctx_destroy(c); return rc; }

@@ -1641,7 +1641,14 @@ int fg_icp_run_batch(fgoicp_ctx* c, const float* R0s, const float* t0s, int n, i
     const long long guard_max = ((long long)(n + S - 1) / S + 1) * ((long long)max_iter + 2) + 8;
     bool all_done = false, results_on_host = false;
     const bool trimmed = c->trim_k > 0 && c->trim_k < c->ns;
-    if (c->icp_mode == 0 && !trimmed && c->nn_mode != 1)
+    // Which driver: the persistent loop kernel (one launch, one synchronisation, nothing for the host to do) for
+    // batches that fit the slot pool -- the latency-bound refinements of the coarse levels and of run()'s first and last
+    // ICP -- and the launch chain for batches that refill their slots many times (hundreds to thousands of refinements on
+    // partial-overlap scans): there the searches are pure throughput, the chain's one-warp-per-query launches run them
+    // ~10 % faster (36 instead of 32 resident warps per SM, no barrier at the end of every stage) and its host polls are
+    // amortised.  Same results either way, bit for bit (tests/test_gpu_parity.py).
+    const bool use_loop = (c->icp_mode == 2 || (c->icp_mode == 0 && n <= S)) && !trimmed && c->nn_mode != 1;
+    if (use_loop)
     {
         // ---- persistent loop kernel: one cooperative launch, one synchronisation for the whole batch
         // block shape of the loop kernel (FGOICP_ICP_SHAPE selects among the instantiations for experiments)
@@ -1685,7 +1692,9 @@ int fg_icp_run_batch(fgoicp_ctx* c, const float* R0s, const float* t0s, int n, i
         a.miss = (unsigned int*)((char*)c->d_icp_loop + ICPL_HEAD + icp_loop_part_bytes(c, c->icp_capacity));
         a.margin = getenv("FGOICP_NN_NO_WARM") ? 0.0f : std::max(0.0f, margin_cfg);
         a.guard_max = guard_max;
-        static const int heavy_cfg = getenv("FGOICP_NN_HEAVY_ROWS") ? atoi(getenv("FGOICP_NN_HEAVY_ROWS")) : 2500;
+        // cooperative scans of heavy queries are OFF by default: measured neutral on W5 / W3 and -10 % on W4 at 2,500 rows
+        // (scans are bound by instruction issue, not by the latency of single heavy ones); FGOICP_NN_HEAVY_ROWS=<n> enables
+        static const int heavy_cfg = getenv("FGOICP_NN_HEAVY_ROWS") ? atoi(getenv("FGOICP_NN_HEAVY_ROWS")) : 0;
         a.heavy_rows = heavy_cfg > 0 ? heavy_cfg : 0x7fffffff;
         FG_CUDA(cudaMemsetAsync(a.ctl, 0, ICPL_HEAD, c->stream));
         // no more blocks than there is work for: a barrier costs time per participating block
@@ -1780,7 +1789,7 @@ int fg_icp_prealloc(fgoicp_ctx* c)
 extern "C" int fgoicp_set_icp_mode(fgoicp_ctx* c, int mode)
 {
     FG_ARG(c, "NULL context");
-    FG_ARG(mode == 0 || mode == 1, "icp mode must be 0 (persistent loop kernel) or 1 (launch chain)");
+    FG_ARG(mode >= 0 && mode <= 2, "icp mode must be 0 (automatic), 1 (launch chain) or 2 (persistent loop kernel)");
     c->icp_mode = mode;
     return FGOICP_OK;
 }

@@ -143,10 +143,13 @@ int fgoicp_set_phased(fgoicp_ctx* ctx, int on);
  * thread-block cluster per search), 1 = same, explicitly, 2 = round-synchronous (all searches advance one
  * iteration per round, bounds of each round through the phase-ordered kernel).  Same results either way. */
 int fgoicp_set_bnb_mode(fgoicp_ctx* ctx, int mode);
-/* Driver of the ICP refinements behind fgoicp_icp / fgoicp_icp_batch / fgoicp_so3_level_ub: 0 = one persistent
- * cooperative kernel per batch (default: the whole loop of icp3d.cu:85-108 on the device, one host synchronisation),
- * 1 = one launch per stage and iteration with a host poll every 8 iterations (also used by trimmed runs).  Same
- * results either way. */
+/* Driver of the ICP refinements behind fgoicp_icp / fgoicp_icp_batch / fgoicp_so3_level_ub:
+ *   2 = one persistent cooperative kernel per batch: the whole loop of icp3d.cu:85-108 on the device, stages separated
+ *       by grid-wide barriers, ONE host synchronisation per batch;
+ *   1 = one launch per stage and iteration with a host poll every 8 iterations (also used by trimmed runs);
+ *   0 = automatic (default): the kernel for batches that fit the pool of instance slots, the launches for batches that
+ *       refill their slots many times (pure throughput; measured ~10 % faster there).
+ * Same results in every mode, bit for bit. */
 int fgoicp_set_icp_mode(fgoicp_ctx* ctx, int mode);
 /* Measurement hook: useful GB/s of independent random gathers of width_bytes (16/32/64/128) over a
  * buffer of `bytes` bytes -- the gather roofline the bound kernels are compared with. */

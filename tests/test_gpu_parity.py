@@ -401,16 +401,17 @@ def test_persistent_icp_loop_equals_the_launch_chain(small_problem, gpu_ctx):
         seeds_t.append(rng.uniform(-0.2, 0.2, 3).astype(np.float32))
     out = {}
     try:
-        for mode in (0, 1):
+        for mode in (2, 1, 0):
             gpu_ctx.set_icp_mode(mode)
             out[mode] = [gpu_ctx.icp_batch(np.array(seeds_R), np.array(seeds_t), 100, thr) for thr in (0.05, 0.005, 0.0005)]
             out[mode].append(tuple(np.asarray(x) for x in gpu_ctx.icp(seeds_R[3], seeds_t[3], 100, 0.005)))
     finally:
         gpu_ctx.set_icp_mode(0)
-    for a, b in zip(out[0], out[1]):
-        for x, y in zip(a, b):
-            assert np.array_equal(x, y)
-    assert out[0][1][3].max() > 10
+    for other in (1, 0):
+        for a, b in zip(out[2], out[other]):
+            for x, y in zip(a, b):
+                assert np.array_equal(x, y)
+    assert out[2][1][3].max() > 10
 
 
 @pytest.mark.parametrize("which", ["synthetic", "dragon"])
@@ -426,7 +427,8 @@ def test_scan_schedules_of_the_icp_loop_change_no_result(which):
     probe = os.path.join(os.path.dirname(os.path.abspath(__file__)), "icp_probe.py")
     outs = {}
     for tag, env in (("default", {}), ("all-coop", {"FGOICP_NN_HEAVY_ROWS": "1"}), ("no-coop", {"FGOICP_NN_HEAVY_ROWS": "0"}),
-                     ("chain", {"FGOICP_ICP_MODE": "1"}), ("no-boxes", {"FGOICP_NN_COARSE": "0"})):
+                     ("chain", {"FGOICP_ICP_MODE": "1"}), ("loop", {"FGOICP_ICP_MODE": "2"}), ("loop-all-coop", {"FGOICP_ICP_MODE": "2", "FGOICP_NN_HEAVY_ROWS": "1"}),
+                     ("no-boxes", {"FGOICP_NN_COARSE": "0"})):
         r = subprocess.run([sys.executable, probe, which], capture_output=True, text=True, env=dict(os.environ, **env), timeout=300)
         assert r.returncode == 0, (tag, r.stderr[-2000:])
         outs[tag] = json.loads([l for l in r.stdout.splitlines() if l.startswith("PROBE ")][-1][6:])

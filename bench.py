@@ -176,6 +176,7 @@ def measure_run(model, data, res, mse, reps, device, world=1, barrier=None, **kw
                      "ms_bnb_ub": st["ms_bnb_ub"], "ms_icp": st["ms_icp"], "ms_bnb_lb": st["ms_bnb_lb"],
                      "ms_first_icp": st.get("ms_first_icp"), "ms_final_icp": st.get("ms_final_icp"),
                      "ms_search_wall": st.get("ms_search_wall"),
+                     "ms_in_abi_calls": st.get("ms_calls"), "ms_in_exchange": st.get("ms_exchange"), "exchanges": st.get("exchanges"),
                      "in_search_evals_per_s_local": st["bound_evals"] / (search_ms * 1e-3) if search_ms > 0 else None,
                      "levels": st["level_log"], "_R": np.asarray(R_out), "_t_out": np.asarray(t_out)})
         g.close()
@@ -196,7 +197,7 @@ def cpp_class_run(w, n_dev, reps=3):
         with tempfile.TemporaryDirectory() as d:
             np.ascontiguousarray(w["model"], np.float32).tofile(os.path.join(d, "model.f32"))
             np.ascontiguousarray(w["data"], np.float32).tofile(os.path.join(d, "data.f32"))
-            env = dict(os.environ, FGOICP_DEVICES=",".join(str(k) for k in range(n_dev)))
+            env = dict(os.environ, FGOICP_DEVICES=",".join(str(k) for k in range(n_dev)), HARNESS_WARMUP="1")
             for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
                 env.pop(k, None)
             runs = []
@@ -212,7 +213,7 @@ def cpp_class_run(w, n_dev, reps=3):
             out = dict(runs[len(runs) // 2])
             out["bnb_ms_all_runs"] = [x["bnb_ms"] for x in runs]
             out["devices"] = n_dev
-            out["what"] = "icp::FastGoICP (C++ drop-in class) in ONE process, frontier sharded over %d GPU(s) by host threads" % n_dev
+            out["what"] = "icp::FastGoICP (C++ drop-in class) in ONE process, frontier sharded over %d GPU(s) by host threads; one small untimed registration first (kernel loading), like the Python arm" % n_dev
             return out
     except Exception as ex:
         return {"error": str(ex)[:300]}
@@ -420,6 +421,14 @@ def run_ours(args):
             mx = ev.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
             bnb["bound_evals_all_ranks"] = float(tot[0].item())
             bnb["in_search_evals_per_s"] = float(tot[0].item()) / (float(mx[1].item()) * 1e-3)
+            # where each rank's wall time went: device time of its searches / refinements, wall time inside the C ABI,
+            # wall time in the exchanges (which includes waiting for the slowest rank of every wave)
+            mine = torch.tensor([bnb["ms_bnb_ub"], bnb["ms_icp"], bnb["ms_bnb_lb"], bnb["ms_in_abi_calls"], bnb["ms_in_exchange"]],
+                                device=dev, dtype=torch.float64)
+            allr = torch.empty(world * 5, device=dev, dtype=torch.float64)
+            dist.all_gather_into_tensor(allr, mine)
+            bnb["per_rank_ms"] = {"columns": ["ms_bnb_ub", "ms_icp", "ms_bnb_lb", "ms_in_abi_calls", "ms_in_exchange"],
+                                  "rows": [[round(float(x), 3) for x in allr[5 * r:5 * r + 5].tolist()] for r in range(world)]}
         else:
             bnb["bound_evals_all_ranks"] = float(bnb["bound_evals_local"])
             bnb["in_search_evals_per_s"] = bnb["in_search_evals_per_s_local"]
@@ -438,10 +447,17 @@ def run_ours(args):
         # the drop-in C++ class (include/fgoicp/fgoicp.hpp; reference fgoicp.hpp:13-43) on the same W5 clouds, sharding the
         # frontier over the N GPUs INSIDE one process (FGOICP_DEVICES=0,...,N-1; no torch, no NCCL): rank 0 runs
         # build/fgoicp_harness while the other ranks wait
+        # (the other ranks wait on a host-side gloo barrier: an NCCL barrier would park a spinning kernel on the very GPUs
+        # the harness is about to use -- measured: 180 ms instead of 91 ms for two devices)
         cpp = None
+        if world > 1:
+            torch.cuda.synchronize()
+            host_group = dist.new_group(backend="gloo")
+            dist.barrier(group=host_group)
         if rank == 0:
             cpp = cpp_class_run(w, world)
-        barrier()
+        if world > 1:
+            dist.barrier(group=host_group)
         if cpp is not None:
             bnb["cpp_class"] = cpp
         if rank == 0 and world == 1 and not args.no_cpu:

@@ -12,6 +12,7 @@
 
 #include <chrono>
 #include <condition_variable>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <functional>
@@ -291,19 +292,30 @@ namespace icp
             std::memcpy(sh[k].R, bR, sizeof(sh[k].R)); std::memcpy(sh[k].t, bT, sizeof(sh[k].t));
             std::memset(&sh[k].st, 0, sizeof(sh[k].st)); sh[k].st.best_icp_index = -1;
         }
+        static const bool log_waves = std::getenv("FGOICP_WAVE_LOG") != nullptr;
+        std::vector<double> t_shard(K, 0.0);
         auto work = [&](int k)
         {
             Shard& s = sh[k];
             const int mk = static_cast<int>(s.ub.size());
             if (mk == 0) return;
+            const double ts = now_ms();
             int rc = fgoicp_so3_level_ub(ctxs_[k], s.cubes.data(), mk, start_best, sse_threshold, s.ub.data(), s.bt.data(),
                                          &s.best, s.R, s.t, &s.st);
+            t_shard[k] = now_ms() - ts;
             if (rc != FGOICP_OK) s.error = std::string("fgoicp_so3_level_ub: ") + fgoicp_last_error();
         };
         // devices 1.. on their own long-lived threads, device 0 on this one; the shards outlive the tasks (wait_all below)
+        const double tw = now_ms();
         for (int k = 1; k < K; ++k) pool_->post(static_cast<size_t>(k - 1), [&work, k]() { work(k); });
         work(0);
         pool_->wait_all();
+        if (log_waves)
+        {
+            std::fprintf(stderr, "[wave ub] m %d wall %.3f ms | per device: call ms (device ub + icp ms):", m, now_ms() - tw);
+            for (int k = 0; k < K; ++k) std::fprintf(stderr, " %.3f (%.3f + %.3f)", t_shard[k], sh[k].st.ms_bnb_ub, sh[k].st.ms_icp);
+            std::fprintf(stderr, "\n");
+        }
         std::memset(&st, 0, sizeof(st)); st.best_icp_index = -1;
         int winner = -1, winner_index = 0;
         for (int k = 0; k < K; ++k)

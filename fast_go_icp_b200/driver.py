@@ -213,7 +213,8 @@ class FastGoICP:
         self.best_t = np.zeros(3, F)
         self.stats = dict(bound_evals=0, rot_cubes=0, icp_runs=0, icp_iters=0, levels=0,
                           ctor_ms=(time.perf_counter() - t0) * 1e3, lut_build_ms=self.ctx.info().build_ms,
-                          ms_bnb_ub=0.0, ms_icp=0.0, ms_bnb_lb=0.0, level_log=[])
+                          ms_bnb_ub=0.0, ms_icp=0.0, ms_bnb_lb=0.0, level_log=[],
+                          ms_calls=0.0, ms_exchange=0.0, exchanges=0)
 
     def close(self):
         self.ctx.close()
@@ -346,8 +347,10 @@ class FastGoICP:
                 if not len(widx):
                     continue
                 my_idx = widx[comm.rank::comm.world]
+                tc0 = time.perf_counter()
                 ub_l, bt_l, e_l, R_l, t_l, st = self.ctx.so3_level_ub(ev[my_idx, :4], self.best_sse, thr,
                                                                      self.best_R, self.best_t)
+                tc1 = time.perf_counter()
                 # ONE exchange per wave: header = (sse bits, global child index, pose of this rank's best ICP), rows =
                 # (ub, best_t) of this rank's cubes.  Global best = MIN over (sse bits, child index): ties -> lowest
                 # child index, which is what a single rank's ascending scan picks.
@@ -360,6 +363,9 @@ class FastGoICP:
                     head[0] = np.array([self.best_sse], F).view(np.uint32)[0]
                     head[1] = np.uint32(0xffffffff)
                 heads, ubt_w = comm.exchange(head, np.concatenate([ub_l[:, None], bt_l], axis=1), len(widx))
+                self.stats["ms_calls"] += (tc1 - tc0) * 1e3
+                self.stats["ms_exchange"] += (time.perf_counter() - tc1) * 1e3
+                self.stats["exchanges"] += 1
                 keys = (heads[:, 0].astype(np.uint64) << np.uint64(32)) | heads[:, 1].astype(np.uint64)
                 win = int(np.argmin(keys))
                 if heads[win, 1] != np.uint32(0xffffffff):
@@ -374,11 +380,16 @@ class FastGoICP:
             if self.skip_dead_lb and F(span / F(2.0)) < F(0.05):
                 # Leaf level: the children of these cubes are never evaluated (fgoicp.cpp:53), so their lower
                 # bounds can only feed the loop's exit test -- the reference computes them anyway (fgoicp.cpp:90);
-                # skipping them changes no output.
-                lb_l, st2 = np.zeros(len(mine), F), capi.LevelStats()
+                # skipping them changes no output (and every rank knows the zeros: nothing to exchange).
+                lb, st2 = np.zeros(n_ev, F), capi.LevelStats()
             else:
+                tc0 = time.perf_counter()
                 lb_l, st2 = self.ctx.so3_level_lb(mine, self.best_sse, thr)
-            lb = comm.gather_rows(lb_l[:, None], n_ev)[:, 0] if n_ev else np.zeros(0, F)
+                tc1 = time.perf_counter()
+                lb = comm.gather_rows(lb_l[:, None], n_ev)[:, 0] if n_ev else np.zeros(0, F)
+                self.stats["ms_calls"] += (tc1 - tc0) * 1e3
+                self.stats["ms_exchange"] += (time.perf_counter() - tc1) * 1e3
+                self.stats["exchanges"] += 1
 
             surv = lb < self.best_sse                                      # fgoicp.cpp:92
             kept = ev[surv].copy()

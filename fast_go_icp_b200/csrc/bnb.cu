@@ -875,22 +875,40 @@ static int bnb_rounds(fgoicp_ctx* c, const float4* d_rot, int Rn, int fix_rot, f
     auto t_prev = std::chrono::steady_clock::now();
     // a search pops at most 4681 cubes, at least one per round
     bool drained = false;
-    for (int round = 0; round < 4700; ++round)
+    // Rounds that cannot use the phase-ordered kernel (trimmed bounds, other samplers) need nothing from the host between
+    // rounds -- finished searches return at once, their slots carry negative spans -- so they are enqueued `burst` at a time
+    // and the host looks at the counters once per burst: 8x fewer synchronisations, i.e. 8x less exposure to the
+    // scheduling of the host thread (the per-round round trip was where the 300-1500 ms outliers of round 1 came from).
+    int burst = can_phase ? 1 : 8;
+    if (const char* e = getenv("FGOICP_BNBR_BURST")) burst = std::max(1, atoi(e));
+    int active_bound = Rn;                             // searches that may still be running (never grows)
+    for (int round = 0; round < 4700 && !drained; round += burst)
     {
-        FG_CUDA(cudaMemsetAsync(d_ctl, 0, 8, c->stream));
-        k_bnbr_round<<<Rn, BNBR_THREADS, smem, c->stream>>>(d_meta, d_pool, d_keys, d_tc, d_cnt, d_lb, d_ub, thr, (int)c->ns, d_ctl);
-        FG_CUDA(cudaGetLastError());
+        for (int b = 0; b < burst; ++b)
+        {
+            FG_CUDA(cudaMemsetAsync(d_ctl, 0, 8, c->stream));
+            k_bnbr_round<<<Rn, BNBR_THREADS, smem, c->stream>>>(d_meta, d_pool, d_keys, d_tc, d_cnt, d_lb, d_ub, thr, (int)c->ns, d_ctl);
+            FG_CUDA(cudaGetLastError());
+            if (burst > 1)
+            {
+                int S = std::min(S_max, fg_bounds_slices(c, active_bound));
+                rc = fg_bounds_plain_counts(c, d_rot, Rn, fix_rot, d_tc, T, d_cnt, S, d_part, d_lb, d_ub);
+                if (rc) return rc;
+            }
+        }
         FG_CUDA(cudaMemcpyAsync((void*)h_ctl, d_ctl, 8, cudaMemcpyDeviceToHost, c->stream));
         FG_CUDA(cudaStreamSynchronize(c->stream));
         const int active = (int)h_ctl[0], pairs = (int)h_ctl[1];
         if (log_rounds)
         {
             auto now = std::chrono::steady_clock::now();
-            fprintf(stderr, "[bnbr] Rn %d round %d active %d pairs %d  +%.1f us\n", Rn, round, active, pairs,
+            fprintf(stderr, "[bnbr] Rn %d round %d active %d pairs %d  +%.1f us\n", Rn, round + burst - 1, active, pairs,
                     std::chrono::duration<double, std::micro>(now - t_prev).count());
             t_prev = now;
         }
         if (active == 0) { drained = true; break; }
+        active_bound = std::min(active_bound, active);
+        if (burst > 1) continue;                       // bounds of the burst's rounds are already enqueued
         bool phased = can_phase && pairs >= min_pairs;
         if (phased)
         {

@@ -99,22 +99,37 @@ k_bounds_multi(LutDev L, const float4* __restrict__ data, int ns,
     }
 }
 
-// Trimmed bounds (extension): one block per (rotation cube, translation cube) pair.  The per-point terms of the
-// pair -- the same ub_i / lb_i the other kernels add up -- are kept in shared memory (2 x ns floats), and each of
-// the two sums runs over the K smallest terms only (trim.cuh).  Unused slots (negative span) are skipped.
-// Clouds whose 2 x ns floats do not fit shared memory (ns > 25,600) keep the terms in a per-block slice of a global
-// scratch buffer instead (GLOBAL = 1: the blocks are persistent and walk the pairs, so the scratch is grid x 8 ns bytes;
-// the select's five passes over the terms are L2 hits).
+// Trimmed bounds (extension): one block per (rotation cube, translation cube) pair.  Both per-point terms of a pair are
+// monotone functions of ONE number, the point's signed residual  e_i = sqrt(d2_i) - rot_r_i  (fg_bound_terms:
+// ub_i = max(e_i, 0)^2, lb_i = max(fma(span, -sqrt3, e_i), 0)^2, every step non-decreasing in e_i under fp32 rounding),
+// so the K smallest ub_i and the K smallest lb_i are the terms of the K smallest e_i -- as multisets, which is all an
+// order-independent fp64 sum sees.  The block therefore keeps ONE float per point (the order-preserving integer key
+// of e_i) in shared memory, runs ONE exact radix select (trim.cuh) and forms both sums from the selected residuals:
+// half the shared memory (4 x ns bytes: five blocks per SM instead of two at ns = 10,000, i.e. 2.5x the gathers in
+// flight) and half the select passes of the first version, which selected ub_i and lb_i separately; same bits.
+// Unused slots (negative span) are skipped.  Clouds whose keys do not fit shared memory (ns > 51,200) keep them in a
+// per-block slice of a global scratch buffer instead (GLOBAL = 1: the blocks are persistent and walk the pairs, the
+// select's passes are L2 hits).
 #define BT_THREADS 256
+__device__ __forceinline__ unsigned int fg_order_key(float x)          // a < b  <=>  key(a) < key(b)  (-0 < +0, NaN on top)
+{
+    const unsigned int b = __float_as_uint(x);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float fg_order_value(unsigned int k)
+{
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
 template <int SAMPLER, int GLOBAL>
 __global__ void __launch_bounds__(BT_THREADS)
 k_bounds_trim(LutDev L, const float4* __restrict__ data, int ns,
               const float4* __restrict__ rot, const float* __restrict__ Rmats, int fix_rot,
               const float4* __restrict__ tcubes, int T, int n_pairs, unsigned int K,
-              float* __restrict__ lb, float* __restrict__ ub, unsigned int* __restrict__ best_ub_bits, float* gscratch)
+              float* __restrict__ lb, float* __restrict__ ub, unsigned int* __restrict__ best_ub_bits, unsigned int* gscratch)
 {
-    extern __shared__ float sv_shared[];          // [2][ns]: ub_i, lb_i (GLOBAL = 0)
-    float* sv = GLOBAL ? gscratch + (size_t)blockIdx.x * 2 * (size_t)ns : sv_shared;
+    extern __shared__ unsigned int sv_shared[];   // [ns]: order key of e_i (GLOBAL = 0)
+    unsigned int* sv = GLOBAL ? gscratch + (size_t)blockIdx.x * (size_t)ns : sv_shared;
     __shared__ float sR[9];
     __shared__ float s_sin;
     __shared__ unsigned int s_hist[256], s_state[2];
@@ -124,7 +139,7 @@ k_bounds_trim(LutDev L, const float4* __restrict__ data, int ns,
     const int r = pair / T;
     const float4 t = tcubes[pair];
     if (t.w < 0.0f) continue;
-    __syncthreads();                              // the previous pair's terms and rotation are no longer read
+    __syncthreads();                              // the previous pair's residuals and rotation are no longer read
     if (threadIdx.x == 0)
     {
         float4 rc = rot[r];
@@ -161,19 +176,30 @@ k_bounds_trim(LutDev L, const float4* __restrict__ data, int ns,
         for (int k = 0; k < 4; ++k)
         {
             const int i = i0 + k * BT_THREADS;
-            float u, l;
-            fg_bound_terms(fg_sample_finish<SAMPLER>(req[k]), rot_r[k], fix_rot != 0, t.w, u, l);
-            if (i < ns) { sv[i] = u; sv[ns + i] = l; }
+            if (i < ns) sv[i] = fg_order_key(fg_bound_residual(fg_sample_finish<SAMPLER>(req[k]), rot_r[k], fix_rot != 0));
         }
     }
     __syncthreads();
-    const float* su = sv;
-    const float* sl = sv + ns;
-    double tu = fg_block_trimmed_sum([&](int i) { return __float_as_uint(su[i]); }, ns, K, s_hist, s_state, s_w);
-    double tl = fg_block_trimmed_sum([&](int i) { return __float_as_uint(sl[i]); }, ns, K, s_hist, s_state, s_w);
+    const unsigned int* sk = sv;
+    const FgSelect sel = fg_block_select([&](int i) { return sk[i]; }, ns, K, s_hist, s_state);
+    double pu = 0.0, pl = 0.0;
+    for (int i = threadIdx.x; i < ns; i += BT_THREADS)
+    {
+        const unsigned int key = sk[i];
+        if (key < sel.vk_bits)
+        {
+            float u, l;
+            fg_bound_from_residual(fg_order_value(key), t.w, u, l);
+            pu += (double)u; pl += (double)l;
+        }
+    }
+    const double tu = fg_block_sum1(pu, s_w);
+    const double tl = fg_block_sum1(pl, s_w);
     if (threadIdx.x == 0)
     {
-        float fu = (float)tu, fl = (float)tl;
+        float uk, lk;
+        fg_bound_from_residual(fg_order_value(sel.vk_bits), t.w, uk, lk);
+        float fu = (float)(tu + (double)sel.take_eq * (double)uk), fl = (float)(tl + (double)sel.take_eq * (double)lk);
         ub[pair] = fu; lb[pair] = fl;
         if (best_ub_bits) atomicMin(best_ub_bits, __float_as_uint(fu));
     }
@@ -236,13 +262,13 @@ static int run_bounds(fgoicp_ctx* c, const BoundsLaunch& b)
     if (c->trim_k > 0)
     {
         // trimmed registration: every pair sums its K smallest terms (one block per pair)
-        size_t smem = sizeof(float) * 2 * c->ns;
-        const bool global_terms = smem > 200 * 1024 || getenv("FGOICP_TRIM_GLOBAL") != nullptr;   // ns > 25,600: terms in HBM / L2
+        size_t smem = sizeof(unsigned int) * c->ns;
+        const bool global_terms = smem > 200 * 1024 || getenv("FGOICP_TRIM_GLOBAL") != nullptr;   // ns > 51,200: residual keys in HBM / L2
         unsigned int* d_bits = (unsigned int*)b.d_best_ub;
         if (d_bits) k_set_u32<<<1, 1, 0, c->stream>>>(d_bits, 0x7f800000u);
         const int n_pairs = b.Rn * b.T;
         dim3 grid((unsigned)n_pairs);
-        float* d_terms = nullptr;
+        unsigned int* d_terms = nullptr;
         if (global_terms)
         {
             grid = dim3((unsigned)std::min(n_pairs, 4 * c->sm_count));
@@ -253,7 +279,7 @@ static int run_bounds(fgoicp_ctx* c, const BoundsLaunch& b)
                 FG_CUDA(cudaMalloc(&c->d_trim, (size_t)4 * c->sm_count * smem));
                 c->trim_bytes = (size_t)4 * c->sm_count * smem;
             }
-            d_terms = (float*)c->d_trim;
+            d_terms = (unsigned int*)c->d_trim;
             smem = 0;
         }
 #define FG_LAUNCH_TRIM(SMP)                                                                                              \

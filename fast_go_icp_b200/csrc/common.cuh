@@ -423,11 +423,23 @@ __device__ __forceinline__ float fg_sample_finish(const SampleReq& r)
 // Per-point body of kernComputeBounds (reference registration.cu:27-60) after the sample:
 // d = sqrt(d2); if (!fix_rot) d -= rot_r; ub = d>0 ? d*d : 0; e = fma(span_t, -sqrt3, d);
 // lb = e>0 ? e*e : 0.
+__device__ __forceinline__ float fg_bound_residual(float d2, float rot_r, bool fix_rot);
+__device__ __forceinline__ void fg_bound_from_residual(float d, float span_t, float& ub, float& lb);
 __device__ __forceinline__ void fg_bound_terms(float d2, float rot_r, bool fix_rot, float span_t,
                                                float& ub, float& lb)
 {
     // branch-free: d - 0 == d bit for bit (d = sqrt >= +0), and x > 0 ? x*x : 0 == sq(max(x, 0)) (NaN -> 0 both ways)
-    float d = __fsub_rn(__fsqrt_rn(d2), fix_rot ? 0.0f : rot_r);
+    fg_bound_from_residual(fg_bound_residual(d2, rot_r, fix_rot), span_t, ub, lb);
+}
+
+// The same per-point body in two steps, for callers that select on the signed residual before they sum (trimmed bounds):
+// fg_bound_residual gives d of fg_bound_terms, fg_bound_from_residual its two terms -- bit for bit the same operations.
+__device__ __forceinline__ float fg_bound_residual(float d2, float rot_r, bool fix_rot)
+{
+    return __fsub_rn(__fsqrt_rn(d2), fix_rot ? 0.0f : rot_r);
+}
+__device__ __forceinline__ void fg_bound_from_residual(float d, float span_t, float& ub, float& lb)
+{
     float du = fmaxf(d, 0.0f);
     ub = __fmul_rn(du, du);
     float e = fmaxf(__fmaf_rn(span_t, -FG_SQRT3, d), 0.0f);

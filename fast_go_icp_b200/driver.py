@@ -10,8 +10,12 @@ the same operation order, so C++ and Python drivers agree bit for bit.
 Sharding: at each level the children to evaluate are dealt round-robin to the
 ranks; after the fixed-rotation phase the best SSE is MIN-reduced (all_reduce on a packed
 (sse bits, child index) key -- NCCL over NVLink on GPUs) and the winner's pose broadcast; per-cube
-results are all-gathered so that every rank rebuilds the identical next frontier.  Results are
-independent of the number of ranks by construction.
+results are all-gathered so that every rank rebuilds the identical next frontier.  The SCHEDULE is independent
+of the number of ranks by construction (which cube is searched against which incumbent, which cube is refined);
+the values are too, except that a bound is an fp64 sum of fp32 terms rounded once and the order of its partial
+sums follows the launch geometry (cluster size depends on the number of cubes a rank holds): a sum that sits within
+~1e-13 relative of an fp32 rounding boundary can round differently.  Never observed (same SSE bits at
+1, 2, 3, 8 ranks); the tests compare bits and would say so.
 """
 import time
 

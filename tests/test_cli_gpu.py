@@ -62,8 +62,9 @@ def test_unchanged_reference_main_cpp_runs_on_this_library(tmp_path):
     """build/fast-go-icp is the reference's src/main.cpp + src/utilities.hpp, UNCHANGED (fast_go_icp_b200/build_cli.py),
     linked against this repository's headers and library: the drop-in claim of SURVEY.md 8b exercised end to end
     (reference src/main.cpp:38-55: config -> load_cloud x2 -> icp::FastGoICP(target, source, res, mse) -> run()).
-    With subsample 1.0 its loader keeps every point, so the Python driver sees the same clouds and must log the same
-    registration: Best Error to the 6 digits the reference's Logger prints, pose to its 4 / 6 decimals."""
+    The reference's loader clamps source_subsample to 0.5 and draws from std::random_device (utilities.hpp:103, 208-217),
+    so the binary registers a RANDOM half of the source: its logged pose must be the true one, and its error per point the
+    one the Python driver reaches on the whole source over the same C ABI."""
     import os
     import re
     import subprocess
@@ -79,26 +80,26 @@ def test_unchanged_reference_main_cpp_runs_on_this_library(tmp_path):
             np.savetxt(f, pts, fmt="%.6f")
     (tmp_path / "demo.toml").write_text(
         '[info]\nversion = "0.2"\n[io]\ntarget = "%s"\nsource = "%s"\n[params]\ntrim = false\n'
-        'target_subsample = 1.0\nsource_subsample = 1.0\nlut_resolution = 0.01\nmse_threshold = 1e-4\n'
+        'target_subsample = 1.0\nsource_subsample = 0.5\nlut_resolution = 0.01\nmse_threshold = 1e-4\n'
         % (tmp_path / "model.txt", tmp_path / "data.txt"))
     r = subprocess.run([exe, "-c", str(tmp_path / "demo.toml"), "-v"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
     out = re.sub(r"\x1b\[[0-9;]*m", "", r.stdout + r.stderr)
-    assert "Target point cloud (20000)" in out and "Source point cloud (4000)" in out and "Fast Go-ICP finished" in out
+    assert "Target point cloud (20000)" in out and "Fast Go-ICP finished" in out, out[-1500:]
+    n_src = int(re.search(r"Source point cloud \((\d+)\)", out).group(1))
+    assert 1700 <= n_src <= 2000                                   # ~Binomial(4000, 0.5), capped at 2000 (utilities.hpp:201, 217)
     m = re.search(r"Searching over! Best Error: ([0-9.eE+-]+)\s+Rotation:\s+((?:[-0-9.eE+]+\s+){9})Translation: ([-0-9.eE+]+)\s+([-0-9.eE+]+)\s+([-0-9.eE+]+)", out)
     assert m, out[-1500:]
     sse = float(m.group(1))
-    R_log = np.array([float(x) for x in m.group(2).split()]).reshape(3, 3)
+    R_log = np.array([float(x) for x in m.group(2).split()]).reshape(3, 3)      # Logger prints the matrix row by row
     t_log = np.array([float(m.group(k)) for k in (3, 4, 5)])
-    # the same clouds as the binary parsed them (6 decimals), through the Python driver over the same C ABI
+    ang = np.degrees(np.arccos(np.clip((np.trace(R_log @ w["R_true"].T) - 1) / 2, -1, 1)))
+    assert ang < 1.0 and np.linalg.norm(t_log - w["t_true"]) < 0.01, (ang, t_log, w["t_true"])
+    # the whole source through the Python driver over the same C ABI: same registration, same error per point
     model = np.loadtxt(tmp_path / "model.txt", skiprows=1, dtype=np.float32)
     data = np.loadtxt(tmp_path / "data.txt", skiprows=1, dtype=np.float32)
     g = driver.FastGoICP(model, data, 0.01, 1e-4)
     R, t = g.run()
-    assert abs(sse - float(g.best_sse)) <= 2e-6 * float(g.best_sse) + 5e-6 * 10 ** np.floor(np.log10(float(g.best_sse)))   # 6 significant digits
-    # the Logger prints glm::mat3 row by row of its operator<< (column-major storage): accept either orientation
-    assert min(np.abs(R_log - R).max(), np.abs(R_log - R.T).max()) <= 1e-4
-    assert np.abs(t_log - t).max() <= 2e-6
-    ang = np.degrees(np.arccos(np.clip((np.trace(R @ w["R_true"].T) - 1) / 2, -1, 1)))
-    assert ang < 1.0 and np.linalg.norm(t - w["t_true"]) < 0.01
+    assert np.abs(R_log - R).max() < 5e-3 and np.abs(t_log - t).max() < 5e-3
+    assert abs(sse / n_src - float(g.best_sse) / len(data)) <= 0.1 * float(g.best_sse) / len(data)
     g.close()

@@ -216,6 +216,9 @@ __device__ __forceinline__ float fg_shrink(float d2, float margin)
 #ifndef FG_NN_MARGIN
 #define FG_NN_MARGIN 2.5e-4f  // winner-memo scan margin in normalised units (0 disables the memo; env FGOICP_NN_MARGIN overrides)
 #endif
+#ifndef FG_NN_RHO_SLACK
+#define FG_NN_RHO_SLACK 1e-5f // relative slack of the winner memo's clearance (the distance formula rounds at ~1.2e-7 relative); 2e-6 / 5e-7 measured: 9-10 % fewer rooted rescans, ICP -1 % (profiles/nn_scan_r02.md)
+#endif
 #ifndef NN_RPL
 #define NN_RPL 1            // rows per lane and pass of the cell-grid search; measured on the dragon pair (W3, ICP ms): 1 -> 3688, 4 -> 3873, 8 -> 4101
 #endif
@@ -513,7 +516,7 @@ __device__ __forceinline__ unsigned long long fg_nn_scan(const CellGrid& g, cons
         for (int o = NN_LPQ / 2; o > 0; o >>= 1) other = fminf(other, __shfl_xor_sync(team_mask, other, o, NN_LPQ));
         other = coop_min_f(other);
         const float ds = fminf(sqrtf(other), sqrtf(U2) * 0.9999f);
-        rho = 0.5f * (ds - sqrtf(wd2)) - (1e-5f * ds + 1e-7f);
+        rho = 0.5f * (ds - sqrtf(wd2)) - (FG_NN_RHO_SLACK * ds + 1e-7f);
     }
     if (ROOTED && NN_FAST_ROOTED && !exact)
     {

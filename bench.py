@@ -450,14 +450,21 @@ def run_ours(args):
         # (the other ranks wait on a host-side gloo barrier: an NCCL barrier would park a spinning kernel on the very GPUs
         # the harness is about to use -- measured: 180 ms instead of 91 ms for two devices)
         cpp = None
+        host_wait = None
         if world > 1:
             torch.cuda.synchronize()
-            host_group = dist.new_group(backend="gloo")
-            dist.barrier(group=host_group)
+            try:
+                host_group = dist.new_group(backend="gloo")
+                host_wait = lambda: dist.barrier(group=host_group)
+                host_wait()
+            except Exception as ex:                       # no usable gloo transport on this box: fall back to NCCL's barrier
+                log("gloo barrier unavailable (%s): the C++ class shares the GPUs with an NCCL barrier" % str(ex)[:120])
+                host_wait = barrier
+                host_wait()
         if rank == 0:
             cpp = cpp_class_run(w, world)
-        if world > 1:
-            dist.barrier(group=host_group)
+        if host_wait:
+            host_wait()
         if cpp is not None:
             bnb["cpp_class"] = cpp
         if rank == 0 and world == 1 and not args.no_cpu:

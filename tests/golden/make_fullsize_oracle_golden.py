@@ -29,6 +29,8 @@ CASES = {
     "w5_mse1e-4": ("w5", 0.005, 1e-4),
     "dragon_mse1e-3": ("dragon", 0.005, 1e-3), "dragon_mse1e-4": ("dragon", 0.005, 1e-4),
     "overlap_mse1e-3": ("overlap", 0.005, 1e-3), "overlap_mse1e-4": ("overlap", 0.005, 1e-4),
+    # trimmed registration (extension; fourth field = trim_fraction): the configurations bench.py times on W2 and W4
+    "skull_trim0.1_mse1e-3": ("skull", 0.005, 1e-3, 0.1), "overlap_trim0.45_mse1e-4": ("overlap", 0.005, 1e-4, 0.45),
 }
 
 
@@ -53,13 +55,14 @@ def write_clouds():
 def run_case(name):
     from fast_go_icp_b200 import driver
     from oracle_context import OracleContext
-    pair, res, mse = CASES[name]
+    pair, res, mse = CASES[name][:3]
+    trim = CASES[name][3] if len(CASES[name]) > 3 else 0.0
     model, data = load(pair)
     t0 = time.perf_counter()
-    g = driver.FastGoICP(model, data, res, mse, ctx_factory=OracleContext)
+    g = driver.FastGoICP(model, data, res, mse, ctx_factory=OracleContext, trim_fraction=trim)
     R, t = g.run()
     st = g.stats
-    out = dict(case=name, pair=pair, nt=len(model), ns=len(data), lut_resolution=res, mse_threshold=mse,
+    out = dict(case=name, pair=pair, nt=len(model), ns=len(data), lut_resolution=res, mse_threshold=mse, trim_fraction=trim,
                schedule="level", produced_by="CPU oracle through fast_go_icp_b200.driver (tests/oracle_context.OracleContext)",
                sse=float(g.best_sse), sse_bits=int(np.float32(g.best_sse).view(np.uint32)),
                R_bits=[int(x) for x in np.asarray(R, np.float32).ravel().view(np.uint32)],

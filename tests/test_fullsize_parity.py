@@ -61,7 +61,7 @@ def test_oracle_through_the_driver_reproduces_its_golden():
 
 
 CASES = ["bunny_mse1e-3", "bunny_mse1e-5", "skull_mse1e-3", "w5_mse1e-4", "dragon_mse1e-3", "dragon_mse1e-4",
-         "overlap_mse1e-3", "overlap_mse1e-4"]
+         "overlap_mse1e-3", "overlap_mse1e-4", "skull_trim0.1_mse1e-3", "overlap_trim0.45_mse1e-4"]
 
 
 @pytest.mark.gpu
@@ -71,7 +71,8 @@ def test_cuda_path_reproduces_the_oracle_result_bit_for_bit(case):
     want = golden(case)
     model, data = clouds(want["pair"])
     assert len(model) == want["nt"] and len(data) == want["ns"]
-    g = driver.FastGoICP(model, data, want["lut_resolution"], want["mse_threshold"], flags=capi.BUILD_PACKED)
+    g = driver.FastGoICP(model, data, want["lut_resolution"], want["mse_threshold"], flags=capi.BUILD_PACKED,
+                         trim_fraction=want.get("trim_fraction", 0.0))
     R, t = g.run()
     check(g, R, t, want)
     g.close()

@@ -826,6 +826,27 @@ int fg_bounds_slices(const fgoicp_ctx* c, int active);
 int fg_bounds_plain_counts(fgoicp_ctx* c, const float4* d_rot, int Rn, int fix_rot, const float4* d_tc, int T,
                            const int* d_counts, int S, double* d_partial, float* d_lb, float* d_ub);
 
+// Scratch of the round-synchronous schedule for a whole level of the outer search, allocated when the schedule is switched
+// on (fgoicp_set_trim / fgoicp_set_bnb_mode) so that run() allocates nothing.  Best effort: bnb_rounds allocates what it
+// needs if this did not happen.
+int fg_rounds_prealloc(fgoicp_ctx* c)
+{
+    const int T = BNB_BATCH_MAX, Rn = 4096;
+    const int S_max = std::max(1, std::min(16, (int)(c->ns / 256)));
+    size_t want = sizeof(BnbrMeta) * (size_t)Rn + sizeof(unsigned long long) * (size_t)Rn * BNBR_POOL + sizeof(unsigned long long) * (size_t)Rn * T
+                + sizeof(float4) * (size_t)Rn * T + sizeof(int) * (size_t)Rn + 2 * sizeof(float) * (size_t)Rn * T
+                + sizeof(double) * 2 * (size_t)Rn * T * S_max + 16 * 256;
+    if (want <= c->rounds_bytes) return FGOICP_OK;
+    FG_CUDA(cudaSetDevice(c->device));
+    FG_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(c->d_rounds); c->d_rounds = nullptr; c->rounds_bytes = 0;
+    if (cudaMalloc(&c->d_rounds, want) == cudaSuccess) c->rounds_bytes = want;
+    else cudaGetLastError();
+    size_t smem = sizeof(unsigned long long) * BNB_POOL;
+    FG_CUDA(cudaFuncSetAttribute(k_bnbr_round, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    return fg::ensure_pinned(c, 4096);
+}
+
 // All Rn searches of a level, one iteration per round (see k_bnbr_round).  Results land in d_out exactly as
 // launch_bnb leaves them.
 static int bnb_rounds(fgoicp_ctx* c, const float4* d_rot, int Rn, int fix_rot, float best_sse, float thr, BnbOut* d_out)
@@ -843,10 +864,21 @@ static int bnb_rounds(fgoicp_ctx* c, const float4* d_rot, int Rn, int fix_rot, f
     size_t need = b_meta + b_pool + b_keys + b_tc + b_cnt + 2 * b_out + b_ctl + b_part;
     if (need > c->rounds_bytes)
     {
+        // Sized once for a whole level of the outer search (<= 4096 rotation cubes: ~45 KB each, ~190 MB), not for this call:
+        // the waves of a level grow (32, 128, 512, the rest, then all of them for the lower bounds), and a cudaFree + cudaMalloc
+        // per growth inside run() was measured to stall the host for 200-550 ms now and then when another process on the
+        // box is in the allocator too (the sporadic outliers of the trimmed searches, profiles/in_search_r02.md).
+        const size_t per_cube = need / (size_t)Rn + 1;
+        const size_t want = std::max(need, per_cube * 4096 + 4096);
         FG_CUDA(cudaStreamSynchronize(c->stream));
         cudaFree(c->d_rounds); c->d_rounds = nullptr; c->rounds_bytes = 0;
-        FG_CUDA(cudaMalloc(&c->d_rounds, need));
-        c->rounds_bytes = need;
+        if (cudaMalloc(&c->d_rounds, want) == cudaSuccess) c->rounds_bytes = want;
+        else
+        {
+            cudaGetLastError();                          // not enough memory for the generous size: exactly what this call needs
+            FG_CUDA(cudaMalloc(&c->d_rounds, need));
+            c->rounds_bytes = need;
+        }
     }
     int rc = fg::ensure_pinned(c, 4096);
     if (rc) return rc;
@@ -1000,6 +1032,7 @@ extern "C" int fgoicp_set_bnb_mode(fgoicp_ctx* c, int mode)
     FG_ARG(c, "NULL context");
     FG_ARG(mode >= 0 && mode <= 2, "mode must be 0 (auto), 1 (persistent) or 2 (round-synchronous)");
     c->bnb_mode = mode;
+    if (mode == 2) return fg_rounds_prealloc(c);
     return FGOICP_OK;
 }
 

@@ -784,6 +784,7 @@ extern "C" int fgoicp_ctx_info(const fgoicp_ctx* c, fgoicp_info* o)
     return FGOICP_OK;
 }
 
+int fg_rounds_prealloc(fgoicp_ctx* c);
 extern "C" int fgoicp_set_trim(fgoicp_ctx* c, float trim_fraction, uint64_t* inliers)
 {
     FG_ARG(c, "NULL context");
@@ -793,6 +794,8 @@ extern "C" int fgoicp_set_trim(fgoicp_ctx* c, float trim_fraction, uint64_t* inl
     size_t k = drop >= c->ns ? 1 : c->ns - drop;
     c->trim_k = (k == c->ns) ? 0 : k;
     if (inliers) *inliers = k;
+    // trimmed searches run round-synchronously: their per-level scratch is allocated now, not inside run()
+    if (c->trim_k > 0) return fg_rounds_prealloc(c);
     return FGOICP_OK;
 }
 

@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(NWARPS * 32, MINB)
 k_bnb_r3m(LutDev L, const float4* __restrict__ data, int ns, const float4* __restrict__ rot, int fix_rot,
           float best_sse, float sse_threshold, int batch_max, BnbOut* __restrict__ out)
 {
-    extern __shared__ unsigned long long poolm[];         // 2 x BNBM_POOL + BNBM_NEW keys
+    extern __shared__ unsigned long long poolm[];         // 2 x BNBM_POOL + 2 x BNBM_NEW keys
     __shared__ float sR[9];
     __shared__ float s_sin;
     __shared__ float4 s_tc[BNB_BATCH_MAX];
@@ -318,7 +318,8 @@ k_bnb_r3m(LutDev L, const float4* __restrict__ data, int ns, const float4* __res
     int parity = 0;
     unsigned long long* A = poolm;                        // current sorted run: A[head .. head + m)
     unsigned long long* B = poolm + BNBM_POOL;            // merge target
-    unsigned long long* C = poolm + 2 * BNBM_POOL;        // children of the batch
+    unsigned long long* const C0 = poolm + 2 * BNBM_POOL; // children of the batch, as spawned; sorted copy behind it
+    unsigned long long* C = C0;
     int head = 0;
 
     if (tid == 0)
@@ -407,6 +408,7 @@ k_bnb_r3m(LutDev L, const float4* __restrict__ data, int ns, const float4* __res
         __syncthreads();
 
         // ---- children of surviving cubes (fgoicp.cpp:148-169), in pop order, into C
+        C = C0;
         const float best_error = s_best_error;
         const unsigned long long cut_key = (unsigned long long)__float_as_uint(best_error) << 32;   // keys >= this are dead
         if (tid < 32)
@@ -445,25 +447,19 @@ k_bnb_r3m(LutDev L, const float4* __restrict__ data, int ns, const float4* __res
         }
         if (nc > 0)
         {
-            // sort the children (bitonic over the next power of two >= nc, <= 256)
-            int P = 8; while (P < nc) P <<= 1;
-            for (int i = nc + tid; i < P; i += NT) C[i] = BNB_KEY_MAX;
+            // sort the children by rank: keys are unique, so a key's position is the number of smaller keys -- nc broadcast
+            // reads per thread and ONE barrier instead of the 36 compare-exchange sweeps (each with its own barrier) of a
+            // bitonic network over 256 keys, which were ~10 us of every iteration of the latency-bound coarse levels
+            unsigned long long* Cs = C + BNBM_NEW;            // sorted children
+            for (int i = tid; i < nc; i += NT)
+            {
+                const unsigned long long key = C[i];
+                int rank = 0;
+                for (int j = 0; j < nc; ++j) rank += C[j] < key;
+                Cs[rank] = key;
+            }
             __syncthreads();
-            for (int k = 2; k <= P; k <<= 1)
-                for (int j = k >> 1; j > 0; j >>= 1)
-                {
-                    for (int i = tid; i < P; i += NT)
-                    {
-                        int ixj = i ^ j;
-                        if (ixj > i)
-                        {
-                            unsigned long long a = C[i], b = C[ixj];
-                            bool up = ((i & k) == 0);
-                            if ((a > b) == up) { C[i] = b; C[ixj] = a; }
-                        }
-                    }
-                    __syncthreads();
-                }
+            C = Cs;
             // children at or above the cut are dead too (cannot happen for a freshly spawned child -- its lb is its
             // parent's, which was below best_error -- but the rule is applied uniformly)
             int ncl;
@@ -754,7 +750,7 @@ static int launch_bnb_w(fgoicp_ctx* c, const float4* d_rot, int Rn, int csize, i
 template <int SAMPLER, int NWARPS, int MINB>
 static int launch_bnbm_t(fgoicp_ctx* c, const float4* d_rot, int Rn, int csize, int fix_rot, float best_sse, float thr, BnbOut* d_out)
 {
-    size_t smem = sizeof(unsigned long long) * (2 * BNBM_POOL + BNBM_NEW);
+    size_t smem = sizeof(unsigned long long) * (2 * BNBM_POOL + 2 * BNBM_NEW);
     FG_CUDA(cudaFuncSetAttribute(k_bnb_r3m<SAMPLER, NWARPS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (csize > 8) FG_CUDA(cudaFuncSetAttribute(k_bnb_r3m<SAMPLER, NWARPS, MINB>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cudaLaunchConfig_t cfg = {};

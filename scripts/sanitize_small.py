@@ -15,6 +15,10 @@ R, _ = driver.rotation_matrix(np.float32(0.1), np.float32(0.2), np.float32(-0.1)
 ctx.bounds_batch(R, 0.125, True, tc[0])
 ctx.sse(R, np.zeros(3, np.float32)); ctx.nn(R, np.zeros(3, np.float32), True); ctx.nn(R, np.zeros(3, np.float32), False)
 ctx.icp(R, np.zeros(3, np.float32), 20, 0.005)
+# batches of refinements through both drivers: the persistent loop kernel (mode 2) and the launch chain (mode 1)
+R0s = np.stack([driver.rotation_matrix(*rot[k, :3])[0] for k in range(6)]); t0s = np.zeros((6, 3), np.float32)
+for mode in (2, 1, 0):
+    ctx.set_icp_mode(mode); ctx.icp_batch(R0s, t0s, 12, 0.005)
 ctx.bnb_r3_batch(rot[:5], True, 1e10, 260 * 1e-4)
 ctx.set_bnb_mode(2); ctx.bnb_r3_batch(rot[:40], False, 3.0, 260 * 1e-4); ctx.set_bnb_mode(0)
 ctx.set_trim(0.2)

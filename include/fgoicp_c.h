@@ -119,9 +119,11 @@ int fgoicp_set_sampler(fgoicp_ctx* ctx, int sampler);
  * fgoicp/fgoicp.hpp:73): with trim_fraction rho > 0 every sum over the data points -- per-cube upper and lower
  * bounds, the exact SSE, the centroids and cross-covariance of the ICP -- runs over the
  * K = ns - floor(ns * rho) points with the smallest residual only.  rho = 0 (default) is the reference's behaviour.
- * *inliers (optional) receives K.  Affects every later call on the context; the bound kernel then keeps the 2 * ns
- * per-point terms of a cube in shared memory (ns <= 25,600) or, for larger clouds, in an L2-resident scratch slice per
- * thread block, and the inner searches run round-synchronously. */
+ * *inliers (optional) receives K.  Affects every later call on the context; the bound kernel then keeps one key per
+ * data point (its signed residual: both bounds are monotone in it, so ONE exact select serves both sums) in shared memory
+ * (ns <= 51,200) or, for larger clouds, in an L2-resident scratch slice per thread block, and the inner searches run
+ * round-synchronously.  Switching trimming on allocates the per-level scratch of that schedule (~45 KB per rotation cube,
+ * sized for 4,096 cubes) so that the searches allocate nothing. */
 int fgoicp_set_trim(fgoicp_ctx* ctx, float trim_fraction, uint64_t* inliers);
 /* CUDA stream (cudaStream_t passed as void*) every later call on this context enqueues on;
  * NULL selects the context's own stream.  Lets a host framework time calls with its own events. */
@@ -141,7 +143,8 @@ int fgoicp_lut_sample(fgoicp_ctx* ctx, const float* q_xyz, size_t n, int sampler
 int fgoicp_set_phased(fgoicp_ctx* ctx, int on);
 /* Schedule of the inner searches behind fgoicp_bnb_r3_batch / fgoicp_so3_level_*: 0 = default (one persistent
  * thread-block cluster per search), 1 = same, explicitly, 2 = round-synchronous (all searches advance one
- * iteration per round, bounds of each round through the phase-ordered kernel).  Same results either way. */
+ * iteration per round, bounds of each round through the phase-ordered kernel; selecting it allocates its per-level
+ * scratch).  Same results either way. */
 int fgoicp_set_bnb_mode(fgoicp_ctx* ctx, int mode);
 /* Driver of the ICP refinements behind fgoicp_icp / fgoicp_icp_batch / fgoicp_so3_level_ub:
  *   2 = one persistent cooperative kernel per batch: the whole loop of icp3d.cu:85-108 on the device, stages separated

@@ -480,8 +480,16 @@ static int build_cell_grid(fgoicp_ctx* c, const float4* d_P)
             const unsigned X = (unsigned)(w % Cx), Y = (unsigned)((w / Cx) % Cy), Z = (unsigned)(w / (Cx * Cy));
             const unsigned packed = X | (Y << 10) | (Z << 20);
             float pf; memcpy(&pf, &packed, 4);
+            // cells of the block its points actually occupy, per axis (offsets 0..7 inside the block, 3 bits each): the binning
+            // function of k_cell_index (one float multiply, floor, clamp) applied to the tight box; it is monotone, so every
+            // point of the block lies in [cell(lo), cell(hi)].  A surface crossing an 8^3 block leaves most of its 64 rows empty.
+            auto cell = [&](float v, int n) { int q = (int)std::floor(v * c->cell_inv_h); return std::min(std::max(q, 0), n - 1); };
+            const unsigned tight = (unsigned)(cell(hlo[w].x, c->cnx) & 7) | ((unsigned)(cell(hhi[w].x, c->cnx) & 7) << 3)
+                                 | ((unsigned)(cell(hlo[w].y, c->cny) & 7) << 6) | ((unsigned)(cell(hhi[w].y, c->cny) & 7) << 9)
+                                 | ((unsigned)(cell(hlo[w].z, c->cnz) & 7) << 12) | ((unsigned)(cell(hhi[w].z, c->cnz) & 7) << 15);
+            float tf; memcpy(&tf, &tight, 4);
             list.push_back(make_float4(hlo[w].x, hlo[w].y, hlo[w].z, pf));
-            list.push_back(make_float4(hhi[w].x, hhi[w].y, hhi[w].z, 0.0f));
+            list.push_back(make_float4(hhi[w].x, hhi[w].y, hhi[w].z, tf));
         }
         c->n_coarse = (int)(list.size() / 2);
         if (c->n_coarse > 0)

@@ -474,7 +474,7 @@ __device__ __forceinline__ unsigned long long fg_nn_scan(const CellGrid& g, cons
         {
             const int k = k0 + lane;
             float lb2 = FG_INF;
-            unsigned int box = 0;
+            unsigned int box = 0, tight = 0;
             if (k < g.n_coarse)
             {
                 const float4 lo = __ldg(g.coarse + 2 * k), hi = __ldg(g.coarse + 2 * k + 1);
@@ -483,6 +483,7 @@ __device__ __forceinline__ unsigned long long fg_nn_scan(const CellGrid& g, cons
                 const float dz = fmaxf(fmaxf(lo.z - lz, lz - hi.z), 0.0f);
                 lb2 = dx * dx + dy * dy + dz * dz;
                 box = __float_as_uint(lo.w);
+                tight = __float_as_uint(hi.w);                     // occupied cell range inside the block, 3 bits per bound (ctx.cu)
             }
             unsigned int live = __ballot_sync(team_mask, lb2 <= U2);
             if (NN_LPQ != 32) live = (live & team_mask) >> ((threadIdx.x & 31) & ~(NN_LPQ - 1));
@@ -493,9 +494,12 @@ __device__ __forceinline__ unsigned long long fg_nn_scan(const CellGrid& g, cons
                 const float lbj = __shfl_sync(team_mask, lb2, j, NN_LPQ);
                 if (lbj > U2) continue;                            // the ball has shrunk meanwhile (U2 is team-uniform here)
                 const unsigned int bj = __shfl_sync(team_mask, box, j, NN_LPQ);
+                const unsigned int tj = __shfl_sync(team_mask, tight, j, NN_LPQ);
                 const int X = (int)(bj & 1023u) * FG_COARSE, Y = (int)((bj >> 10) & 1023u) * FG_COARSE, Z = (int)(bj >> 20) * FG_COARSE;
-                const int z0 = max(Z, cz0), z1 = min(Z + FG_COARSE - 1, cz1), y0 = max(Y, cy0), y1 = min(Y + FG_COARSE - 1, cy1);
-                if (z0 <= z1 && y0 <= y1) scan_rows(z0, z1, y0, y1, X, min(X + FG_COARSE - 1, g.nx - 1));
+                // only the rows and columns of the block that hold points (a surface leaves most of its 64 rows empty)
+                const int z0 = max(Z + (int)((tj >> 12) & 7u), cz0), z1 = min(Z + (int)((tj >> 15) & 7u), cz1);
+                const int y0 = max(Y + (int)((tj >> 6) & 7u), cy0), y1 = min(Y + (int)((tj >> 9) & 7u), cy1);
+                if (z0 <= z1 && y0 <= y1) scan_rows(z0, z1, y0, y1, X + (int)(tj & 7u), X + (int)((tj >> 3) & 7u));
             }
         }
     }

@@ -103,7 +103,9 @@ struct CellGrid
     int n_coarse = 0;
     int coarse_min_rows = 320;     // rows of a ball beyond which the coarse boxes are consulted (+ n_coarse / 8)
 };
-#define FG_COARSE 8
+#ifndef FG_COARSE
+#define FG_COARSE 8      // cells per axis of a coarse block (4 measured: see profiles/nn_scan_r02.md); the tight cell bounds of a block use 3 bits each
+#endif
 
 struct fgoicp_ctx
 {

@@ -484,9 +484,10 @@ static int build_cell_grid(fgoicp_ctx* c, const float4* d_P)
             // function of k_cell_index (one float multiply, floor, clamp) applied to the tight box; it is monotone, so every
             // point of the block lies in [cell(lo), cell(hi)].  A surface crossing an 8^3 block leaves most of its 64 rows empty.
             auto cell = [&](float v, int n) { int q = (int)std::floor(v * c->cell_inv_h); return std::min(std::max(q, 0), n - 1); };
-            const unsigned tight = (unsigned)(cell(hlo[w].x, c->cnx) & 7) | ((unsigned)(cell(hhi[w].x, c->cnx) & 7) << 3)
-                                 | ((unsigned)(cell(hlo[w].y, c->cny) & 7) << 6) | ((unsigned)(cell(hhi[w].y, c->cny) & 7) << 9)
-                                 | ((unsigned)(cell(hlo[w].z, c->cnz) & 7) << 12) | ((unsigned)(cell(hhi[w].z, c->cnz) & 7) << 15);
+            const int bx0 = (int)X * FG_COARSE, by0 = (int)Y * FG_COARSE, bz0 = (int)Z * FG_COARSE;
+            const unsigned tight = (unsigned)(cell(hlo[w].x, c->cnx) - bx0) | ((unsigned)(cell(hhi[w].x, c->cnx) - bx0) << 3)
+                                 | ((unsigned)(cell(hlo[w].y, c->cny) - by0) << 6) | ((unsigned)(cell(hhi[w].y, c->cny) - by0) << 9)
+                                 | ((unsigned)(cell(hlo[w].z, c->cnz) - bz0) << 12) | ((unsigned)(cell(hhi[w].z, c->cnz) - bz0) << 15);
             float tf; memcpy(&tf, &tight, 4);
             list.push_back(make_float4(hlo[w].x, hlo[w].y, hlo[w].z, pf));
             list.push_back(make_float4(hhi[w].x, hhi[w].y, hhi[w].z, tf));

@@ -4,11 +4,11 @@ import os
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
-from bench_repo_clouds import load_pair  # noqa: E402
+import numpy as np  # noqa: E402
 from fast_go_icp_b200 import capi, driver  # noqa: E402
 
-model, data, _, _ = load_pair("dragon")
+z = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "dragon_full.npz"))
+model, data = z["model"], z["data"]
 g = driver.FastGoICP(model, data, 0.005, 1e-4, flags=capi.BUILD_PACKED)
 g.run()
 print("run_ms", g.stats["run_ms"], "icp ms", g.stats["ms_icp"], "iters", g.stats["icp_iters"])
